@@ -1,0 +1,449 @@
+#!/usr/bin/env python
+"""bench.py — rasterizer forward+backward views/s (BASELINE.json metric) on N GPUs of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+One "step" = one view of SURVEY §8(d): SH fwd -> project fwd -> bin/sort -> blend fwd (rgb + alpha) ->
+[fixed synthetic upstream gradients] -> blend bwd -> SH bwd -> project bwd [-> NCCL all-reduce of the
+59 N parameter-gradient floats when N_gpus > 1].  Workload at N=1: cfg2 = 1 M Gaussians, 1920x1080,
+SH degree 3 (BASELINE.json configs[1]).  Multi-GPU is view-parallel (weak scaling): every rank renders
+its own camera of the same replicated scene.
+
+Prints ONE JSON line (rank 0).  `value` = device-timed views/s with everything resident in HBM, through
+the C ABI (`rasterizer.cuda` -> libgsr_b200.so).  `e2e` = views/s through the public autograd API
+(`rasterizer.project_gaussians / spherical_harmonics / rasterize_gaussians`) with the per-view inputs
+(camera matrices, upstream image gradients) copied from pinned host memory and the rendered image + alpha
+read back to the host inside the timed region.  `roofline` is for the blend-adjoint kernel (the dominant
+one).  `cpu_baseline` = the CPU oracle (a port; oracle/) on the host cores.  `--impl reference` times the
+reference path's CPU implementation (the oracle port: the reference's own CPU code is Python and cannot
+travel to the GPU box) on all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "gaussian-splatting-toolkit_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "rasterizer fwd+bwd views/sec @1080p, 1M Gaussians"
+UNIT = "views/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg4"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget-s", type=float, default=200.0, help="wall-clock bound of the reference arm")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm_sorted = sorted(sm)
+        return {"sm_mhz": sm_sorted[len(sm_sorted) // 2], "sm_max_mhz": max(smax), "power_w_max": max(power),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------------
+def algorithmic_bytes(N, M, P, T):
+    """SURVEY §8(d) per-view algorithmic bytes (FP32, each tensor touched once)."""
+    return {
+        "sh_fwd": 216 * N, "project_fwd": 100 * N, "cumsum": 8 * N, "key_emit": 20 * N + 12 * M, "sort": 24 * M,
+        "bin_edges": 8 * M + 8 * T, "blend_fwd": 40 * M + 20 * P + 8 * T, "blend_bwd": 40 * M + 24 * P + 8 * T + 36 * N,
+        "project_bwd": 152 * N, "sh_bwd": 216 * N, "total": 748 * N + 124 * M + 44 * P + 24 * T,
+    }
+
+
+class ResidentView:
+    """One view through the C ABI with every input resident in HBM (the `value` leg).  Stage boundaries carry
+    CUDA events (on torch's current stream = the launching stream) for the per-kernel breakdown."""
+
+    STAGES = ["sh_fwd", "project_fwd", "binning", "blend_fwd", "blend_bwd", "sh_bwd", "project_bwd"]
+
+    def __init__(self, s, flat_grads=None):
+        import torch
+        from rasterizer import cuda as C
+
+        self.torch, self.C, self.s = torch, C, s
+        self.N = s["means3d"].shape[0]
+        H, W, bw = s["img_height"], s["img_width"], s["block_width"]
+        self.tb = ((W + bw - 1) // bw, (H + bw - 1) // bw, 1)
+        self.degree = {1: 0, 4: 1, 9: 2, 16: 3, 25: 4}[s["sh_coeffs"].shape[1]]
+        self.viewdirs = (s["means3d"] - s["cam_pos"][None, :]).contiguous()
+        self.opac = s["opacities"].reshape(-1, 1).contiguous()
+        self.zeros_n = torch.zeros(self.N, device=s["means3d"].device)
+        self.pin_total = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.events = []
+        self.M = 0
+        self.flat = flat_grads
+
+    def _mark(self, rec):
+        if rec is not None:
+            e = self.torch.cuda.Event(enable_timing=True)
+            e.record()
+            rec.append(e)
+
+    def step(self, record=False):
+        torch, C, s = self.torch, self.C, self.s
+        H, W, bw, N = s["img_height"], s["img_width"], s["block_width"], self.N
+        rec = [] if record else None
+        self._mark(rec)
+        rgb_sh = C.compute_sh_forward(N, self.degree, s["degrees_to_use"], self.viewdirs, s["sh_coeffs"])
+        colors = torch.clamp(rgb_sh + 0.5, min=0.0)
+        self._mark(rec)
+        cov3d, xys, depths, radii, conics, comp, nth = C.project_gaussians_forward(
+            N, s["means3d"], s["scales"], s["glob_scale"], s["quats"], s["viewmat"], s["projmat"], s["fx"], s["fy"],
+            s["cx"], s["cy"], H, W, bw, s["clip_thresh"])
+        self._mark(rec)
+        cum = C.cumsum_tiles_hit(nth, self.pin_total)
+        torch.cuda.current_stream().synchronize()
+        M = self.M = int(self.pin_total.item())
+        isect, gids = C.map_gaussian_to_intersects(N, M, xys, depths, radii, cum, self.tb, bw)
+        ks, vs = C.sort_intersects(isect, gids, self.tb[0] * self.tb[1])
+        bins = C.get_tile_bin_edges(M, ks, self.tb)
+        self._mark(rec)
+        img, fT, fi = C.rasterize_forward(self.tb, (bw, bw, 1), (W, H, 1), vs, bins, xys, conics, colors, self.opac,
+                                          s["background"])
+        alpha = 1 - fT
+        self._mark(rec)
+        v_xy, v_conic, v_colors, v_opacity = C.rasterize_backward(H, W, bw, vs, bins, xys, conics, colors, self.opac,
+                                                                  s["background"], fT, fi, s["v_out_img"],
+                                                                  s["v_out_alpha"])
+        self._mark(rec)
+        v_rgb_sh = torch.where(rgb_sh + 0.5 > 0, v_colors, torch.zeros_like(v_colors))
+        v_coeffs = C.compute_sh_backward(N, self.degree, s["degrees_to_use"], self.viewdirs, v_rgb_sh)
+        self._mark(rec)
+        _, _, v_mean, v_scale, v_quat = C.project_gaussians_backward(
+            N, s["means3d"], s["scales"], s["glob_scale"], s["quats"], s["viewmat"], s["projmat"], s["fx"], s["fy"],
+            s["cx"], s["cy"], H, W, cov3d, radii, conics, comp, v_xy, self.zeros_n, v_conic, self.zeros_n)
+        self._mark(rec)
+        if rec is not None:
+            self.events.append(rec)
+        return img, alpha, (v_coeffs, v_mean, v_scale, v_quat, v_opacity)
+
+    def stage_ms(self):
+        out = {k: 0.0 for k in self.STAGES}
+        for rec in self.events:
+            for i, k in enumerate(self.STAGES):
+                out[k] += rec[i].elapsed_time(rec[i + 1])
+        n = max(1, len(self.events))
+        return {k: v / n for k, v in out.items()}
+
+
+class PublicApiView:
+    """One view through the public autograd API with HOST buffers for the per-view inputs/outputs (`e2e`)."""
+
+    def __init__(self, s, scene_np):
+        import torch
+
+        self.torch, self.s = torch, s
+        dev = s["means3d"].device
+        self.means = s["means3d"].clone().requires_grad_(True)
+        self.scales = s["scales"].clone().requires_grad_(True)
+        self.quats = s["quats"].clone().requires_grad_(True)
+        self.coeffs = s["sh_coeffs"].clone().requires_grad_(True)
+        self.opac = s["opacities"].reshape(-1, 1).clone().requires_grad_(True)
+        pin = lambda a: torch.from_numpy(a).pin_memory()
+        self.h_viewmat, self.h_projmat = pin(scene_np["viewmat"]), pin(scene_np["projmat"])
+        self.h_vimg, self.h_valpha = pin(scene_np["v_out_img"]), pin(scene_np["v_out_alpha"])
+        H, W = s["img_height"], s["img_width"]
+        self.h_img = torch.empty((H, W, 3), dtype=torch.float32).pin_memory()
+        self.h_alpha = torch.empty((H, W), dtype=torch.float32).pin_memory()
+        self.d_viewmat = torch.empty_like(s["viewmat"]); self.d_projmat = torch.empty_like(s["projmat"])
+        self.d_vimg = torch.empty((H, W, 3), device=dev); self.d_valpha = torch.empty((H, W), device=dev)
+        self.h2d = sum(t.numel() * t.element_size() for t in (self.h_viewmat, self.h_projmat, self.h_vimg, self.h_valpha))
+        self.d2h = sum(t.numel() * t.element_size() for t in (self.h_img, self.h_alpha))
+
+    def step(self):
+        import rasterizer
+        from rasterizer.sh import spherical_harmonics
+
+        torch, s = self.torch, self.s
+        H, W, bw = s["img_height"], s["img_width"], s["block_width"]
+        self.d_viewmat.copy_(self.h_viewmat, non_blocking=True)
+        self.d_projmat.copy_(self.h_projmat, non_blocking=True)
+        self.d_vimg.copy_(self.h_vimg, non_blocking=True)
+        self.d_valpha.copy_(self.h_valpha, non_blocking=True)
+        for p in (self.means, self.scales, self.quats, self.coeffs, self.opac):
+            p.grad = None
+        xys, depths, radii, conics, comp, nth, cov3d = rasterizer.project_gaussians(
+            self.means, self.scales, s["glob_scale"], self.quats, self.d_viewmat, self.d_projmat, s["fx"], s["fy"],
+            s["cx"], s["cy"], H, W, bw, s["clip_thresh"])
+        viewdirs = self.means.detach() - s["cam_pos"][None, :]
+        rgbs = torch.clamp(spherical_harmonics(s["degrees_to_use"], viewdirs, self.coeffs) + 0.5, min=0.0)
+        img, alpha = rasterizer.rasterize_gaussians(xys, depths, radii, conics, nth, rgbs, self.opac, H, W, bw,
+                                                    background=s["background"], return_alpha=True)
+        self.h_img.copy_(img.detach(), non_blocking=True)
+        self.h_alpha.copy_(alpha.detach(), non_blocking=True)
+        torch.autograd.backward([img, alpha], [self.d_vimg, self.d_valpha])
+        return (self.coeffs.grad, self.means.grad, self.scales.grad, self.quats.grad, self.opac.grad)
+
+
+def timed_loop(torch, dist, world, fn, steps, warmup):
+    """W untimed + exactly K timed steps, barrier + synchronize on both sides, CUDA events, max over ranks."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item())
+
+
+def make_scene_for_rank(workload, rank):
+    from rasterizer.synthetic import look_at_viewmat, make_config_scene
+
+    viewmat = None if rank == 0 else look_at_viewmat(yaw_deg=45.0 * rank)  # cfg5: yaw = rank * 45 deg
+    return make_config_scene(workload, seed=0, viewmat=viewmat)
+
+
+def cpu_leg(scene_np, n_views_budget_s, steps=None, warmup=0):
+    """Times the CPU oracle (port of the reference path) on all host threads.  Each step is a bounded sample:
+    the whole view when it fits the budget, else a band of tile rows (fraction f of the image) — SH /
+    projection / binning always run on all N Gaussians.  Returns (views_per_s, description, cores, ms_per_step)."""
+    from oracle import oracle as orc
+
+    orc.build()
+    cores = orc.num_threads()
+    s = scene_np
+    t0 = time.perf_counter()
+    orc.render_view(s, s["v_out_img"], s["v_out_alpha"])  # one untimed full view: page-in + calibration
+    t_full = time.perf_counter() - t0
+    if steps is None:
+        steps = max(1, min(3, int(n_views_budget_s / max(t_full, 1e-3)) - 1))
+        warmup = 0
+    total_steps = steps + warmup
+    bw, H = s["block_width"], s["img_height"]
+    tiles_y = (H + bw - 1) // bw
+    frac = min(1.0, n_views_budget_s / (total_steps * t_full))
+    rows = max(1, int(round(frac * tiles_y)))
+    r0 = (tiles_y - rows) // 2
+    tile_rows = (r0, r0 + rows)
+    frac = rows / tiles_y
+    for _ in range(warmup):
+        orc.render_view(s, s["v_out_img"], s["v_out_alpha"], tile_rows=tile_rows)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        orc.render_view(s, s["v_out_img"], s["v_out_alpha"], tile_rows=tile_rows)
+    dt = time.perf_counter() - t0
+    views_per_s = steps * frac / dt
+    desc = (f"{steps} step(s), each the full per-Gaussian work (SH, projection, binning of all {s['means3d'].shape[0]} "
+            f"Gaussians) + blend fwd/bwd of {rows}/{tiles_y} tile rows ({frac:.3f} of a view), scaled to whole views; "
+            f"CPU oracle (C + OpenMP port of the reference CUDA path), {cores} threads")
+    return views_per_s, desc, cores, 1e3 * dt / steps
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        # rank 0 alone times the CPU path; the other ranks leave immediately
+        if rank != 0:
+            return
+        scene_np = make_scene_for_rank(args.workload, 0)
+        v, desc, cores, ms = cpu_leg(scene_np, args.cpu_budget_s, steps=args.steps, warmup=args.warmup)
+        line = {
+            "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: seeded synthetic scene of SURVEY 8(d), CPU path"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from rasterizer import _lib
+    from rasterizer.synthetic import scene_to_torch
+
+    _lib.load()  # fail loudly if libgsr_b200.so is missing
+    scene_np = make_scene_for_rank(args.workload, rank)
+    s = scene_to_torch(scene_np, torch.device("cuda", local_rank))
+    N = s["means3d"].shape[0]
+    H, W, bw = s["img_height"], s["img_width"], s["block_width"]
+    P, T = H * W, ((W + bw - 1) // bw) * ((H + bw - 1) // bw)
+
+    # flat gradient bucket for the view-parallel all-reduce: 48 (SH) + 3 + 3 + 4 + 1 = 59 floats / Gaussian
+    flat = torch.zeros(59 * N, device=s["means3d"].device) if world > 1 else None
+
+    def allreduce(grads):
+        if world == 1:
+            return
+        off = 0
+        for g in grads:
+            n = g.numel()
+            flat[off:off + n].copy_(g.reshape(-1))
+            off += n
+        dist.all_reduce(flat)
+
+    rv = ResidentView(s)
+    recording = {"on": False}
+
+    def resident_step():
+        _, _, grads = rv.step(record=recording["on"])
+        allreduce(grads)
+
+    sampler = ClockSampler(local_rank)
+    # warm-up outside, then the timed region with stage events
+    for _ in range(args.warmup):
+        resident_step()
+    recording["on"] = True
+    sampler.start()
+    ms_total = timed_loop(torch, dist, world, resident_step, args.steps, 0)
+    clocks = sampler.stop()
+    recording["on"] = False
+    ms_per_step = ms_total / args.steps
+    value = world * args.steps / (ms_total * 1e-3)
+    stages = rv.stage_ms()
+    M = rv.M
+    visible = None
+
+    # e2e through the public API with host buffers
+    pv = PublicApiView(s, scene_np)
+
+    def e2e_step():
+        grads = pv.step()
+        allreduce(grads)
+
+    e2e_ms = timed_loop(torch, dist, world, e2e_step, args.steps, args.warmup)
+    e2e_value = world * args.steps / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        ab = algorithmic_bytes(N, M, P, T)
+        t_bwd = stages["blend_bwd"] * 1e-3
+        achieved = ab["blend_bwd"] / t_bwd / 1e9
+        roofline = {
+            "kernel": "blend_backward_kernel (gsr_rasterize_backward)", "bound": "hbm", "achieved": achieved, "peak": peak,
+            "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": ab["blend_bwd"], "avg_launch_ms": stages["blend_bwd"],
+            "note": "blend kernels are FP32-issue bound (>=100 flop/B); a low HBM fraction is expected (SURVEY 8d)",
+            "blend_fwd": {"achieved": ab["blend_fwd"] / (stages["blend_fwd"] * 1e-3) / 1e9, "avg_launch_ms": stages["blend_fwd"],
+                          "algorithmic_bytes_per_launch": ab["blend_fwd"]},
+            "whole_view": {"achieved": ab["total"] / (ms_per_step * 1e-3) / 1e9, "algorithmic_bytes": ab["total"]},
+        }
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {N} Gaussians, {W}x{H}, SH degree {s['sh_degree']}, fwd+bwd, "
+                                   f"block_width {bw}, seeded scene of SURVEY 8(d)",
+                       "num_intersects": M, "pixels": P, "tiles": T, "parallelism": f"view-parallel x{world}",
+                       "l2_policy": "inputs larger than L2 (192 MB SH coefficients + 192 MB SH gradients per view; "
+                                    "no explicit flush)"},
+            "stages_ms": stages,
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": pv.h2d,
+                    "d2h_bytes_per_step": pv.d2h,
+                    "api": "rasterizer.project_gaussians + spherical_harmonics + rasterize_gaussians + autograd backward"},
+            "gpu_launches": 8 * args.steps,
+            "gpu_launches_note": "own kernels per step: sh_fwd, project_fwd, map_intersects, tile_bin_edges, blend_fwd, "
+                                 "blend_bwd, sh_bwd, project_bwd (+ CUB scan/sort and cudaMemset not counted) ; counted for the "
+                                 "resident leg only",
+            "clocks": clocks, "roofline": roofline,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            v, desc, cores, _ = cpu_leg(scene_np, 25.0)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

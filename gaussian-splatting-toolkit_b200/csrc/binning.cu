@@ -1,0 +1,162 @@
+// binning.cu — tile binning for sm_100a: intersection offsets (scan), key emission, radix sort, bin edges.
+//
+// Replaces, in the reference's forward orchestration (rasterizer/rasterize.py:92-183 -> rasterizer/utils.py):
+//   torch.cumsum(int32) + .item()          utils.py:123-124      -> gsr_cumsum_tiles_hit
+//   map_gaussian_to_intersects kernel      csrc/forward.cu:94-127 -> gsr_map_gaussian_to_intersects
+//   torch.sort(int64) + torch.gather       utils.py:179-180       -> gsr_sort_intersects
+//   get_tile_bin_edges kernel              csrc/forward.cu:132-154 -> gsr_get_tile_bin_edges
+//
+// All of it is HBM-bound integer work.  The sort keeps the reference's key format ((tile << 32) | depth bits,
+// int64) so sorted keys are bit-identical, but only radix-sorts the bits that can be non-zero
+// (32 + ceil(log2(num_tiles))) and carries the 4-byte Gaussian id as the value instead of producing an
+// 8-byte permutation and gathering through it.
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include "common.cuh"
+
+namespace gsr {
+
+constexpr int BIN_THREADS = 256;
+
+__global__ void __launch_bounds__(BIN_THREADS)
+map_intersects_kernel(int n, const float2 *__restrict__ xys, const float *__restrict__ depths,
+                      const int *__restrict__ radii, const int *__restrict__ cum_tiles_hit, int tiles_x,
+                      int tiles_y, int block_width, int64_t *__restrict__ isect_ids,
+                      int *__restrict__ gaussian_ids) {
+  const int idx = blockIdx.x * BIN_THREADS + threadIdx.x;
+  if (idx >= n) return;
+  const int r = radii[idx];
+  if (r <= 0) return;
+  const float2 c = xys[idx];
+  int x0, y0, x1, y1;
+  tile_bbox(c.x, c.y, (float)r, tiles_x, tiles_y, block_width, x0, y0, x1, y1);
+  int cur = (idx == 0) ? 0 : cum_tiles_hit[idx - 1];
+  const int64_t depth_id = (int64_t)__float_as_int(depths[idx]);  // sign-extending, as the reference
+  for (int i = y0; i < y1; ++i) {
+    for (int j = x0; j < x1; ++j) {
+      const int64_t tile_id = (int64_t)(i * tiles_x + j);
+      isect_ids[cur] = (tile_id << 32) | depth_id;
+      gaussian_ids[cur] = idx;
+      ++cur;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(BIN_THREADS)
+tile_bin_edges_kernel(int m, const int64_t *__restrict__ keys, int2 *__restrict__ tile_bins) {
+  const int idx = blockIdx.x * BIN_THREADS + threadIdx.x;
+  if (idx >= m) return;
+  const int cur = (int)(keys[idx] >> 32);
+  if (idx == 0) tile_bins[cur].x = 0;
+  if (idx == m - 1) tile_bins[cur].y = m;
+  if (idx == 0) return;
+  const int prev = (int)(keys[idx - 1] >> 32);
+  if (prev != cur) {
+    tile_bins[prev].y = idx;
+    tile_bins[cur].x = idx;
+  }
+}
+
+static inline int key_end_bit(int num_tiles) {
+  int bits = 0;
+  while ((1ll << bits) < (long long)num_tiles) ++bits;
+  return 32 + (bits < 1 ? 1 : bits);
+}
+
+}  // namespace gsr
+
+extern "C" {
+
+GSR_API size_t gsr_cumsum_workspace_bytes(int num_points) {
+  size_t bytes = 0;
+  cub::DeviceScan::InclusiveSum(nullptr, bytes, (const int *)nullptr, (int *)nullptr, num_points > 0 ? num_points : 1);
+  return bytes + 256;
+}
+
+GSR_API int gsr_cumsum_tiles_hit(int num_points, const int32_t *num_tiles_hit, int32_t *cum_tiles_hit,
+                                 int32_t *total_host_pinned, void *workspace, size_t workspace_bytes,
+                                 void *stream) {
+  using namespace gsr;
+  GSR_REQUIRE(num_points >= 0, GSR_ERR_INVALID_ARGUMENT, "cumsum_tiles_hit: num_points < 0");
+  if (num_points == 0) {
+    if (total_host_pinned) *total_host_pinned = 0;
+    return GSR_OK;
+  }
+  GSR_REQUIRE(num_tiles_hit && cum_tiles_hit && workspace, GSR_ERR_INVALID_ARGUMENT, "cumsum_tiles_hit: null pointer");
+  size_t need = 0;
+  cub::DeviceScan::InclusiveSum(nullptr, need, num_tiles_hit, cum_tiles_hit, num_points);
+  GSR_REQUIRE(workspace_bytes >= need, GSR_ERR_WORKSPACE, "cumsum_tiles_hit: workspace %zu < %zu bytes",
+              workspace_bytes, need);
+  GSR_CUDA(cub::DeviceScan::InclusiveSum(workspace, need, num_tiles_hit, cum_tiles_hit, num_points,
+                                         (cudaStream_t)stream));
+  if (total_host_pinned)
+    GSR_CUDA(cudaMemcpyAsync(total_host_pinned, cum_tiles_hit + (num_points - 1), sizeof(int32_t),
+                             cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return GSR_OK;
+}
+
+GSR_API int gsr_map_gaussian_to_intersects(int num_points, int num_intersects, const float *xys,
+                                           const float *depths, const int32_t *radii,
+                                           const int32_t *cum_tiles_hit, unsigned tiles_x, unsigned tiles_y,
+                                           unsigned block_width, int64_t *isect_ids, int32_t *gaussian_ids,
+                                           void *stream) {
+  using namespace gsr;
+  GSR_REQUIRE(num_points >= 0 && num_intersects >= 0, GSR_ERR_INVALID_ARGUMENT, "map_gaussian_to_intersects: negative size");
+  GSR_REQUIRE(block_width > 1 && block_width <= 16, GSR_ERR_INVALID_ARGUMENT,
+              "block_width must be between 2 and 16 (got %u)", block_width);
+  if (num_points == 0 || num_intersects == 0) return GSR_OK;
+  GSR_REQUIRE(xys && depths && radii && cum_tiles_hit && isect_ids && gaussian_ids, GSR_ERR_INVALID_ARGUMENT,
+              "map_gaussian_to_intersects: null pointer");
+  GSR_REQUIRE((uintptr_t)xys % 8 == 0, GSR_ERR_INVALID_ARGUMENT, "map_gaussian_to_intersects: xys must be 8-byte aligned");
+  map_intersects_kernel<<<cdiv(num_points, BIN_THREADS), BIN_THREADS, 0, (cudaStream_t)stream>>>(
+      num_points, reinterpret_cast<const float2 *>(xys), depths, radii, cum_tiles_hit, (int)tiles_x, (int)tiles_y,
+      (int)block_width, isect_ids, gaussian_ids);
+  GSR_CHECK_LAUNCH("map_intersects_kernel");
+  return GSR_OK;
+}
+
+GSR_API size_t gsr_sort_workspace_bytes(int num_intersects) {
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint64_t *)nullptr, (uint64_t *)nullptr,
+                                  (const int *)nullptr, (int *)nullptr, num_intersects > 0 ? num_intersects : 1, 0, 64);
+  return bytes + 256;
+}
+
+GSR_API int gsr_sort_intersects(int num_intersects, int num_tiles, const int64_t *isect_ids,
+                                const int32_t *gaussian_ids, int64_t *isect_ids_sorted,
+                                int32_t *gaussian_ids_sorted, void *workspace, size_t workspace_bytes,
+                                void *stream) {
+  using namespace gsr;
+  GSR_REQUIRE(num_intersects >= 0 && num_tiles > 0, GSR_ERR_INVALID_ARGUMENT, "sort_intersects: bad sizes");
+  if (num_intersects == 0) return GSR_OK;
+  GSR_REQUIRE(isect_ids && gaussian_ids && isect_ids_sorted && gaussian_ids_sorted && workspace,
+              GSR_ERR_INVALID_ARGUMENT, "sort_intersects: null pointer");
+  const int end_bit = key_end_bit(num_tiles);
+  size_t need = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, need, (const uint64_t *)isect_ids, (uint64_t *)isect_ids_sorted,
+                                  gaussian_ids, gaussian_ids_sorted, num_intersects, 0, end_bit);
+  GSR_REQUIRE(workspace_bytes >= need, GSR_ERR_WORKSPACE, "sort_intersects: workspace %zu < %zu bytes",
+              workspace_bytes, need);
+  GSR_CUDA(cub::DeviceRadixSort::SortPairs(workspace, need, (const uint64_t *)isect_ids,
+                                           (uint64_t *)isect_ids_sorted, gaussian_ids, gaussian_ids_sorted,
+                                           num_intersects, 0, end_bit, (cudaStream_t)stream));
+  return GSR_OK;
+}
+
+GSR_API int gsr_get_tile_bin_edges(int num_intersects, const int64_t *isect_ids_sorted, int num_tiles,
+                                   int32_t *tile_bins, void *stream) {
+  using namespace gsr;
+  GSR_REQUIRE(num_intersects >= 0 && num_tiles >= 0, GSR_ERR_INVALID_ARGUMENT, "get_tile_bin_edges: negative size");
+  if (num_tiles == 0) return GSR_OK;
+  GSR_REQUIRE(tile_bins, GSR_ERR_INVALID_ARGUMENT, "get_tile_bin_edges: null pointer");
+  GSR_REQUIRE((uintptr_t)tile_bins % 8 == 0, GSR_ERR_INVALID_ARGUMENT, "get_tile_bin_edges: tile_bins must be 8-byte aligned");
+  GSR_CUDA(cudaMemsetAsync(tile_bins, 0, sizeof(int32_t) * 2 * (size_t)num_tiles, (cudaStream_t)stream));
+  if (num_intersects == 0) return GSR_OK;
+  GSR_REQUIRE(isect_ids_sorted, GSR_ERR_INVALID_ARGUMENT, "get_tile_bin_edges: null pointer");
+  tile_bin_edges_kernel<<<cdiv(num_intersects, BIN_THREADS), BIN_THREADS, 0, (cudaStream_t)stream>>>(
+      num_intersects, isect_ids_sorted, reinterpret_cast<int2 *>(tile_bins));
+  GSR_CHECK_LAUNCH("tile_bin_edges_kernel");
+  return GSR_OK;
+}
+}

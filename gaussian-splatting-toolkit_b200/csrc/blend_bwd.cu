@@ -1,0 +1,268 @@
+// blend_bwd.cu — adjoint of the per-tile alpha compositing (3 channels, FP32) for sm_100a.
+//
+// Replaces rasterize_backward_kernel (reference csrc/backward.cu:133-303, launched from
+// bindings.cu:471-528).  Per pixel it replays the contributors back-to-front from (T_final, final_idx)
+// exactly as the reference does (alpha clamp 0.99, clamp derivative ignored, T *= 1/(1-alpha)).
+//
+// What is different from the reference kernel:
+//   * only the batches at or before max(final_idx) of the CTA are staged at all (the reference stages every
+//     batch of the tile and skips inside);
+//   * double-buffered shared-memory ring of packed records with register prefetch, one barrier per batch;
+//   * warp = 8x4 pixel sub-tile + the same conservative warp-uniform ellipse reject as the forward, so most
+//     (warp, Gaussian) pairs never reach the reduction;
+//   * the 9 per-Gaussian partial sums are reduced across the warp with a transposing butterfly
+//     (8 values in 4+2+1+1+1 = 9 shuffles, + 5 for the ninth) instead of 9 x 5 = 45 shuffles
+//     (cg::reduce per value, backward.cu:275-278), and the nine totals end up in nine DIFFERENT lanes, so the
+//     global accumulation is ONE predicated RED instruction per (warp, Gaussian) instead of nine serial
+//     atomicAdds issued by lane 0 (backward.cu:279-300);
+//   * outputs are zero-filled by this call (cudaMemsetAsync) rather than by torch::zeros in the caller.
+#include "common.cuh"
+
+namespace gsr {
+
+// defined in blend_fwd.cu (same translation-unit-local copies kept identical on purpose)
+__device__ __forceinline__ void alpha_extents_b(float a, float b, float c, float opac, float &ex, float &ey) {
+  const float det = a * c - b * b;
+  const float tau2 = 2.f * __logf(255.f * opac);
+  if (!(tau2 >= 0.f)) {
+    ex = (opac == opac) ? -1e30f : __int_as_float(0x7fc00000);
+    ey = ex;
+    return;
+  }
+  ex = sqrtf(tau2 * c / det) * 1.001f + 0.01f;
+  ey = sqrtf(tau2 * a / det) * 1.001f + 0.01f;
+}
+
+// Sum 8 per-lane values across the warp.  On return, lane L with (L & 3) == 0 holds in v[0] the total of
+// value number ((L>>4)&1)*4 + ((L>>3)&1)*2 + ((L>>2)&1).
+__device__ __forceinline__ float warp_transpose_reduce8(float v[8], int lane) {
+  const unsigned full = 0xffffffffu;
+  {
+    const bool hi = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float send = hi ? v[i] : v[i + 4];
+      const float keep = hi ? v[i + 4] : v[i];
+      v[i] = keep + __shfl_xor_sync(full, send, 16);
+    }
+  }
+  {
+    const bool hi = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float send = hi ? v[i] : v[i + 2];
+      const float keep = hi ? v[i + 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(full, send, 8);
+    }
+  }
+  {
+    const bool hi = lane & 4;
+    const float send = hi ? v[0] : v[1];
+    const float keep = hi ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(full, send, 4);
+  }
+  v[0] += __shfl_xor_sync(full, v[0], 2);
+  v[0] += __shfl_xor_sync(full, v[0], 1);
+  return v[0];
+}
+
+__device__ __forceinline__ float warp_sum(float x) {
+  const unsigned full = 0xffffffffu;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(full, x, o);
+  return x;
+}
+
+template <int MAX_THREADS>
+__global__ void __launch_bounds__(MAX_THREADS)
+blend_backward_kernel(int tiles_x, int img_w, int img_h, int block_width,
+                      const int *__restrict__ gaussian_ids_sorted, const int2 *__restrict__ tile_bins,
+                      const float2 *__restrict__ xys, const float *__restrict__ conics,
+                      const float *__restrict__ colors, const float *__restrict__ opacities,
+                      const float *__restrict__ background, const float *__restrict__ final_Ts,
+                      const int *__restrict__ final_idx, const float *__restrict__ v_output,
+                      const float *__restrict__ v_output_alpha, float *__restrict__ v_xy,
+                      float *__restrict__ v_conic, float *__restrict__ v_colors,
+                      float *__restrict__ v_opacity) {
+  __shared__ float4 s_rec[2][3][MAX_THREADS];
+  __shared__ int s_warp_max[MAX_THREADS / 32];
+
+  const unsigned full = 0xffffffffu;
+  const int tile_x = blockIdx.x, tile_y = blockIdx.y;
+  const int tile_id = tile_y * tiles_x + tile_x;
+  const int tr = threadIdx.x, nthreads = blockDim.x, lane = tr & 31, warp = tr >> 5;
+
+  // thread -> pixel (same mapping as the forward kernel)
+  int lx, ly;
+  if (block_width == 16) {
+    lx = ((warp & 1) << 3) + (lane & 7);
+    ly = ((warp >> 1) << 2) + (lane >> 3);
+  } else {
+    lx = tr % block_width;
+    ly = tr / block_width;
+  }
+  const int ipx = tile_x * block_width + lx, ipy = tile_y * block_width + ly;
+  const bool inside = (ly < block_width) && (ipx < img_w) && (ipy < img_h);
+  const float px = (float)ipx, py = (float)ipy;
+  const int pix = inside ? (ipy * img_w + ipx) : 0;
+
+  const int wx0 = __reduce_min_sync(full, inside ? ipx : 0x7fffffff);
+  const int wx1 = __reduce_max_sync(full, inside ? ipx : -0x7fffffff);
+  const int wy0 = __reduce_min_sync(full, inside ? ipy : 0x7fffffff);
+  const int wy1 = __reduce_max_sync(full, inside ? ipy : -0x7fffffff);
+  const float fx0 = (float)wx0, fx1 = (float)wx1, fy0 = (float)wy0, fy1 = (float)wy1;
+
+  const int2 range = tile_bins[tile_id];
+
+  const float T_final = inside ? final_Ts[pix] : 1.f;
+  float T = T_final;
+  float3 buffer = make_float3(0.f, 0.f, 0.f);
+  // reference: bin_final = inside ? final_index : 0 (backward.cu:168); -1 for outside threads is
+  // equivalent because they are never valid
+  const int bin_final = inside ? final_idx[pix] : -1;
+  float3 v_out = make_float3(0.f, 0.f, 0.f);
+  float v_out_alpha = 0.f;
+  if (inside) {
+    v_out = make_float3(v_output[3 * (size_t)pix], v_output[3 * (size_t)pix + 1], v_output[3 * (size_t)pix + 2]);
+    v_out_alpha = v_output_alpha[pix];
+  }
+  const float bg_dot = background[0] * v_out.x + background[1] * v_out.y + background[2] * v_out.z;
+
+  const int warp_bin_final = __reduce_max_sync(full, bin_final);
+  if (lane == 0) s_warp_max[warp] = warp_bin_final;
+  __syncthreads();
+  int cta_bin_final = -1;
+  for (int w = 0; w < (nthreads >> 5); ++w) cta_bin_final = max(cta_bin_final, s_warp_max[w]);
+
+  // process sorted indices [range.x, end) back to front
+  const int end = min(range.y, cta_bin_final + 1);
+  const int count = end - range.x;
+  if (count <= 0) return;  // uniform across the CTA
+  const int num_batches = (count + nthreads - 1) / nthreads;
+
+  // per-lane destination of the reduced totals: lanes 0,4,..,28 own values 0..7, lane 1 owns value 8
+  //   value 0..2 -> v_colors, 3..5 -> v_conic, 6..7 -> v_xy, 8 -> v_opacity
+  float *dst_base = nullptr;
+  int dst_stride = 0;
+  {
+    const int vi = (lane & 3) == 0 ? (((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1))
+                                   : (lane == 1 ? 8 : -1);
+    if (vi >= 0 && vi < 3) { dst_base = v_colors + vi; dst_stride = 3; }
+    else if (vi >= 3 && vi < 6) { dst_base = v_conic + (vi - 3); dst_stride = 3; }
+    else if (vi >= 6 && vi < 8) { dst_base = v_xy + (vi - 6); dst_stride = 2; }
+    else if (vi == 8) { dst_base = v_opacity; dst_stride = 1; }
+  }
+
+  float4 r0, r1, r2;
+  auto fetch = [&](int idx) {
+    if (idx >= range.x) {
+      const int g = gaussian_ids_sorted[idx];
+      const float2 xy = xys[g];
+      const float opac = opacities[g];
+      const float a = conics[3 * (size_t)g], b = conics[3 * (size_t)g + 1], c = conics[3 * (size_t)g + 2];
+      float ex, ey;
+      alpha_extents_b(a, b, c, opac, ex, ey);
+      r0 = make_float4(xy.x, xy.y, opac, ex);
+      r1 = make_float4(a, b, c, ey);
+      r2 = make_float4(colors[3 * (size_t)g], colors[3 * (size_t)g + 1], colors[3 * (size_t)g + 2], __int_as_float(g));
+    }
+  };
+  fetch(end - 1 - tr);
+
+  for (int b = 0; b < num_batches; ++b) {
+    const int buf = b & 1;
+    const int batch_end = end - 1 - nthreads * b;  // sorted index held by slot 0
+    if (batch_end - tr >= range.x) {
+      s_rec[buf][0][tr] = r0;
+      s_rec[buf][1][tr] = r1;
+      s_rec[buf][2][tr] = r2;
+    }
+    __syncthreads();
+    if (b + 1 < num_batches) fetch(batch_end - nthreads - tr);
+
+    const int batch_size = min(nthreads, batch_end + 1 - range.x);
+    for (int t = max(0, batch_end - warp_bin_final); t < batch_size; ++t) {
+      const float4 q0 = s_rec[buf][0][t];
+      const float4 q1 = s_rec[buf][1][t];
+      if (q0.x + q0.w < fx0 || q0.x - q0.w > fx1 || q0.y + q1.w < fy0 || q0.y - q1.w > fy1) continue;
+      const float dx = q0.x - px, dy = q0.y - py;
+      const float sigma = 0.5f * (q1.x * dx * dx + q1.z * dy * dy) + q1.y * dx * dy;
+      const float vis = __expf(-sigma);
+      const float opac = q0.z;
+      const float alpha = fminf(0.99f, opac * vis);
+      const bool valid = inside && (batch_end - t <= bin_final) && !(sigma < 0.f || alpha < 1.f / 255.f);
+      if (!__any_sync(full, valid)) continue;
+
+      float v[8];
+      float v_opac_l = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = 0.f;
+      const float4 q2 = s_rec[buf][2][t];
+      if (valid) {
+        const float ra = 1.f / (1.f - alpha);
+        T *= ra;
+        const float fac = alpha * T;
+        v[0] = fac * v_out.x;
+        v[1] = fac * v_out.y;
+        v[2] = fac * v_out.z;
+        float v_alpha = 0.f;
+        v_alpha += (q2.x * T - buffer.x * ra) * v_out.x;
+        v_alpha += (q2.y * T - buffer.y * ra) * v_out.y;
+        v_alpha += (q2.z * T - buffer.z * ra) * v_out.z;
+        v_alpha += T_final * ra * v_out_alpha;
+        v_alpha += -T_final * ra * bg_dot;
+        buffer.x += q2.x * fac;
+        buffer.y += q2.y * fac;
+        buffer.z += q2.z * fac;
+        const float v_sigma = -opac * vis * v_alpha;
+        v[3] = 0.5f * v_sigma * dx * dx;
+        v[4] = v_sigma * dx * dy;
+        v[5] = 0.5f * v_sigma * dy * dy;
+        v[6] = v_sigma * (q1.x * dx + q1.y * dy);
+        v[7] = v_sigma * (q1.y * dx + q1.z * dy);
+        v_opac_l = vis * v_alpha;
+      }
+      const float tot8 = warp_transpose_reduce8(v, lane);
+      const float tot_op = warp_sum(v_opac_l);
+      if (dst_base != nullptr) {
+        const int g = __float_as_int(q2.w);
+        atomicAdd(dst_base + (size_t)g * dst_stride, lane == 1 ? tot_op : tot8);
+      }
+    }
+  }
+}
+
+}  // namespace gsr
+
+extern "C" GSR_API int gsr_rasterize_backward(unsigned img_height, unsigned img_width, unsigned block_width,
+                                              int num_points, const int32_t *gaussian_ids_sorted,
+                                              const int32_t *tile_bins, const float *xys, const float *conics,
+                                              const float *colors, const float *opacities,
+                                              const float *background, const float *final_Ts,
+                                              const int32_t *final_idx, const float *v_output,
+                                              const float *v_output_alpha, float *v_xy, float *v_conic,
+                                              float *v_colors, float *v_opacity, void *stream) {
+  using namespace gsr;
+  GSR_REQUIRE(block_width > 1 && block_width <= 16, GSR_ERR_INVALID_ARGUMENT,
+              "block_width must be between 2 and 16 (got %u)", block_width);
+  GSR_REQUIRE(img_height > 0 && img_width > 0 && num_points >= 0, GSR_ERR_INVALID_ARGUMENT, "rasterize_backward: bad sizes");
+  if (num_points == 0) return GSR_OK;
+  GSR_REQUIRE(gaussian_ids_sorted && tile_bins && xys && conics && colors && opacities && background && final_Ts &&
+                  final_idx && v_output && v_output_alpha && v_xy && v_conic && v_colors && v_opacity,
+              GSR_ERR_INVALID_ARGUMENT, "rasterize_backward: null pointer");
+  GSR_REQUIRE((uintptr_t)xys % 8 == 0 && (uintptr_t)tile_bins % 8 == 0, GSR_ERR_INVALID_ARGUMENT,
+              "rasterize_backward: xys / tile_bins must be 8-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  GSR_CUDA(cudaMemsetAsync(v_xy, 0, sizeof(float) * 2 * (size_t)num_points, st));
+  GSR_CUDA(cudaMemsetAsync(v_conic, 0, sizeof(float) * 3 * (size_t)num_points, st));
+  GSR_CUDA(cudaMemsetAsync(v_colors, 0, sizeof(float) * 3 * (size_t)num_points, st));
+  GSR_CUDA(cudaMemsetAsync(v_opacity, 0, sizeof(float) * (size_t)num_points, st));
+  const dim3 grid(cdiv(img_width, block_width), cdiv(img_height, block_width), 1);
+  const unsigned threads = cdiv(block_width * block_width, 32) * 32;
+  blend_backward_kernel<256><<<grid, threads, 0, st>>>(
+      (int)grid.x, (int)img_width, (int)img_height, (int)block_width, gaussian_ids_sorted,
+      reinterpret_cast<const int2 *>(tile_bins), reinterpret_cast<const float2 *>(xys), conics, colors, opacities,
+      background, final_Ts, final_idx, v_output, v_output_alpha, v_xy, v_conic, v_colors, v_opacity);
+  GSR_CHECK_LAUNCH("blend_backward_kernel");
+  return GSR_OK;
+}

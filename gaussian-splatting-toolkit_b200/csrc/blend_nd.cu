@@ -1,0 +1,250 @@
+// blend_nd.cu — N-channel variants of the per-tile compositing and its adjoint for sm_100a.
+//
+// Replaces nd_rasterize_forward (reference csrc/forward.cu:159-276, bindings.cu:330-399) and
+// nd_rasterize_backward_kernel (csrc/backward.cu:23-131, bindings.cu:401-469), which the reference
+// selects whenever colors.shape[-1] != 3 (rasterizer/rasterize.py:145-148,213-216).  No model of the
+// toolkit uses C != 3, so these kernels favour exact reproduction of the reference's numerics over speed:
+//   * forward colour accumulators are binary16: acc = __hadd(acc, __float2half(colour * vis))
+//     (forward.cu:253-256);
+//   * the backward excludes the last contributor (idx < bin_final, backward.cu:64-65), keeps the running
+//     sum S in binary16 (backward.cu:46-50,105) and uses the 0.99 alpha clamp (backward.cu:78).
+// Structure: geometry records are staged through shared memory exactly like the 3-channel kernels;
+// colours (C floats per Gaussian) are read from global memory by the lanes that need them; the per-pixel
+// accumulators live in registers (templated on a channel bucket).
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace gsr {
+
+template <int CMAX>
+__global__ void __launch_bounds__(256)
+nd_blend_forward_kernel(int tiles_x, int img_w, int img_h, int block_width, int channels,
+                        const int *__restrict__ gaussian_ids_sorted, const int2 *__restrict__ tile_bins,
+                        const float2 *__restrict__ xys, const float *__restrict__ conics,
+                        const float *__restrict__ colors, const float *__restrict__ opacities,
+                        const float *__restrict__ background, float *__restrict__ out_img,
+                        float *__restrict__ final_Ts, int *__restrict__ final_idx) {
+  __shared__ float4 s_geo[2][256];  // {x, y, opacity, a} , {b, c, id, -}
+  const int tile_id = blockIdx.y * tiles_x + blockIdx.x;
+  const int tr = threadIdx.x, nthreads = blockDim.x;
+  const int lx = tr % block_width, ly = tr / block_width;
+  const int ipx = blockIdx.x * block_width + lx, ipy = blockIdx.y * block_width + ly;
+  const bool inside = (ly < block_width) && (ipx < img_w) && (ipy < img_h);
+  const float px = (float)ipx, py = (float)ipy;
+  bool done = !inside;
+  const int2 range = tile_bins[tile_id];
+  const int num_batches = (range.y - range.x + nthreads - 1) / nthreads;
+
+  __half acc[CMAX];
+#pragma unroll
+  for (int c = 0; c < CMAX; ++c) acc[c] = __float2half(0.f);
+  float T = 1.f;
+  int cur_idx = 0;
+
+  for (int b = 0; b < num_batches; ++b) {
+    if (__syncthreads_count(done) >= nthreads) break;
+    const int batch_start = range.x + nthreads * b;
+    const int idx = batch_start + tr;
+    if (idx < range.y) {
+      const int g = gaussian_ids_sorted[idx];
+      const float2 xy = xys[g];
+      s_geo[0][tr] = make_float4(xy.x, xy.y, opacities[g], conics[3 * (size_t)g]);
+      s_geo[1][tr] = make_float4(conics[3 * (size_t)g + 1], conics[3 * (size_t)g + 2], __int_as_float(g), 0.f);
+    }
+    __syncthreads();
+    const int batch_size = min(nthreads, range.y - batch_start);
+    for (int t = 0; (t < batch_size) && !done; ++t) {
+      const float4 q0 = s_geo[0][t], q1 = s_geo[1][t];
+      const float dx = q0.x - px, dy = q0.y - py;
+      const float sigma = 0.5f * (q0.w * dx * dx + q1.y * dy * dy) + q1.x * dx * dy;
+      const float alpha = fminf(0.999f, q0.z * __expf(-sigma));
+      if (sigma < 0.f || alpha < 1.f / 255.f) continue;
+      const float next_T = T * (1.f - alpha);
+      if (next_T <= 1e-4f) {
+        done = true;
+        break;
+      }
+      const int g = __float_as_int(q1.z);
+      const float vis = alpha * T;
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c)
+        if (c < channels) acc[c] = __hadd(acc[c], __float2half(colors[(size_t)channels * g + c] * vis));
+      T = next_T;
+      cur_idx = batch_start + t;
+    }
+  }
+  if (inside) {
+    const int pix = ipy * img_w + ipx;
+    final_Ts[pix] = T;
+    final_idx[pix] = cur_idx;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+      if (c < channels) out_img[(size_t)pix * channels + c] = __half2float(acc[c]) + T * background[c];
+  }
+}
+
+__device__ __forceinline__ float warp_sum_nd(float x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  return x;
+}
+
+template <int CMAX>
+__global__ void __launch_bounds__(256)
+nd_blend_backward_kernel(int tiles_x, int img_w, int img_h, int block_width, int channels,
+                         const int *__restrict__ gaussian_ids_sorted, const int2 *__restrict__ tile_bins,
+                         const float2 *__restrict__ xys, const float *__restrict__ conics,
+                         const float *__restrict__ colors, const float *__restrict__ opacities,
+                         const float *__restrict__ background, const float *__restrict__ final_Ts,
+                         const int *__restrict__ final_idx, const float *__restrict__ v_output,
+                         const float *__restrict__ v_output_alpha, float *__restrict__ v_xy,
+                         float *__restrict__ v_conic, float *__restrict__ v_colors,
+                         float *__restrict__ v_opacity) {
+  const unsigned full = 0xffffffffu;
+  const int tile_id = blockIdx.y * tiles_x + blockIdx.x;
+  const int tr = threadIdx.x, lane = tr & 31;
+  const int lx = tr % block_width, ly = tr / block_width;
+  const int ipx = blockIdx.x * block_width + lx, ipy = blockIdx.y * block_width + ly;
+  const bool inside = (ly < block_width) && (ipx < img_w) && (ipy < img_h);
+  const float px = (float)ipx, py = (float)ipy;
+  const int pix = inside ? ipy * img_w + ipx : 0;
+  const int2 range = tile_bins[tile_id];
+  const float T_final = inside ? final_Ts[pix] : 1.f;
+  float T = T_final;
+  const float v_out_alpha = inside ? v_output_alpha[pix] : 0.f;
+  float v_out[CMAX];
+  __half S[CMAX];
+#pragma unroll
+  for (int c = 0; c < CMAX; ++c) {
+    v_out[c] = (inside && c < channels) ? v_output[(size_t)pix * channels + c] : 0.f;
+    S[c] = __float2half(0.f);
+  }
+  const int bin_final = inside ? final_idx[pix] : 0;
+  const int warp_bin_final = __reduce_max_sync(full, bin_final);
+  // warp-synchronous walk, back to front, last contributor excluded (backward.cu:64-65)
+  for (int idx = warp_bin_final - 1; idx >= range.x; --idx) {
+    bool valid = inside && idx < bin_final;
+    const int g = gaussian_ids_sorted[idx];
+    const float ca = conics[3 * (size_t)g], cb = conics[3 * (size_t)g + 1], cc = conics[3 * (size_t)g + 2];
+    const float2 center = xys[g];
+    const float dx = center.x - px, dy = center.y - py;
+    const float sigma = 0.5f * (ca * dx * dx + cc * dy * dy) + cb * dx * dy;
+    if (sigma < 0.f) valid = false;
+    const float opac = opacities[g];
+    const float vis = __expf(-sigma);
+    const float alpha = fminf(0.99f, opac * vis);
+    if (alpha < 1.f / 255.f) valid = false;
+    if (!__any_sync(full, valid)) continue;
+    float l_conic0 = 0.f, l_conic1 = 0.f, l_conic2 = 0.f, l_xy0 = 0.f, l_xy1 = 0.f, l_op = 0.f;
+    if (valid) {
+      const float ra = 1.f / (1.f - alpha);
+      T *= ra;
+      const float fac = alpha * T;
+      float v_alpha = 0.f;
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c) {
+        if (c < channels) {
+          const float col = colors[(size_t)channels * g + c];
+          atomicAdd(&v_colors[(size_t)channels * g + c], fac * v_out[c]);
+          v_alpha += (col * T - __half2float(S[c]) * ra) * v_out[c];
+          v_alpha += -T_final * ra * background[c] * v_out[c];
+          S[c] = __hadd(S[c], __float2half(col * fac));
+        }
+      }
+      v_alpha += T_final * ra * v_out_alpha;
+      const float v_sigma = -opac * vis * v_alpha;
+      l_conic0 = 0.5f * v_sigma * dx * dx;
+      l_conic1 = v_sigma * dx * dy;
+      l_conic2 = 0.5f * v_sigma * dy * dy;
+      l_xy0 = v_sigma * (ca * dx + cb * dy);
+      l_xy1 = v_sigma * (cb * dx + cc * dy);
+      l_op = vis * v_alpha;
+    }
+    l_conic0 = warp_sum_nd(l_conic0);
+    l_conic1 = warp_sum_nd(l_conic1);
+    l_conic2 = warp_sum_nd(l_conic2);
+    l_xy0 = warp_sum_nd(l_xy0);
+    l_xy1 = warp_sum_nd(l_xy1);
+    l_op = warp_sum_nd(l_op);
+    if (lane == 0) {
+      atomicAdd(v_conic + 3 * (size_t)g, l_conic0);
+      atomicAdd(v_conic + 3 * (size_t)g + 1, l_conic1);
+      atomicAdd(v_conic + 3 * (size_t)g + 2, l_conic2);
+      atomicAdd(v_xy + 2 * (size_t)g, l_xy0);
+      atomicAdd(v_xy + 2 * (size_t)g + 1, l_xy1);
+      atomicAdd(v_opacity + g, l_op);
+    }
+  }
+}
+
+}  // namespace gsr
+
+#define GSR_ND_DISPATCH(KERNEL, ...)                                             \
+  do {                                                                           \
+    if (channels <= 4) KERNEL<4><<<grid, threads, 0, st>>>(__VA_ARGS__);         \
+    else if (channels <= 8) KERNEL<8><<<grid, threads, 0, st>>>(__VA_ARGS__);    \
+    else if (channels <= 16) KERNEL<16><<<grid, threads, 0, st>>>(__VA_ARGS__);  \
+    else KERNEL<32><<<grid, threads, 0, st>>>(__VA_ARGS__);                      \
+  } while (0)
+
+extern "C" {
+
+GSR_API int gsr_nd_rasterize_forward(unsigned img_height, unsigned img_width, unsigned block_width,
+                                     unsigned channels, int num_points, const int32_t *gaussian_ids_sorted,
+                                     const int32_t *tile_bins, const float *xys, const float *conics,
+                                     const float *colors, const float *opacities, const float *background,
+                                     float *out_img, float *final_Ts, int32_t *final_idx, void *stream) {
+  using namespace gsr;
+  (void)num_points;
+  GSR_REQUIRE(block_width > 1 && block_width <= 16, GSR_ERR_INVALID_ARGUMENT,
+              "block_width must be between 2 and 16 (got %u)", block_width);
+  GSR_REQUIRE(channels >= 1 && channels <= GSR_MAX_CHANNELS, GSR_ERR_UNSUPPORTED,
+              "nd_rasterize_forward: channels %u not in [1,%d]", channels, GSR_MAX_CHANNELS);
+  GSR_REQUIRE(img_height > 0 && img_width > 0, GSR_ERR_INVALID_ARGUMENT, "nd_rasterize_forward: empty image");
+  GSR_REQUIRE(gaussian_ids_sorted && tile_bins && xys && conics && colors && opacities && background && out_img &&
+                  final_Ts && final_idx,
+              GSR_ERR_INVALID_ARGUMENT, "nd_rasterize_forward: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const dim3 grid(cdiv(img_width, block_width), cdiv(img_height, block_width), 1);
+  const unsigned threads = cdiv(block_width * block_width, 32) * 32;
+  GSR_ND_DISPATCH(nd_blend_forward_kernel, (int)grid.x, (int)img_width, (int)img_height, (int)block_width,
+                  (int)channels, gaussian_ids_sorted, reinterpret_cast<const int2 *>(tile_bins),
+                  reinterpret_cast<const float2 *>(xys), conics, colors, opacities, background, out_img, final_Ts,
+                  final_idx);
+  GSR_CHECK_LAUNCH("nd_blend_forward_kernel");
+  return GSR_OK;
+}
+
+GSR_API int gsr_nd_rasterize_backward(unsigned img_height, unsigned img_width, unsigned block_width,
+                                      unsigned channels, int num_points, const int32_t *gaussian_ids_sorted,
+                                      const int32_t *tile_bins, const float *xys, const float *conics,
+                                      const float *colors, const float *opacities, const float *background,
+                                      const float *final_Ts, const int32_t *final_idx, const float *v_output,
+                                      const float *v_output_alpha, float *v_xy, float *v_conic,
+                                      float *v_colors, float *v_opacity, void *stream) {
+  using namespace gsr;
+  GSR_REQUIRE(block_width > 1 && block_width <= 16, GSR_ERR_INVALID_ARGUMENT,
+              "block_width must be between 2 and 16 (got %u)", block_width);
+  GSR_REQUIRE(channels >= 1 && channels <= GSR_MAX_CHANNELS, GSR_ERR_UNSUPPORTED,
+              "nd_rasterize_backward: channels %u not in [1,%d]", channels, GSR_MAX_CHANNELS);
+  GSR_REQUIRE(img_height > 0 && img_width > 0 && num_points >= 0, GSR_ERR_INVALID_ARGUMENT, "nd_rasterize_backward: bad sizes");
+  if (num_points == 0) return GSR_OK;
+  GSR_REQUIRE(gaussian_ids_sorted && tile_bins && xys && conics && colors && opacities && background && final_Ts &&
+                  final_idx && v_output && v_output_alpha && v_xy && v_conic && v_colors && v_opacity,
+              GSR_ERR_INVALID_ARGUMENT, "nd_rasterize_backward: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  GSR_CUDA(cudaMemsetAsync(v_xy, 0, sizeof(float) * 2 * (size_t)num_points, st));
+  GSR_CUDA(cudaMemsetAsync(v_conic, 0, sizeof(float) * 3 * (size_t)num_points, st));
+  GSR_CUDA(cudaMemsetAsync(v_colors, 0, sizeof(float) * channels * (size_t)num_points, st));
+  GSR_CUDA(cudaMemsetAsync(v_opacity, 0, sizeof(float) * (size_t)num_points, st));
+  const dim3 grid(cdiv(img_width, block_width), cdiv(img_height, block_width), 1);
+  const unsigned threads = cdiv(block_width * block_width, 32) * 32;
+  GSR_ND_DISPATCH(nd_blend_backward_kernel, (int)grid.x, (int)img_width, (int)img_height, (int)block_width,
+                  (int)channels, gaussian_ids_sorted, reinterpret_cast<const int2 *>(tile_bins),
+                  reinterpret_cast<const float2 *>(xys), conics, colors, opacities, background, final_Ts, final_idx,
+                  v_output, v_output_alpha, v_xy, v_conic, v_colors, v_opacity);
+  GSR_CHECK_LAUNCH("nd_blend_backward_kernel");
+  return GSR_OK;
+}
+}

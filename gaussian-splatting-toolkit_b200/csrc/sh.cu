@@ -1,0 +1,233 @@
+// sh.cu — spherical-harmonics colour evaluation and its adjoint for sm_100a.
+//
+// Replaces compute_sh_forward_kernel / compute_sh_backward_kernel of the reference
+// (gs_toolkit/gs_components/rasterizer/cuda/csrc/sh.cuh:33-224, launched from bindings.cu:58-103).
+//
+// Both kernels are pure HBM streaming (216 B per Gaussian at degree 3).  The reference lets every thread
+// walk its own 192-byte coefficient row (32 different cache lines per warp-level load).  Here a CTA of
+// 128 threads owns 128 consecutive Gaussians = one contiguous 128*K*3-float block, moves it between HBM
+// and shared memory with fully coalesced 128-bit accesses, and each thread then reads / writes its own
+// row in shared memory with an odd row stride (bank-conflict free).  The backward writes every one of
+// the K*3 outputs itself (zeros above degrees_to_use), so no separate zero-fill pass is needed.
+#include "common.cuh"
+
+namespace gsr {
+
+__constant__ float kSH_C1 = 0.4886025119029199f;
+__constant__ float kSH_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                                -1.0925484305920792f, 0.5462742152960396f};
+__constant__ float kSH_C3[7] = {-0.5900435899266435f, 2.890611442640554f,  -0.4570457994644658f,
+                                0.3731763325901154f,  -0.4570457994644658f, 1.445305721320277f,
+                                -0.5900435899266435f};
+__constant__ float kSH_C4[9] = {2.5033429417967046f,  -1.7701307697799304f, 0.9461746957575601f,
+                                -0.6690465435572892f, 0.10578554691520431f, -0.6690465435572892f,
+                                0.47308734787878004f, -1.7701307697799304f, 0.6258357354491761f};
+#define GSR_SH_C0 0.28209479177387814f
+
+constexpr int SH_THREADS = 128;
+
+__host__ __device__ inline int num_sh_bases(int degree) {  // sh.cuh:21-31
+  return degree == 0 ? 1 : degree == 1 ? 4 : degree == 2 ? 9 : degree == 3 ? 16 : 25;
+}
+
+// basis values for the bands 1..deg (Y[0] = C0 is handled by the callers); dir normalised as sh.cuh:44-48
+__device__ __forceinline__ void sh_basis(int deg, float dx, float dy, float dz, float *Y) {
+  if (deg < 1) return;
+  float norm = sqrtf(dx * dx + dy * dy + dz * dz);
+  float x = dx / norm, y = dy / norm, z = dz / norm;
+  Y[1] = -kSH_C1 * y;
+  Y[2] = kSH_C1 * z;
+  Y[3] = -kSH_C1 * x;
+  if (deg < 2) return;
+  float xx = x * x, xy = x * y, xz = x * z, yy = y * y, yz = y * z, zz = z * z;
+  Y[4] = kSH_C2[0] * xy;
+  Y[5] = kSH_C2[1] * yz;
+  Y[6] = kSH_C2[2] * (2.f * zz - xx - yy);
+  Y[7] = kSH_C2[3] * xz;
+  Y[8] = kSH_C2[4] * (xx - yy);
+  if (deg < 3) return;
+  Y[9] = kSH_C3[0] * y * (3.f * xx - yy);
+  Y[10] = kSH_C3[1] * xy * z;
+  Y[11] = kSH_C3[2] * y * (4.f * zz - xx - yy);
+  Y[12] = kSH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy);
+  Y[13] = kSH_C3[4] * x * (4.f * zz - xx - yy);
+  Y[14] = kSH_C3[5] * z * (xx - yy);
+  Y[15] = kSH_C3[6] * x * (xx - 3.f * yy);
+  if (deg < 4) return;
+  Y[16] = kSH_C4[0] * xy * (xx - yy);
+  Y[17] = kSH_C4[1] * yz * (3.f * xx - yy);
+  Y[18] = kSH_C4[2] * xy * (7.f * zz - 1.f);
+  Y[19] = kSH_C4[3] * yz * (7.f * zz - 3.f);
+  Y[20] = kSH_C4[4] * (zz * (35.f * zz - 30.f) + 3.f);
+  Y[21] = kSH_C4[5] * xz * (7.f * zz - 3.f);
+  Y[22] = kSH_C4[6] * (xx - yy) * (7.f * zz - 1.f);
+  Y[23] = kSH_C4[7] * xz * (xx - 3.f * yy);
+  Y[24] = kSH_C4[8] * (xx * (xx - 3.f * yy) - yy * (3.f * xx - yy));
+}
+
+// smem row stride: odd => row-per-thread accesses are bank-conflict free
+__host__ __device__ inline int sh_row_stride(int row_len) { return row_len | 1; }
+
+// Coalesced global -> shared copy of `count` floats laid out [rows][row_len] into rows of `stride`.
+__device__ __forceinline__ void stage_in(const float *__restrict__ g, float *s, int count, int row_len,
+                                         int stride, bool vec_ok) {
+  int tid = threadIdx.x;
+  int nvec = vec_ok ? (count >> 2) : 0;
+  const float4 *g4 = reinterpret_cast<const float4 *>(g);
+  for (int i = tid; i < nvec; i += SH_THREADS) {
+    float4 v = __ldg(g4 + i);
+    int f = i << 2;
+    int r = f / row_len, c = f - r * row_len;
+    float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      s[r * stride + c] = vv[j];
+      if (++c == row_len) { c = 0; ++r; }
+    }
+  }
+  for (int f = (nvec << 2) + tid; f < count; f += SH_THREADS) {
+    int r = f / row_len, c = f - r * row_len;
+    s[r * stride + c] = __ldg(g + f);
+  }
+}
+
+// Coalesced shared -> global copy (inverse of stage_in).
+__device__ __forceinline__ void stage_out(float *__restrict__ g, const float *s, int count, int row_len,
+                                          int stride, bool vec_ok) {
+  int tid = threadIdx.x;
+  int nvec = vec_ok ? (count >> 2) : 0;
+  float4 *g4 = reinterpret_cast<float4 *>(g);
+  for (int i = tid; i < nvec; i += SH_THREADS) {
+    int f = i << 2;
+    int r = f / row_len, c = f - r * row_len;
+    float vv[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      vv[j] = s[r * stride + c];
+      if (++c == row_len) { c = 0; ++r; }
+    }
+    g4[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+  }
+  for (int f = (nvec << 2) + tid; f < count; f += SH_THREADS) {
+    int r = f / row_len, c = f - r * row_len;
+    g[f] = s[r * stride + c];
+  }
+}
+
+__global__ void __launch_bounds__(SH_THREADS)
+sh_forward_kernel(int n, int K, int deg_use, const float *__restrict__ viewdirs,
+                  const float *__restrict__ coeffs, float *__restrict__ colors, int vec_ok) {
+  extern __shared__ float smem[];
+  const int row_len = 3 * K, stride = sh_row_stride(row_len);
+  const int g0 = blockIdx.x * SH_THREADS;
+  const int rows = min(SH_THREADS, n - g0);
+  stage_in(coeffs + (size_t)g0 * row_len, smem, rows * row_len, row_len, stride, vec_ok != 0);
+  __syncthreads();
+  const int tid = threadIdx.x;
+  if (tid < rows) {
+    const int g = g0 + tid;
+    float Y[25];
+    sh_basis(deg_use, viewdirs[3 * (size_t)g], viewdirs[3 * (size_t)g + 1], viewdirs[3 * (size_t)g + 2], Y);
+    const float *c = smem + tid * stride;
+    float out[3];
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      float acc = GSR_SH_C0 * c[ch];
+      if (deg_use >= 1) acc += Y[1] * c[3 + ch] + Y[2] * c[6 + ch] + Y[3] * c[9 + ch];
+      if (deg_use >= 2) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 4; k < 9; ++k) s += Y[k] * c[3 * k + ch];
+        acc += s;
+      }
+      if (deg_use >= 3) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 9; k < 16; ++k) s += Y[k] * c[3 * k + ch];
+        acc += s;
+      }
+      if (deg_use >= 4) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 16; k < 25; ++k) s += Y[k] * c[3 * k + ch];
+        acc += s;
+      }
+      out[ch] = acc;
+    }
+    colors[3 * (size_t)g] = out[0];
+    colors[3 * (size_t)g + 1] = out[1];
+    colors[3 * (size_t)g + 2] = out[2];
+  }
+}
+
+__global__ void __launch_bounds__(SH_THREADS)
+sh_backward_kernel(int n, int K, int deg_use, const float *__restrict__ viewdirs,
+                   const float *__restrict__ v_colors, float *__restrict__ v_coeffs, int vec_ok) {
+  extern __shared__ float smem[];
+  const int row_len = 3 * K, stride = sh_row_stride(row_len);
+  const int g0 = blockIdx.x * SH_THREADS;
+  const int rows = min(SH_THREADS, n - g0);
+  const int tid = threadIdx.x;
+  const int Ku = num_sh_bases(deg_use);
+  if (tid < rows) {
+    const int g = g0 + tid;
+    float Y[25];
+    Y[0] = GSR_SH_C0;
+    sh_basis(deg_use, viewdirs[3 * (size_t)g], viewdirs[3 * (size_t)g + 1], viewdirs[3 * (size_t)g + 2], Y);
+    const float v0 = v_colors[3 * (size_t)g], v1 = v_colors[3 * (size_t)g + 1], v2 = v_colors[3 * (size_t)g + 2];
+    float *o = smem + tid * stride;
+#pragma unroll
+    for (int k = 0; k < 25; ++k) {
+      if (k < K) {
+        float y = (k < Ku) ? Y[k] : 0.f;
+        o[3 * k] = y * v0;
+        o[3 * k + 1] = y * v1;
+        o[3 * k + 2] = y * v2;
+      }
+    }
+  }
+  __syncthreads();
+  stage_out(v_coeffs + (size_t)g0 * row_len, smem, rows * row_len, row_len, stride, vec_ok != 0);
+}
+
+}  // namespace gsr
+
+extern "C" {
+
+GSR_API int gsr_compute_sh_forward(int num_points, int degree, int degrees_to_use, const float *viewdirs,
+                                   const float *coeffs, float *colors, void *stream) {
+  using namespace gsr;
+  GSR_REQUIRE(num_points >= 0, GSR_ERR_INVALID_ARGUMENT, "compute_sh_forward: num_points < 0");
+  GSR_REQUIRE(degree >= 0 && degree <= 4, GSR_ERR_UNSUPPORTED, "compute_sh_forward: degree %d not in [0,4]", degree);
+  GSR_REQUIRE(degrees_to_use >= 0 && degrees_to_use <= degree, GSR_ERR_INVALID_ARGUMENT,
+              "compute_sh_forward: degrees_to_use %d not in [0,%d]", degrees_to_use, degree);
+  if (num_points == 0) return GSR_OK;
+  GSR_REQUIRE(viewdirs && coeffs && colors, GSR_ERR_INVALID_ARGUMENT, "compute_sh_forward: null pointer");
+  const int K = num_sh_bases(degree);
+  const size_t smem = (size_t)SH_THREADS * sh_row_stride(3 * K) * sizeof(float);
+  // every CTA's block starts at g0*3K floats: 16-byte aligned iff the base is and 128*3K*4 % 16 == 0 (always)
+  const int vec_ok = ((uintptr_t)coeffs % 16 == 0) ? 1 : 0;
+  sh_forward_kernel<<<cdiv(num_points, SH_THREADS), SH_THREADS, smem, (cudaStream_t)stream>>>(
+      num_points, K, degrees_to_use, viewdirs, coeffs, colors, vec_ok);
+  GSR_CHECK_LAUNCH("sh_forward_kernel");
+  return GSR_OK;
+}
+
+GSR_API int gsr_compute_sh_backward(int num_points, int degree, int degrees_to_use, const float *viewdirs,
+                                    const float *v_colors, float *v_coeffs, void *stream) {
+  using namespace gsr;
+  GSR_REQUIRE(num_points >= 0, GSR_ERR_INVALID_ARGUMENT, "compute_sh_backward: num_points < 0");
+  GSR_REQUIRE(degree >= 0 && degree <= 4, GSR_ERR_UNSUPPORTED, "compute_sh_backward: degree %d not in [0,4]", degree);
+  GSR_REQUIRE(degrees_to_use >= 0 && degrees_to_use <= degree, GSR_ERR_INVALID_ARGUMENT,
+              "compute_sh_backward: degrees_to_use %d not in [0,%d]", degrees_to_use, degree);
+  if (num_points == 0) return GSR_OK;
+  GSR_REQUIRE(viewdirs && v_colors && v_coeffs, GSR_ERR_INVALID_ARGUMENT, "compute_sh_backward: null pointer");
+  const int K = num_sh_bases(degree);
+  const size_t smem = (size_t)SH_THREADS * sh_row_stride(3 * K) * sizeof(float);
+  const int vec_ok = ((uintptr_t)v_coeffs % 16 == 0) ? 1 : 0;
+  sh_backward_kernel<<<cdiv(num_points, SH_THREADS), SH_THREADS, smem, (cudaStream_t)stream>>>(
+      num_points, K, degrees_to_use, viewdirs, v_colors, v_coeffs, vec_ok);
+  GSR_CHECK_LAUNCH("sh_backward_kernel");
+  return GSR_OK;
+}
+}

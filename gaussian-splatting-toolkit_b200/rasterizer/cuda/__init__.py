@@ -1,0 +1,311 @@
+"""`rasterizer.cuda` — the native-binding surface of the reference package, backed by libgsr_b200.so.
+
+The reference module (rasterizer/cuda/__init__.py:4-26) exposes lazy trampolines to the 11 pybind
+functions of csrc/ext.cpp:6-17.  The same 11 names with the same positional arguments and return
+tuples are provided here; each allocates its outputs with torch (like bindings.cu does with
+torch::zeros / torch::empty, but uninitialised: the kernels write every element) and calls the C ABI of
+include/gsr_b200.h with raw device pointers on torch's current stream.
+
+Argument checking mirrors bindings.h:10-15 (CHECK_CUDA / CHECK_CONTIGUOUS -> RuntimeError) and the
+AT_ERROR shape checks of bindings.cu:65-68,86-93,420-426,490-496.
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+import torch
+from torch import Tensor
+
+from .. import _lib
+
+_P = _lib.C.c_void_p
+
+
+def _ptr(t: Tensor):
+    return _P(t.data_ptr())
+
+
+def _check_input(x: Tensor, name: str, dtype=None) -> None:
+    if not isinstance(x, Tensor) or not x.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+    if not x.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+    if dtype is not None and x.dtype != dtype:
+        raise RuntimeError(f"{name}: expected scalar type {dtype} but found {x.dtype}")
+
+
+class _Guard:
+    """DEVICE_GUARD(tensor) of bindings.h:16-17 + the stream to launch on (the reference uses the legacy
+    default stream; we use torch's current stream of the tensor's device)."""
+
+    __slots__ = ("dev", "prev", "stream")
+
+    def __init__(self, t: Tensor):
+        self.dev = t.device.index if t.device.index is not None else torch.cuda.current_device()
+
+    def __enter__(self):
+        self.prev = torch.cuda.current_device()
+        if self.prev != self.dev:
+            torch.cuda.set_device(self.dev)
+        self.stream = _P(torch.cuda.current_stream(self.dev).cuda_stream)
+        return self.stream
+
+    def __exit__(self, *exc):
+        if self.prev != self.dev:
+            torch.cuda.set_device(self.prev)
+        return False
+
+
+def num_sh_bases(degree: int) -> int:
+    return {0: 1, 1: 4, 2: 9, 3: 16}.get(degree, 25)
+
+
+# ---------------------------------------------------------------------------------------------------
+def compute_sh_forward(num_points: int, degree: int, degrees_to_use: int, viewdirs: Tensor, coeffs: Tensor) -> Tensor:
+    _check_input(viewdirs, "viewdirs", torch.float32)
+    _check_input(coeffs, "coeffs", torch.float32)
+    nb = num_sh_bases(degree)
+    if coeffs.dim() != 3 or coeffs.size(0) != num_points or coeffs.size(1) != nb or coeffs.size(2) != 3:
+        raise RuntimeError("coeffs must have dimensions (N, D, 3)")
+    colors = torch.empty((num_points, 3), dtype=torch.float32, device=coeffs.device)
+    with _Guard(coeffs) as st:
+        _lib.check(_lib.load().gsr_compute_sh_forward(num_points, degree, degrees_to_use, _ptr(viewdirs),
+                                                      _ptr(coeffs), _ptr(colors), st), "compute_sh_forward")
+    return colors
+
+
+def compute_sh_backward(num_points: int, degree: int, degrees_to_use: int, viewdirs: Tensor, v_colors: Tensor) -> Tensor:
+    _check_input(viewdirs, "viewdirs", torch.float32)
+    _check_input(v_colors, "v_colors", torch.float32)
+    if viewdirs.dim() != 2 or viewdirs.size(0) != num_points or viewdirs.size(1) != 3:
+        raise RuntimeError("viewdirs must have dimensions (N, 3)")
+    if v_colors.dim() != 2 or v_colors.size(0) != num_points or v_colors.size(1) != 3:
+        raise RuntimeError("v_colors must have dimensions (N, 3)")
+    nb = num_sh_bases(degree)
+    v_coeffs = torch.empty((num_points, nb, 3), dtype=torch.float32, device=v_colors.device)
+    with _Guard(v_colors) as st:
+        _lib.check(_lib.load().gsr_compute_sh_backward(num_points, degree, degrees_to_use, _ptr(viewdirs),
+                                                       _ptr(v_colors), _ptr(v_coeffs), st), "compute_sh_backward")
+    return v_coeffs
+
+
+def compute_cov2d_bounds(num_pts: int, covs2d: Tensor) -> Tuple[Tensor, Tensor]:
+    _check_input(covs2d, "covs2d", torch.float32)
+    conics = torch.empty((num_pts, covs2d.size(1)), dtype=torch.float32, device=covs2d.device)
+    radii = torch.empty((num_pts, 1), dtype=torch.float32, device=covs2d.device)
+    with _Guard(covs2d) as st:
+        _lib.check(_lib.load().gsr_compute_cov2d_bounds(num_pts, _ptr(covs2d), _ptr(conics), _ptr(radii), st),
+                   "compute_cov2d_bounds")
+    return conics, radii
+
+
+# ---------------------------------------------------------------------------------------------------
+def project_gaussians_forward(num_points: int, means3d: Tensor, scales: Tensor, glob_scale: float, quats: Tensor,
+                              viewmat: Tensor, projmat: Tensor, fx: float, fy: float, cx: float, cy: float,
+                              img_height: int, img_width: int, block_width: int, clip_thresh: float):
+    for t, n in ((means3d, "means3d"), (scales, "scales"), (quats, "quats"), (viewmat, "viewmat"),
+                 (projmat, "projmat")):
+        _check_input(t, n, torch.float32)
+    if viewmat.numel() < 12 or projmat.numel() < 16:
+        raise RuntimeError("viewmat needs >= 12 and projmat 16 elements")
+    dev = means3d.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    i32 = dict(dtype=torch.int32, device=dev)
+    cov3d = torch.empty((num_points, 6), **f32)
+    xys = torch.empty((num_points, 2), **f32)
+    depths = torch.empty((num_points,), **f32)
+    radii = torch.empty((num_points,), **i32)
+    conics = torch.empty((num_points, 3), **f32)
+    compensation = torch.empty((num_points,), **f32)
+    num_tiles_hit = torch.empty((num_points,), **i32)
+    with _Guard(means3d) as st:
+        _lib.check(_lib.load().gsr_project_gaussians_forward(
+            num_points, _ptr(means3d), _ptr(scales), float(glob_scale), _ptr(quats), _ptr(viewmat), _ptr(projmat),
+            float(fx), float(fy), float(cx), float(cy), int(img_height), int(img_width), int(block_width),
+            float(clip_thresh), _ptr(cov3d), _ptr(xys), _ptr(depths), _ptr(radii), _ptr(conics),
+            _ptr(compensation), _ptr(num_tiles_hit), st), "project_gaussians_forward")
+    return cov3d, xys, depths, radii, conics, compensation, num_tiles_hit
+
+
+def project_gaussians_backward(num_points: int, means3d: Tensor, scales: Tensor, glob_scale: float, quats: Tensor,
+                               viewmat: Tensor, projmat: Tensor, fx: float, fy: float, cx: float, cy: float,
+                               img_height: int, img_width: int, cov3d: Tensor, radii: Tensor, conics: Tensor,
+                               compensation: Tensor, v_xy: Tensor, v_depth: Tensor, v_conic: Tensor,
+                               v_compensation: Tensor):
+    for t, n in ((means3d, "means3d"), (scales, "scales"), (quats, "quats"), (viewmat, "viewmat"),
+                 (projmat, "projmat"), (cov3d, "cov3d"), (conics, "conics"), (compensation, "compensation"),
+                 (v_xy, "v_xy"), (v_depth, "v_depth"), (v_conic, "v_conic"), (v_compensation, "v_compensation")):
+        _check_input(t, n, torch.float32)
+    _check_input(radii, "radii", torch.int32)
+    dev = means3d.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    v_cov2d = torch.empty((num_points, 3), **f32)
+    v_cov3d = torch.empty((num_points, 6), **f32)
+    v_mean3d = torch.empty((num_points, 3), **f32)
+    v_scale = torch.empty((num_points, 3), **f32)
+    v_quat = torch.empty((num_points, 4), **f32)
+    with _Guard(means3d) as st:
+        _lib.check(_lib.load().gsr_project_gaussians_backward(
+            num_points, _ptr(means3d), _ptr(scales), float(glob_scale), _ptr(quats), _ptr(viewmat), _ptr(projmat),
+            float(fx), float(fy), float(cx), float(cy), int(img_height), int(img_width), _ptr(cov3d), _ptr(radii),
+            _ptr(conics), _ptr(compensation), _ptr(v_xy), _ptr(v_depth), _ptr(v_conic), _ptr(v_compensation),
+            _ptr(v_cov2d), _ptr(v_cov3d), _ptr(v_mean3d), _ptr(v_scale), _ptr(v_quat), st),
+            "project_gaussians_backward")
+    return v_cov2d, v_cov3d, v_mean3d, v_scale, v_quat
+
+
+# ---------------------------------------------------------------------------------------------------
+def cumsum_tiles_hit(num_tiles_hit: Tensor, total_pinned: Tensor = None) -> Tensor:
+    """int32 inclusive scan (replaces torch.cumsum at rasterizer/utils.py:123).  If `total_pinned` (a pinned
+    CPU int32 tensor with one element) is given, the total is copied into it asynchronously."""
+    _check_input(num_tiles_hit, "num_tiles_hit", torch.int32)
+    n = num_tiles_hit.numel()
+    lib = _lib.load()
+    cum = torch.empty_like(num_tiles_hit)
+    ws_bytes = lib.gsr_cumsum_workspace_bytes(n)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=num_tiles_hit.device)
+    with _Guard(num_tiles_hit) as st:
+        _lib.check(lib.gsr_cumsum_tiles_hit(n, _ptr(num_tiles_hit), _ptr(cum),
+                                            _P(total_pinned.data_ptr()) if total_pinned is not None else None,
+                                            _ptr(ws), ws_bytes, st), "cumsum_tiles_hit")
+    return cum
+
+
+def map_gaussian_to_intersects(num_points: int, num_intersects: int, xys: Tensor, depths: Tensor, radii: Tensor,
+                               cum_tiles_hit: Tensor, tile_bounds: Tuple[int, int, int], block_width: int):
+    _check_input(xys, "xys", torch.float32)
+    _check_input(depths, "depths", torch.float32)
+    _check_input(radii, "radii", torch.int32)
+    _check_input(cum_tiles_hit, "cum_tiles_hit", torch.int32)
+    gaussian_ids = torch.zeros((num_intersects,), dtype=torch.int32, device=xys.device)
+    isect_ids = torch.zeros((num_intersects,), dtype=torch.int64, device=xys.device)
+    with _Guard(xys) as st:
+        _lib.check(_lib.load().gsr_map_gaussian_to_intersects(
+            num_points, num_intersects, _ptr(xys), _ptr(depths), _ptr(radii), _ptr(cum_tiles_hit),
+            int(tile_bounds[0]), int(tile_bounds[1]), int(block_width), _ptr(isect_ids), _ptr(gaussian_ids), st),
+            "map_gaussian_to_intersects")
+    return isect_ids, gaussian_ids
+
+
+def sort_intersects(isect_ids: Tensor, gaussian_ids: Tensor, num_tiles: int) -> Tuple[Tensor, Tensor]:
+    """Stable radix sort of (key, Gaussian id) pairs (replaces torch.sort + torch.gather, utils.py:179-180)."""
+    _check_input(isect_ids, "isect_ids", torch.int64)
+    _check_input(gaussian_ids, "gaussian_ids", torch.int32)
+    m = isect_ids.numel()
+    lib = _lib.load()
+    keys = torch.empty_like(isect_ids)
+    vals = torch.empty_like(gaussian_ids)
+    ws_bytes = lib.gsr_sort_workspace_bytes(m)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=isect_ids.device)
+    with _Guard(isect_ids) as st:
+        _lib.check(lib.gsr_sort_intersects(m, int(num_tiles), _ptr(isect_ids), _ptr(gaussian_ids), _ptr(keys),
+                                           _ptr(vals), _ptr(ws), ws_bytes, st), "sort_intersects")
+    return keys, vals
+
+
+def get_tile_bin_edges(num_intersects: int, isect_ids_sorted: Tensor, tile_bounds: Tuple[int, int, int]) -> Tensor:
+    _check_input(isect_ids_sorted, "isect_ids_sorted", torch.int64)
+    num_tiles = int(tile_bounds[0]) * int(tile_bounds[1])
+    tile_bins = torch.empty((num_tiles, 2), dtype=torch.int32, device=isect_ids_sorted.device)
+    with _Guard(isect_ids_sorted) as st:
+        _lib.check(_lib.load().gsr_get_tile_bin_edges(num_intersects, _ptr(isect_ids_sorted), num_tiles,
+                                                      _ptr(tile_bins), st), "get_tile_bin_edges")
+    return tile_bins
+
+
+# ---------------------------------------------------------------------------------------------------
+def _check_raster_inputs(gaussian_ids_sorted, tile_bins, xys, conics, colors, opacities, background):
+    _check_input(gaussian_ids_sorted, "gaussian_ids_sorted", torch.int32)
+    _check_input(tile_bins, "tile_bins", torch.int32)
+    _check_input(xys, "xys", torch.float32)
+    _check_input(conics, "conics", torch.float32)
+    _check_input(colors, "colors", torch.float32)
+    _check_input(opacities, "opacities", torch.float32)
+    _check_input(background, "background", torch.float32)
+
+
+def _rasterize_forward(nd: bool, tile_bounds, block, img_size, gaussian_ids_sorted, tile_bins, xys, conics, colors,
+                       opacities, background):
+    _check_raster_inputs(gaussian_ids_sorted, tile_bins, xys, conics, colors, opacities, background)
+    channels = colors.size(1)
+    img_width, img_height = int(img_size[0]), int(img_size[1])
+    block_width = int(block[0])
+    dev = xys.device
+    out_img = torch.empty((img_height, img_width, channels), dtype=torch.float32, device=dev)
+    final_Ts = torch.empty((img_height, img_width), dtype=torch.float32, device=dev)
+    final_idx = torch.empty((img_height, img_width), dtype=torch.int32, device=dev)
+    lib = _lib.load()
+    with _Guard(xys) as st:
+        if nd:
+            rc = lib.gsr_nd_rasterize_forward(img_height, img_width, block_width, channels, xys.size(0),
+                                              _ptr(gaussian_ids_sorted), _ptr(tile_bins), _ptr(xys), _ptr(conics),
+                                              _ptr(colors), _ptr(opacities), _ptr(background), _ptr(out_img),
+                                              _ptr(final_Ts), _ptr(final_idx), st)
+        else:
+            if channels != 3:
+                raise RuntimeError("rasterize_forward: colors must have 3 channels (use nd_rasterize_forward)")
+            rc = lib.gsr_rasterize_forward(img_height, img_width, block_width, xys.size(0),
+                                           _ptr(gaussian_ids_sorted), _ptr(tile_bins), _ptr(xys), _ptr(conics),
+                                           _ptr(colors), _ptr(opacities), _ptr(background), _ptr(out_img),
+                                           _ptr(final_Ts), _ptr(final_idx), st)
+        _lib.check(rc, "nd_rasterize_forward" if nd else "rasterize_forward")
+    return out_img, final_Ts, final_idx
+
+
+def rasterize_forward(tile_bounds, block, img_size, gaussian_ids_sorted, tile_bins, xys, conics, colors, opacities,
+                      background):
+    return _rasterize_forward(False, tile_bounds, block, img_size, gaussian_ids_sorted, tile_bins, xys, conics,
+                              colors, opacities, background)
+
+
+def nd_rasterize_forward(tile_bounds, block, img_size, gaussian_ids_sorted, tile_bins, xys, conics, colors,
+                         opacities, background):
+    return _rasterize_forward(True, tile_bounds, block, img_size, gaussian_ids_sorted, tile_bins, xys, conics,
+                              colors, opacities, background)
+
+
+def _rasterize_backward(nd: bool, img_height, img_width, block_width, gaussians_ids_sorted, tile_bins, xys, conics,
+                        colors, opacities, background, final_Ts, final_idx, v_output, v_output_alpha):
+    _check_input(xys, "xys", torch.float32)
+    _check_input(colors, "colors", torch.float32)
+    if xys.dim() != 2 or xys.size(1) != 2:
+        raise RuntimeError("xys must have dimensions (num_points, 2)")
+    if colors.dim() != 2 or (not nd and colors.size(1) != 3):
+        raise RuntimeError("colors must have 2 dimensions")
+    # the reference calls .contiguous() on everything else (bindings.cu:510-526)
+    gaussians_ids_sorted = gaussians_ids_sorted.contiguous()
+    tile_bins, conics, opacities = tile_bins.contiguous(), conics.contiguous(), opacities.contiguous()
+    background, final_Ts, final_idx = background.contiguous(), final_Ts.contiguous(), final_idx.contiguous()
+    v_output, v_output_alpha = v_output.contiguous(), v_output_alpha.contiguous()
+    if v_output.dtype != torch.float32 or v_output_alpha.dtype != torch.float32:
+        raise RuntimeError("v_output / v_output_alpha: expected scalar type Float")
+    num_points, channels = xys.size(0), colors.size(1)
+    dev = xys.device
+    v_xy = torch.empty((num_points, 2), dtype=torch.float32, device=dev)
+    v_conic = torch.empty((num_points, 3), dtype=torch.float32, device=dev)
+    v_colors = torch.empty((num_points, channels), dtype=torch.float32, device=dev)
+    v_opacity = torch.empty((num_points, 1), dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    with _Guard(xys) as st:
+        args = (_ptr(gaussians_ids_sorted), _ptr(tile_bins), _ptr(xys), _ptr(conics), _ptr(colors), _ptr(opacities),
+                _ptr(background), _ptr(final_Ts), _ptr(final_idx), _ptr(v_output), _ptr(v_output_alpha), _ptr(v_xy),
+                _ptr(v_conic), _ptr(v_colors), _ptr(v_opacity), st)
+        if nd:
+            rc = lib.gsr_nd_rasterize_backward(int(img_height), int(img_width), int(block_width), channels,
+                                               num_points, *args)
+        else:
+            rc = lib.gsr_rasterize_backward(int(img_height), int(img_width), int(block_width), num_points, *args)
+        _lib.check(rc, "nd_rasterize_backward" if nd else "rasterize_backward")
+    return v_xy, v_conic, v_colors, v_opacity
+
+
+def rasterize_backward(img_height, img_width, block_width, gaussians_ids_sorted, tile_bins, xys, conics, colors,
+                       opacities, background, final_Ts, final_idx, v_output, v_output_alpha):
+    return _rasterize_backward(False, img_height, img_width, block_width, gaussians_ids_sorted, tile_bins, xys,
+                               conics, colors, opacities, background, final_Ts, final_idx, v_output, v_output_alpha)
+
+
+def nd_rasterize_backward(img_height, img_width, block_width, gaussians_ids_sorted, tile_bins, xys, conics, colors,
+                          opacities, background, final_Ts, final_idx, v_output, v_output_alpha):
+    return _rasterize_backward(True, img_height, img_width, block_width, gaussians_ids_sorted, tile_bins, xys,
+                               conics, colors, opacities, background, final_Ts, final_idx, v_output, v_output_alpha)

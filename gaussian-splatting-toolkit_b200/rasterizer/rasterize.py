@@ -1,0 +1,90 @@
+"""Tile rasterization of projected Gaussians — same surface as the reference `rasterizer.rasterize`
+(rasterizer/rasterize.py:14-247)."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+from torch import Tensor
+from torch.autograd import Function
+
+from . import cuda as _C
+from .utils import bin_and_sort_gaussians, compute_cumulative_intersects
+
+
+def rasterize_gaussians(xys: Tensor, depths: Tensor, radii: Tensor, conics: Tensor, num_tiles_hit: Tensor,
+                        colors: Tensor, opacity: Tensor, img_height: int, img_width: int, block_width: int,
+                        background: Optional[Tensor] = None, return_alpha: Optional[bool] = False):
+    """Sort/bin the projected Gaussians per tile and alpha-composite them front to back.
+
+    Differentiable w.r.t. xys, conics, colors, opacity.  Returns out_img [H,W,C] (and out_alpha [H,W] =
+    1 - final transmittance when `return_alpha`).  `block_width` must equal the one given to
+    project_gaussians (rasterizer/rasterize.py:14-90)."""
+    assert block_width > 1 and block_width <= 16, "block_width must be between 2 and 16"
+    if colors.dtype == torch.uint8:
+        colors = colors.float() / 255
+    if background is not None:
+        assert background.shape[0] == colors.shape[-1], (
+            f"incorrect shape of background color tensor, expected shape {colors.shape[-1]}")
+    else:
+        background = torch.ones(colors.shape[-1], dtype=torch.float32, device=colors.device)
+    if xys.ndimension() != 2 or xys.size(1) != 2:
+        raise ValueError("xys must have dimensions (N, 2)")
+    if colors.ndimension() != 2:
+        raise ValueError("colors must have dimensions (N, D)")
+    return _RasterizeGaussians.apply(xys.contiguous(), depths.contiguous(), radii.contiguous(), conics.contiguous(),
+                                     num_tiles_hit.contiguous(), colors.contiguous(), opacity.contiguous(),
+                                     img_height, img_width, block_width, background.contiguous(), return_alpha)
+
+
+class _RasterizeGaussians(Function):
+    """autograd node: scan -> key emission -> radix sort -> bin edges -> blend, and the blend adjoint."""
+
+    @staticmethod
+    def forward(ctx, xys, depths, radii, conics, num_tiles_hit, colors, opacity, img_height, img_width, block_width,
+                background=None, return_alpha=False):
+        num_points = xys.size(0)
+        tile_bounds = ((img_width + block_width - 1) // block_width, (img_height + block_width - 1) // block_width, 1)
+        block = (block_width, block_width, 1)
+        img_size = (img_width, img_height, 1)
+        channels = colors.shape[-1]
+
+        num_intersects, cum_tiles_hit = compute_cumulative_intersects(num_tiles_hit)
+        if num_intersects < 1:
+            # empty scene: background image, zero-size bookkeeping (rasterizer/rasterize.py:119-127)
+            out_img = torch.ones(img_height, img_width, channels, device=xys.device) * background
+            gaussian_ids_sorted = torch.zeros(0, 1, device=xys.device)
+            tile_bins = torch.zeros(0, 2, device=xys.device)
+            final_Ts = torch.zeros(img_height, img_width, device=xys.device)
+            final_idx = torch.zeros(img_height, img_width, device=xys.device)
+        else:
+            _, _, _, gaussian_ids_sorted, tile_bins = bin_and_sort_gaussians(
+                num_points, num_intersects, xys, depths, radii, cum_tiles_hit, tile_bounds, block_width)
+            fwd = _C.rasterize_forward if channels == 3 else _C.nd_rasterize_forward
+            out_img, final_Ts, final_idx = fwd(tile_bounds, block, img_size, gaussian_ids_sorted, tile_bins, xys,
+                                               conics, colors, opacity, background)
+
+        ctx.meta = (img_height, img_width, block_width, num_intersects)
+        ctx.save_for_backward(gaussian_ids_sorted, tile_bins, xys, conics, colors, opacity, background, final_Ts,
+                              final_idx)
+        if return_alpha:
+            return out_img, 1 - final_Ts
+        return out_img
+
+    @staticmethod
+    def backward(ctx, v_out_img, v_out_alpha=None):
+        img_height, img_width, block_width, num_intersects = ctx.meta
+        if v_out_alpha is None:
+            v_out_alpha = torch.zeros_like(v_out_img[..., 0])
+        (gaussian_ids_sorted, tile_bins, xys, conics, colors, opacity, background, final_Ts,
+         final_idx) = ctx.saved_tensors
+        if num_intersects < 1:
+            v_xy, v_conic = torch.zeros_like(xys), torch.zeros_like(conics)
+            v_colors, v_opacity = torch.zeros_like(colors), torch.zeros_like(opacity)
+        else:
+            bwd = _C.rasterize_backward if colors.shape[-1] == 3 else _C.nd_rasterize_backward
+            v_xy, v_conic, v_colors, v_opacity = bwd(img_height, img_width, block_width, gaussian_ids_sorted,
+                                                     tile_bins, xys, conics, colors, opacity, background, final_Ts,
+                                                     final_idx, v_out_img, v_out_alpha)
+            v_opacity = v_opacity.view_as(opacity)
+        return (v_xy, None, None, v_conic, None, v_colors, v_opacity, None, None, None, None, None)

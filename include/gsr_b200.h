@@ -1,0 +1,181 @@
+/*
+ * gsr_b200.h — C ABI of the B200-native Gaussian-splatting rasterizer (libgsr_b200.so).
+ *
+ * This is the drop-in boundary for the hot path of Gaussian-Splatting-Toolkit's `rasterizer` package.
+ * Every entry point below replaces one pybind binding of the reference's native module
+ * (gs_toolkit/gs_components/rasterizer/cuda/csrc/ext.cpp:6-17, C++ signatures in bindings.h:19-115),
+ * or one ATen library call the reference's Python wrapper makes between those bindings
+ * (rasterizer/utils.py:123 torch.cumsum, :179-180 torch.sort + torch.gather).
+ *
+ * Conventions
+ *  - Plain C: pointers + sizes only. No torch / pybind types cross this boundary.
+ *  - Unless a name ends in `_host`, every pointer is a DEVICE pointer (cudaMalloc'd or carved from the
+ *    caller's allocator, e.g. torch's caching allocator) valid on the current CUDA device, and `stream`
+ *    is a `cudaStream_t` passed as `void*` (NULL = legacy default stream).  Calls are asynchronous with
+ *    respect to the host: they enqueue work on `stream` and return.
+ *  - All floating point is IEEE binary32, all arrays dense row-major ("contiguous"):
+ *    means3d/scales [N,3], quats [N,4] (w,x,y,z), viewmat row-major 3x4 or 4x4 (first 12 floats used),
+ *    projmat row-major 4x4 (= P * V), xys [N,2], conics [N,3] (a,b,c upper-triangular inverse cov2d),
+ *    cov3d [N,6] upper-triangular, colors [N,C], opacities [N], images [H,W,C], final_Ts / final_idx [H,W].
+ *    radii, num_tiles_hit, cum_tiles_hit, gaussian_ids, tile_bins [T,2], final_idx are int32;
+ *    isect_ids are int64 = (tile_id << 32) | bits(depth).
+ *  - Outputs are fully written by the call (no pre-zeroing by the caller is required; where the
+ *    reference relies on torch::zeros the call zero-fills on `stream` itself).
+ *  - Return value: 0 (GSR_OK) on success, a negative gsr_status otherwise; gsr_last_error() returns a
+ *    thread-local human-readable message for the last failure.  Launch errors are checked
+ *    (cudaGetLastError) after every launch — the reference never checks.
+ *  - Thread-safety: no global mutable state besides the thread-local error string; re-entrant per device.
+ */
+#ifndef GSR_B200_H
+#define GSR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define GSR_API __declspec(dllexport)
+#else
+#define GSR_API __attribute__((visibility("default")))
+#endif
+
+typedef enum gsr_status {
+  GSR_OK = 0,
+  GSR_ERR_INVALID_ARGUMENT = -1, /* bad sizes / block_width outside [2,16] / null pointer */
+  GSR_ERR_CUDA = -2,             /* a CUDA runtime call or kernel launch failed */
+  GSR_ERR_WORKSPACE = -3,        /* workspace too small */
+  GSR_ERR_UNSUPPORTED = -4       /* e.g. SH degree > 4, channels > GSR_MAX_CHANNELS */
+} gsr_status;
+
+#define GSR_MAX_CHANNELS 32
+
+/* library identification */
+GSR_API const char *gsr_version(void);      /* "0.1.2+b200.<n>": tracks rasterizer/version.py:1 */
+GSR_API const char *gsr_last_error(void);   /* thread-local message of the last non-zero return */
+GSR_API int gsr_built_for_sm(void);         /* 100 : the only arch in the fatbin is sm_100a */
+
+/* ------------------------------------------------------------------------------------------------
+ * Spherical harmonics  — replaces compute_sh_forward / compute_sh_backward
+ * (bindings.h:23-33, bindings.cu:58-103, kernels sh.cuh:33-224)
+ * degree = degree of the stored coefficients (K = (degree+1)^2 bases, degree <= 4),
+ * degrees_to_use <= degree.  coeffs [N,K,3], viewdirs [N,3] (normalised inside), colors [N,3].
+ * Backward writes ALL K*3 entries of v_coeffs (zeros for bases above degrees_to_use).
+ * ---------------------------------------------------------------------------------------------- */
+GSR_API int gsr_compute_sh_forward(int num_points, int degree, int degrees_to_use,
+                                   const float *viewdirs, const float *coeffs, float *colors,
+                                   void *stream);
+GSR_API int gsr_compute_sh_backward(int num_points, int degree, int degrees_to_use,
+                                    const float *viewdirs, const float *v_colors, float *v_coeffs,
+                                    void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * EWA projection — replaces project_gaussians_forward / project_gaussians_backward
+ * (bindings.h:35-55, bindings.cu:105-216, kernels forward.cu:13-90, backward.cu:305-453)
+ * Forward outputs: cov3d [N,6], xys [N,2], depths [N], radii [N] i32, conics [N,3], compensation [N],
+ * num_tiles_hit [N] i32.  Culled Gaussians get radii = num_tiles_hit = 0 and zeros elsewhere, except
+ * that cov3d / conics are written as far as the reference kernel writes them before its early returns
+ * (forward.cu:46-47,68).
+ * Backward outputs: v_cov2d [N,3], v_cov3d [N,6] (returned by the reference binding, discarded by its
+ * Python wrapper; may be NULL here), v_mean3d [N,3], v_scale [N,3], v_quat [N,4]; zero where radii<=0.
+ * ---------------------------------------------------------------------------------------------- */
+GSR_API int gsr_project_gaussians_forward(int num_points, const float *means3d, const float *scales,
+                                          float glob_scale, const float *quats, const float *viewmat,
+                                          const float *projmat, float fx, float fy, float cx, float cy,
+                                          unsigned img_height, unsigned img_width, unsigned block_width,
+                                          float clip_thresh, float *cov3d, float *xys, float *depths,
+                                          int32_t *radii, float *conics, float *compensation,
+                                          int32_t *num_tiles_hit, void *stream);
+GSR_API int gsr_project_gaussians_backward(int num_points, const float *means3d, const float *scales,
+                                           float glob_scale, const float *quats, const float *viewmat,
+                                           const float *projmat, float fx, float fy, float cx, float cy,
+                                           unsigned img_height, unsigned img_width, const float *cov3d,
+                                           const int32_t *radii, const float *conics,
+                                           const float *compensation, const float *v_xy,
+                                           const float *v_depth, const float *v_conic,
+                                           const float *v_compensation, float *v_cov2d /*nullable*/,
+                                           float *v_cov3d /*nullable*/, float *v_mean3d, float *v_scale,
+                                           float *v_quat, void *stream);
+
+/* compute_cov2d_bounds (bindings.h:19-21, bindings.cu:19-56): cov2d [N,3] -> conics [N,3], radii [N] f32 */
+GSR_API int gsr_compute_cov2d_bounds(int num_pts, const float *covs2d, float *conics, float *radii,
+                                     void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Tile binning
+ * gsr_cumsum_tiles_hit   replaces torch.cumsum(num_tiles_hit, int32) (rasterizer/utils.py:123).
+ *                        If total_host_pinned != NULL the total M is also written there (a pinned
+ *                        HOST int32 the caller reads after synchronising `stream`; replaces `.item()`).
+ * gsr_map_gaussian_to_intersects  replaces the binding of the same name (bindings.h:57-61,
+ *                        bindings.cu:218-251, kernel forward.cu:94-127).
+ * gsr_sort_intersects    replaces torch.sort(int64) + torch.gather (rasterizer/utils.py:179-180):
+ *                        stable ascending radix sort of the 64-bit keys carrying the int32 Gaussian ids;
+ *                        only the bits that can be set (32 depth bits + ceil(log2(num_tiles)) tile bits)
+ *                        are sorted.
+ * gsr_get_tile_bin_edges replaces the binding of the same name (bindings.h:63-66, bindings.cu:253-267,
+ *                        kernel forward.cu:132-154); tile_bins [num_tiles,2] is zero-filled first.
+ * Workspace: call the *_workspace_bytes query, hand in a device buffer of at least that size.
+ * ---------------------------------------------------------------------------------------------- */
+GSR_API size_t gsr_cumsum_workspace_bytes(int num_points);
+GSR_API int gsr_cumsum_tiles_hit(int num_points, const int32_t *num_tiles_hit, int32_t *cum_tiles_hit,
+                                 int32_t *total_host_pinned /*nullable*/, void *workspace,
+                                 size_t workspace_bytes, void *stream);
+GSR_API int gsr_map_gaussian_to_intersects(int num_points, int num_intersects, const float *xys,
+                                           const float *depths, const int32_t *radii,
+                                           const int32_t *cum_tiles_hit, unsigned tiles_x,
+                                           unsigned tiles_y, unsigned block_width, int64_t *isect_ids,
+                                           int32_t *gaussian_ids, void *stream);
+GSR_API size_t gsr_sort_workspace_bytes(int num_intersects);
+GSR_API int gsr_sort_intersects(int num_intersects, int num_tiles, const int64_t *isect_ids,
+                                const int32_t *gaussian_ids, int64_t *isect_ids_sorted,
+                                int32_t *gaussian_ids_sorted, void *workspace, size_t workspace_bytes,
+                                void *stream);
+GSR_API int gsr_get_tile_bin_edges(int num_intersects, const int64_t *isect_ids_sorted, int num_tiles,
+                                   int32_t *tile_bins, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Per-tile alpha compositing and its adjoint — replaces rasterize_forward / rasterize_backward
+ * (bindings.h:68-115, bindings.cu:269-328,471-528, kernels forward.cu:278-395, backward.cu:133-303)
+ * and the N-D variants nd_rasterize_forward / nd_rasterize_backward (bindings.cu:330-469,
+ * kernels forward.cu:159-276, backward.cu:23-131).
+ * Forward outputs: out_img [H,W,C], final_Ts [H,W], final_idx [H,W] i32 (absolute index into the sorted
+ * list of the last contributing Gaussian).
+ * Backward outputs: v_xy [N,2], v_conic [N,3], v_colors [N,C], v_opacity [N] — zero-filled by the call
+ * and accumulated with block-reduced atomics.
+ * The 3-channel calls compute in FP32.  The N-D calls (C != 3, 1 <= C <= GSR_MAX_CHANNELS) reproduce the
+ * reference's numerics: binary16 colour accumulators and a backward that excludes the last contributor
+ * (backward.cu:64-65) — see DESIGN.md "N-D variants".
+ * ---------------------------------------------------------------------------------------------- */
+GSR_API int gsr_rasterize_forward(unsigned img_height, unsigned img_width, unsigned block_width,
+                                  int num_points, const int32_t *gaussian_ids_sorted,
+                                  const int32_t *tile_bins, const float *xys, const float *conics,
+                                  const float *colors, const float *opacities, const float *background,
+                                  float *out_img, float *final_Ts, int32_t *final_idx, void *stream);
+GSR_API int gsr_rasterize_backward(unsigned img_height, unsigned img_width, unsigned block_width,
+                                   int num_points, const int32_t *gaussian_ids_sorted,
+                                   const int32_t *tile_bins, const float *xys, const float *conics,
+                                   const float *colors, const float *opacities, const float *background,
+                                   const float *final_Ts, const int32_t *final_idx,
+                                   const float *v_output, const float *v_output_alpha, float *v_xy,
+                                   float *v_conic, float *v_colors, float *v_opacity, void *stream);
+GSR_API int gsr_nd_rasterize_forward(unsigned img_height, unsigned img_width, unsigned block_width,
+                                     unsigned channels, int num_points,
+                                     const int32_t *gaussian_ids_sorted, const int32_t *tile_bins,
+                                     const float *xys, const float *conics, const float *colors,
+                                     const float *opacities, const float *background, float *out_img,
+                                     float *final_Ts, int32_t *final_idx, void *stream);
+GSR_API int gsr_nd_rasterize_backward(unsigned img_height, unsigned img_width, unsigned block_width,
+                                      unsigned channels, int num_points,
+                                      const int32_t *gaussian_ids_sorted, const int32_t *tile_bins,
+                                      const float *xys, const float *conics, const float *colors,
+                                      const float *opacities, const float *background,
+                                      const float *final_Ts, const int32_t *final_idx,
+                                      const float *v_output, const float *v_output_alpha, float *v_xy,
+                                      float *v_conic, float *v_colors, float *v_opacity, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSR_B200_H */

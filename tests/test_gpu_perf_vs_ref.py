@@ -1,0 +1,87 @@
+"""Side-by-side device timing of libgsr_b200 and the unmodified reference CUDA extension (oracle/_ref) on the
+BASELINE cfg2 view (1 M Gaussians, 1080p, SH degree 3, fwd+bwd), same inputs, same orchestration, CUDA events,
+5 warm-up + 20 timed iterations, median.  The numbers are written to gpurun_out/perf_vs_ref.json (and copied
+to profiles/ by hand); the test itself only asserts that both back-ends produced the same image."""
+import json
+import os
+import statistics
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _time_view(C, s, sort_impl, iters=20, warm=5):
+    from pipelines import run_view_bindings
+
+    times = []
+    out = None
+    for i in range(warm + iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = run_view_bindings(C, s, backward=True, sort_impl=sort_impl)
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= warm:
+            times.append(e0.elapsed_time(e1))
+    return statistics.median(times), out
+
+
+def _time_stages(C, s, sort_impl, iters=10):
+    """Per-binding device times via events around each native call (median over iters)."""
+    import pipelines
+
+    names = ["compute_sh_forward", "project_gaussians_forward", "map_gaussian_to_intersects", "get_tile_bin_edges",
+             "rasterize_forward", "rasterize_backward", "compute_sh_backward", "project_gaussians_backward",
+             "sort_intersects"]
+    acc = {n: [] for n in names}
+
+    class Timed:
+        def __getattr__(self, name):
+            fn = getattr(C, name)
+            if name not in acc:
+                return fn
+
+            def wrapped(*a, **k):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                r = fn(*a, **k)
+                e1.record()
+                acc[name].append((e0, e1))
+                return r
+
+            return wrapped
+
+    for _ in range(iters):
+        pipelines.run_view_bindings(Timed(), s, backward=True, sort_impl=sort_impl)
+    torch.cuda.synchronize()
+    return {n: statistics.median([a.elapsed_time(b) for a, b in v]) for n, v in acc.items() if v}
+
+
+def test_cfg2_ours_vs_reference_extension():
+    from oracle.build_ref import load_ref
+    from rasterizer import cuda as C
+    from rasterizer.synthetic import make_config_scene, scene_to_torch
+
+    ref_ext = load_ref()
+    if ref_ext is None:
+        pytest.skip("oracle/_ref/rasterizer_ref_cuda.so not present")
+    scene = make_config_scene("cfg2")
+    s = scene_to_torch(scene, "cuda")
+    t_ref, o_ref = _time_view(ref_ext, s, "torch")
+    t_ours, o_ours = _time_view(C, s, "gsr")
+    st_ref = _time_stages(ref_ext, s, "torch")
+    st_ours = _time_stages(C, s, "gsr")
+    rep = {"workload": "cfg2 1M Gaussians 1920x1080 SH3 fwd+bwd", "M": o_ours["num_intersects"],
+           "reference_ext_ms_per_view": t_ref, "ours_ms_per_view": t_ours, "speedup": t_ref / t_ours,
+           "reference_ext_views_per_s": 1e3 / t_ref, "ours_views_per_s": 1e3 / t_ours,
+           "reference_ext_stage_ms": st_ref, "ours_stage_ms": st_ours,
+           "note": "reference orchestration uses torch.cumsum/.item()/torch.sort/torch.gather as rasterizer/utils.py does"}
+    print(json.dumps(rep, indent=1))
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(rep, open(os.path.join(ROOT, "gpurun_out", "perf_vs_ref.json"), "w"), indent=1)
+    d = (o_ours["out_img"] - o_ref["out_img"]).abs()
+    assert float((d > 1e-4 * o_ref["out_img"].abs() + 1e-5).float().mean()) < 2e-3
