@@ -8,30 +8,17 @@
 //   * only the batches at or before max(final_idx) of the CTA are staged at all (the reference stages every
 //     batch of the tile and skips inside);
 //   * double-buffered shared-memory ring of packed records with register prefetch, one barrier per batch;
-//   * warp = 8x4 pixel sub-tile + the same conservative warp-uniform ellipse reject as the forward, so most
-//     (warp, Gaussian) pairs never reach the reduction;
+//   * warp = 8x4 pixel sub-tile; each warp compacts a batch to the Gaussians whose alpha >= 1/255 extent box
+//     overlaps its pixel rectangle (ballot compaction, blend_common.cuh) and only walks the survivors;
 //   * the 9 per-Gaussian partial sums are reduced across the warp with a transposing butterfly
 //     (8 values in 4+2+1+1+1 = 9 shuffles, + 5 for the ninth) instead of 9 x 5 = 45 shuffles
 //     (cg::reduce per value, backward.cu:275-278), and the nine totals end up in nine DIFFERENT lanes, so the
 //     global accumulation is ONE predicated RED instruction per (warp, Gaussian) instead of nine serial
 //     atomicAdds issued by lane 0 (backward.cu:279-300);
 //   * outputs are zero-filled by this call (cudaMemsetAsync) rather than by torch::zeros in the caller.
-#include "common.cuh"
+#include "blend_common.cuh"
 
 namespace gsr {
-
-// defined in blend_fwd.cu (same translation-unit-local copies kept identical on purpose)
-__device__ __forceinline__ void alpha_extents_b(float a, float b, float c, float opac, float &ex, float &ey) {
-  const float det = a * c - b * b;
-  const float tau2 = 2.f * __logf(255.f * opac);
-  if (!(tau2 >= 0.f)) {
-    ex = (opac == opac) ? -1e30f : __int_as_float(0x7fc00000);
-    ey = ex;
-    return;
-  }
-  ex = sqrtf(tau2 * c / det) * 1.001f + 0.01f;
-  ey = sqrtf(tau2 * a / det) * 1.001f + 0.01f;
-}
 
 // Sum 8 per-lane values across the warp.  On return, lane L with (L & 3) == 0 holds in v[0] the total of
 // value number ((L>>4)&1)*4 + ((L>>3)&1)*2 + ((L>>2)&1).
@@ -73,8 +60,7 @@ __device__ __forceinline__ float warp_sum(float x) {
   return x;
 }
 
-template <int MAX_THREADS>
-__global__ void __launch_bounds__(MAX_THREADS)
+__global__ void __launch_bounds__(BLEND_THREADS)
 blend_backward_kernel(int tiles_x, int img_w, int img_h, int block_width,
                       const int *__restrict__ gaussian_ids_sorted, const int2 *__restrict__ tile_bins,
                       const float2 *__restrict__ xys, const float *__restrict__ conics,
@@ -84,49 +70,43 @@ blend_backward_kernel(int tiles_x, int img_w, int img_h, int block_width,
                       const float *__restrict__ v_output_alpha, float *__restrict__ v_xy,
                       float *__restrict__ v_conic, float *__restrict__ v_colors,
                       float *__restrict__ v_opacity) {
-  __shared__ float4 s_rec[2][3][MAX_THREADS];
-  __shared__ int s_warp_max[MAX_THREADS / 32];
+  __shared__ float4 s_rec[2][3][BLEND_THREADS];
+  __shared__ unsigned char s_list[BLEND_THREADS / 32][BLEND_THREADS];
+  __shared__ int s_warp_max[BLEND_THREADS / 32];
 
   const unsigned full = 0xffffffffu;
   const int tile_x = blockIdx.x, tile_y = blockIdx.y;
   const int tile_id = tile_y * tiles_x + tile_x;
   const int tr = threadIdx.x, nthreads = blockDim.x, lane = tr & 31, warp = tr >> 5;
-
-  // thread -> pixel (same mapping as the forward kernel)
   int lx, ly;
-  if (block_width == 16) {
-    lx = ((warp & 1) << 3) + (lane & 7);
-    ly = ((warp >> 1) << 2) + (lane >> 3);
-  } else {
-    lx = tr % block_width;
-    ly = tr / block_width;
-  }
+  map_pixel(block_width, lx, ly);
   const int ipx = tile_x * block_width + lx, ipy = tile_y * block_width + ly;
   const bool inside = (ly < block_width) && (ipx < img_w) && (ipy < img_h);
   const float px = (float)ipx, py = (float)ipy;
   const int pix = inside ? (ipy * img_w + ipx) : 0;
 
-  const int wx0 = __reduce_min_sync(full, inside ? ipx : 0x7fffffff);
-  const int wx1 = __reduce_max_sync(full, inside ? ipx : -0x7fffffff);
-  const int wy0 = __reduce_min_sync(full, inside ? ipy : 0x7fffffff);
-  const int wy1 = __reduce_max_sync(full, inside ? ipy : -0x7fffffff);
-  const float fx0 = (float)wx0, fx1 = (float)wx1, fy0 = (float)wy0, fy1 = (float)wy1;
+  const float fx0 = (float)__reduce_min_sync(full, inside ? ipx : 0x7fffffff);
+  const float fx1 = (float)__reduce_max_sync(full, inside ? ipx : -0x7fffffff);
+  const float fy0 = (float)__reduce_min_sync(full, inside ? ipy : 0x7fffffff);
+  const float fy1 = (float)__reduce_max_sync(full, inside ? ipy : -0x7fffffff);
 
   const int2 range = tile_bins[tile_id];
 
   const float T_final = inside ? final_Ts[pix] : 1.f;
   float T = T_final;
-  float3 buffer = make_float3(0.f, 0.f, 0.f);
+  float buf_r = 0.f, buf_g = 0.f, buf_b = 0.f;
   // reference: bin_final = inside ? final_index : 0 (backward.cu:168); -1 for outside threads is
   // equivalent because they are never valid
   const int bin_final = inside ? final_idx[pix] : -1;
-  float3 v_out = make_float3(0.f, 0.f, 0.f);
-  float v_out_alpha = 0.f;
+  float vo_r = 0.f, vo_g = 0.f, vo_b = 0.f, vo_a = 0.f;
   if (inside) {
-    v_out = make_float3(v_output[3 * (size_t)pix], v_output[3 * (size_t)pix + 1], v_output[3 * (size_t)pix + 2]);
-    v_out_alpha = v_output_alpha[pix];
+    vo_r = v_output[3 * (size_t)pix];
+    vo_g = v_output[3 * (size_t)pix + 1];
+    vo_b = v_output[3 * (size_t)pix + 2];
+    vo_a = v_output_alpha[pix];
   }
-  const float bg_dot = background[0] * v_out.x + background[1] * v_out.y + background[2] * v_out.z;
+  // T_final * ra * v_out_alpha - T_final * ra * sum_c bg_c v_out_c  =  ra * c_final   (backward.cu:252-256)
+  const float c_final = T_final * (vo_a - (background[0] * vo_r + background[1] * vo_g + background[2] * vo_b));
 
   const int warp_bin_final = __reduce_max_sync(full, bin_final);
   if (lane == 0) s_warp_max[warp] = warp_bin_final;
@@ -134,7 +114,7 @@ blend_backward_kernel(int tiles_x, int img_w, int img_h, int block_width,
   int cta_bin_final = -1;
   for (int w = 0; w < (nthreads >> 5); ++w) cta_bin_final = max(cta_bin_final, s_warp_max[w]);
 
-  // process sorted indices [range.x, end) back to front
+  // only sorted indices [range.x, end) can be contributors of any pixel of this tile; walk them back to front
   const int end = min(range.y, cta_bin_final + 1);
   const int count = end - range.x;
   if (count <= 0) return;  // uniform across the CTA
@@ -153,73 +133,69 @@ blend_backward_kernel(int tiles_x, int img_w, int img_h, int block_width,
     else if (vi == 8) { dst_base = v_opacity; dst_stride = 1; }
   }
 
-  float4 r0, r1, r2;
-  auto fetch = [&](int idx) {
-    if (idx >= range.x) {
-      const int g = gaussian_ids_sorted[idx];
-      const float2 xy = xys[g];
-      const float opac = opacities[g];
-      const float a = conics[3 * (size_t)g], b = conics[3 * (size_t)g + 1], c = conics[3 * (size_t)g + 2];
-      float ex, ey;
-      alpha_extents_b(a, b, c, opac, ex, ey);
-      r0 = make_float4(xy.x, xy.y, opac, ex);
-      r1 = make_float4(a, b, c, ey);
-      r2 = make_float4(colors[3 * (size_t)g], colors[3 * (size_t)g + 1], colors[3 * (size_t)g + 2], __int_as_float(g));
-    }
-  };
-  fetch(end - 1 - tr);
+  BlendRecord rec;
+  if (end - 1 - tr >= range.x)
+    rec = gather_record(gaussian_ids_sorted[end - 1 - tr], xys, conics, colors, opacities);
 
   for (int b = 0; b < num_batches; ++b) {
     const int buf = b & 1;
-    const int batch_end = end - 1 - nthreads * b;  // sorted index held by slot 0
+    const int batch_end = end - 1 - nthreads * b;  // sorted index held by slot 0; slot t holds batch_end - t
     if (batch_end - tr >= range.x) {
-      s_rec[buf][0][tr] = r0;
-      s_rec[buf][1][tr] = r1;
-      s_rec[buf][2][tr] = r2;
+      s_rec[buf][0][tr] = rec.r0;
+      s_rec[buf][1][tr] = rec.r1;
+      s_rec[buf][2][tr] = rec.r2;
     }
     __syncthreads();
-    if (b + 1 < num_batches) fetch(batch_end - nthreads - tr);
-
+    {
+      const int nxt = batch_end - nthreads - tr;
+      if (nxt >= range.x) rec = gather_record(gaussian_ids_sorted[nxt], xys, conics, colors, opacities);
+    }
     const int batch_size = min(nthreads, batch_end + 1 - range.x);
-    for (int t = max(0, batch_end - warp_bin_final); t < batch_size; ++t) {
+    const int t_begin = max(0, batch_end - warp_bin_final);  // slots before it are behind every lane's last contributor
+    if (t_begin >= batch_size) continue;
+    const int n_list = compact_survivors(s_rec[buf][0], t_begin, batch_size, fx0, fx1, fy0, fy1, s_list[warp], lane);
+    for (int i = 0; i < n_list; ++i) {
+      const int t = s_list[warp][i];
       const float4 q0 = s_rec[buf][0][t];
       const float4 q1 = s_rec[buf][1][t];
-      if (q0.x + q0.w < fx0 || q0.x - q0.w > fx1 || q0.y + q1.w < fy0 || q0.y - q1.w > fy1) continue;
       const float dx = q0.x - px, dy = q0.y - py;
-      const float sigma = 0.5f * (q1.x * dx * dx + q1.z * dy * dy) + q1.y * dx * dy;
-      const float vis = __expf(-sigma);
-      const float opac = q0.z;
+      const float gx = q1.x * dx, gy = q1.z * dy;      // A dx, C dy
+      const float power = dx * (gx + q1.y * dy) + gy * dy;  // = -sigma log2(e)
+      const float vis = exp2f(power);
+      const float opac = q1.w;
       const float alpha = fminf(0.99f, opac * vis);
-      const bool valid = inside && (batch_end - t <= bin_final) && !(sigma < 0.f || alpha < 1.f / 255.f);
+      const bool valid = inside && (batch_end - t <= bin_final) && !(power > 0.f || alpha < 1.f / 255.f);
       if (!__any_sync(full, valid)) continue;
 
       float v[8];
       float v_opac_l = 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = 0.f;
+      for (int k = 0; k < 8; ++k) v[k] = 0.f;
       const float4 q2 = s_rec[buf][2][t];
       if (valid) {
         const float ra = 1.f / (1.f - alpha);
         T *= ra;
         const float fac = alpha * T;
-        v[0] = fac * v_out.x;
-        v[1] = fac * v_out.y;
-        v[2] = fac * v_out.z;
-        float v_alpha = 0.f;
-        v_alpha += (q2.x * T - buffer.x * ra) * v_out.x;
-        v_alpha += (q2.y * T - buffer.y * ra) * v_out.y;
-        v_alpha += (q2.z * T - buffer.z * ra) * v_out.z;
-        v_alpha += T_final * ra * v_out_alpha;
-        v_alpha += -T_final * ra * bg_dot;
-        buffer.x += q2.x * fac;
-        buffer.y += q2.y * fac;
-        buffer.z += q2.z * fac;
+        v[0] = fac * vo_r;
+        v[1] = fac * vo_g;
+        v[2] = fac * vo_b;
+        float v_alpha = (q2.x * T - buf_r * ra) * vo_r;
+        v_alpha += (q2.y * T - buf_g * ra) * vo_g;
+        v_alpha += (q2.z * T - buf_b * ra) * vo_b;
+        v_alpha += ra * c_final;
+        buf_r += q2.x * fac;
+        buf_g += q2.y * fac;
+        buf_b += q2.z * fac;
         const float v_sigma = -opac * vis * v_alpha;
-        v[3] = 0.5f * v_sigma * dx * dx;
+        // conic = -(2A, B, 2C) ln2 : v_conic = (0.5 v_sigma dx^2, v_sigma dx dy, 0.5 v_sigma dy^2)
+        const float hs = 0.5f * v_sigma;
+        v[3] = hs * dx * dx;
         v[4] = v_sigma * dx * dy;
-        v[5] = 0.5f * v_sigma * dy * dy;
-        v[6] = v_sigma * (q1.x * dx + q1.y * dy);
-        v[7] = v_sigma * (q1.y * dx + q1.z * dy);
+        v[5] = hs * dy * dy;
+        // v_xy = v_sigma * (a dx + b dy, b dx + c dy) with a = -2A ln2, b = -B ln2, c = -2C ln2
+        const float ws = -kLn2 * v_sigma;
+        v[6] = ws * (2.f * gx + q1.y * dy);
+        v[7] = ws * (q1.y * dx + 2.f * gy);
         v_opac_l = vis * v_alpha;
       }
       const float tot8 = warp_transpose_reduce8(v, lane);
@@ -259,7 +235,7 @@ extern "C" GSR_API int gsr_rasterize_backward(unsigned img_height, unsigned img_
   GSR_CUDA(cudaMemsetAsync(v_opacity, 0, sizeof(float) * (size_t)num_points, st));
   const dim3 grid(cdiv(img_width, block_width), cdiv(img_height, block_width), 1);
   const unsigned threads = cdiv(block_width * block_width, 32) * 32;
-  blend_backward_kernel<256><<<grid, threads, 0, st>>>(
+  blend_backward_kernel<<<grid, threads, 0, st>>>(
       (int)grid.x, (int)img_width, (int)img_height, (int)block_width, gaussian_ids_sorted,
       reinterpret_cast<const int2 *>(tile_bins), reinterpret_cast<const float2 *>(xys), conics, colors, opacities,
       background, final_Ts, final_idx, v_output, v_output_alpha, v_xy, v_conic, v_colors, v_opacity);

@@ -187,6 +187,42 @@ def map_gaussian_to_intersects(num_points: int, num_intersects: int, xys: Tensor
     return isect_ids, gaussian_ids
 
 
+def count_tiles_tight(xys: Tensor, radii: Tensor, conics: Tensor, opacities: Tensor, img_height: int, img_width: int,
+                      block_width: int) -> Tensor:
+    """Per-Gaussian number of bounding-box tiles in which some pixel can reach alpha >= 1/255 (exact, conservative
+    culling; see include/gsr_b200.h).  Always <= the reference's num_tiles_hit."""
+    _check_input(xys, "xys", torch.float32)
+    _check_input(radii, "radii", torch.int32)
+    _check_input(conics, "conics", torch.float32)
+    _check_input(opacities, "opacities", torch.float32)
+    n = xys.size(0)
+    out = torch.empty((n,), dtype=torch.int32, device=xys.device)
+    with _Guard(xys) as st:
+        _lib.check(_lib.load().gsr_count_tiles_tight(n, _ptr(xys), _ptr(radii), _ptr(conics), _ptr(opacities),
+                                                     int(img_height), int(img_width), int(block_width), _ptr(out), st),
+                   "count_tiles_tight")
+    return out
+
+
+def map_gaussian_to_intersects_tight(num_points: int, num_intersects: int, xys: Tensor, depths: Tensor, radii: Tensor,
+                                     conics: Tensor, opacities: Tensor, cum_tiles: Tensor, img_height: int,
+                                     img_width: int, block_width: int):
+    _check_input(xys, "xys", torch.float32)
+    _check_input(depths, "depths", torch.float32)
+    _check_input(radii, "radii", torch.int32)
+    _check_input(conics, "conics", torch.float32)
+    _check_input(opacities, "opacities", torch.float32)
+    _check_input(cum_tiles, "cum_tiles", torch.int32)
+    gaussian_ids = torch.empty((num_intersects,), dtype=torch.int32, device=xys.device)
+    isect_ids = torch.empty((num_intersects,), dtype=torch.int64, device=xys.device)
+    with _Guard(xys) as st:
+        _lib.check(_lib.load().gsr_map_gaussian_to_intersects_tight(
+            num_points, num_intersects, _ptr(xys), _ptr(depths), _ptr(radii), _ptr(conics), _ptr(opacities),
+            _ptr(cum_tiles), int(img_height), int(img_width), int(block_width), _ptr(isect_ids), _ptr(gaussian_ids),
+            st), "map_gaussian_to_intersects_tight")
+    return isect_ids, gaussian_ids
+
+
 def sort_intersects(isect_ids: Tensor, gaussian_ids: Tensor, num_tiles: int) -> Tuple[Tensor, Tensor]:
     """Stable radix sort of (key, Gaussian id) pairs (replaces torch.sort + torch.gather, utils.py:179-180)."""
     _check_input(isect_ids, "isect_ids", torch.int64)

@@ -8,8 +8,30 @@ import torch
 from torch import Tensor
 from torch.autograd import Function
 
+import os
+
 from . import cuda as _C
-from .utils import bin_and_sort_gaussians, compute_cumulative_intersects
+from .utils import bin_and_sort_gaussians, compute_cumulative_intersects, get_tile_bin_edges
+
+# GSR_TIGHT_BINNING=0 switches the internal binning of rasterize_gaussians back to the reference's
+# bounding-box lists (num_tiles_hit); the rendered image and the gradients are the same either way.
+_TIGHT = os.environ.get("GSR_TIGHT_BINNING", "1") != "0"
+
+
+def _bin_tight(xys, depths, radii, conics, opacity, img_height, img_width, block_width, tile_bounds):
+    """Internal binning with exact tile culling: only (Gaussian, tile) pairs in which some pixel can reach
+    alpha >= 1/255 are listed (a subset of the reference's bounding-box list, in the same order)."""
+    opac = opacity.reshape(-1)
+    tiles = _C.count_tiles_tight(xys, radii, conics, opac, img_height, img_width, block_width)
+    num_intersects, cum = compute_cumulative_intersects(tiles)
+    if num_intersects < 1:
+        return 0, None, None
+    isect_ids, gaussian_ids = _C.map_gaussian_to_intersects_tight(
+        xys.size(0), num_intersects, xys, depths, radii, conics, opac, cum, img_height, img_width, block_width)
+    num_tiles = tile_bounds[0] * tile_bounds[1]
+    isect_ids_sorted, gaussian_ids_sorted = _C.sort_intersects(isect_ids, gaussian_ids, num_tiles)
+    tile_bins = get_tile_bin_edges(num_intersects, isect_ids_sorted, tile_bounds)
+    return num_intersects, gaussian_ids_sorted, tile_bins
 
 
 def rasterize_gaussians(xys: Tensor, depths: Tensor, radii: Tensor, conics: Tensor, num_tiles_hit: Tensor,
@@ -49,7 +71,12 @@ class _RasterizeGaussians(Function):
         img_size = (img_width, img_height, 1)
         channels = colors.shape[-1]
 
-        num_intersects, cum_tiles_hit = compute_cumulative_intersects(num_tiles_hit)
+        if _TIGHT and opacity.dtype == torch.float32 and opacity.numel() == num_points:
+            num_intersects, gaussian_ids_sorted, tile_bins = _bin_tight(
+                xys, depths, radii, conics, opacity, img_height, img_width, block_width, tile_bounds)
+            cum_tiles_hit = None
+        else:
+            num_intersects, cum_tiles_hit = compute_cumulative_intersects(num_tiles_hit)
         if num_intersects < 1:
             # empty scene: background image, zero-size bookkeeping (rasterizer/rasterize.py:119-127)
             out_img = torch.ones(img_height, img_width, channels, device=xys.device) * background
@@ -58,8 +85,9 @@ class _RasterizeGaussians(Function):
             final_Ts = torch.zeros(img_height, img_width, device=xys.device)
             final_idx = torch.zeros(img_height, img_width, device=xys.device)
         else:
-            _, _, _, gaussian_ids_sorted, tile_bins = bin_and_sort_gaussians(
-                num_points, num_intersects, xys, depths, radii, cum_tiles_hit, tile_bounds, block_width)
+            if cum_tiles_hit is not None:
+                _, _, _, gaussian_ids_sorted, tile_bins = bin_and_sort_gaussians(
+                    num_points, num_intersects, xys, depths, radii, cum_tiles_hit, tile_bounds, block_width)
             fwd = _C.rasterize_forward if channels == 3 else _C.nd_rasterize_forward
             out_img, final_Ts, final_idx = fwd(tile_bounds, block, img_size, gaussian_ids_sorted, tile_bins, xys,
                                                conics, colors, opacity, background)

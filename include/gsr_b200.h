@@ -127,6 +127,21 @@ GSR_API int gsr_map_gaussian_to_intersects(int num_points, int num_intersects, c
                                            const int32_t *cum_tiles_hit, unsigned tiles_x,
                                            unsigned tiles_y, unsigned block_width, int64_t *isect_ids,
                                            int32_t *gaussian_ids, void *stream);
+/* Exact tile culling (no counterpart in the reference; used inside rasterize_gaussians in place of
+ * num_tiles_hit + gsr_map_gaussian_to_intersects).  Of the tiles in the reference's bounding box
+ * (helpers.cuh:11-34) only those are kept in which at least one pixel can reach alpha >= 1/255
+ * (forward.cu:360-363) — the reference `continue`s on every pixel of the dropped (Gaussian, tile) pairs, so
+ * images, final_Ts and all gradients are unchanged while the sort and both blend kernels see fewer pairs.
+ * gsr_count_tiles_tight writes the per-Gaussian kept-tile count; after gsr_cumsum_tiles_hit on those counts
+ * gsr_map_gaussian_to_intersects_tight emits keys / ids for exactly the kept pairs, in the reference's order. */
+GSR_API int gsr_count_tiles_tight(int num_points, const float *xys, const int32_t *radii, const float *conics,
+                                  const float *opacities, unsigned img_height, unsigned img_width,
+                                  unsigned block_width, int32_t *tiles_touched, void *stream);
+GSR_API int gsr_map_gaussian_to_intersects_tight(int num_points, int num_intersects, const float *xys,
+                                                 const float *depths, const int32_t *radii, const float *conics,
+                                                 const float *opacities, const int32_t *cum_tiles_touched,
+                                                 unsigned img_height, unsigned img_width, unsigned block_width,
+                                                 int64_t *isect_ids, int32_t *gaussian_ids, void *stream);
 GSR_API size_t gsr_sort_workspace_bytes(int num_intersects);
 GSR_API int gsr_sort_intersects(int num_intersects, int num_tiles, const int64_t *isect_ids,
                                 const int32_t *gaussian_ids, int64_t *isect_ids_sorted,

@@ -17,8 +17,9 @@ def _tile_bounds(W, H, bw):
     return ((W + bw - 1) // bw, (H + bw - 1) // bw, 1)
 
 
-def run_view_bindings(C, s, backward=True, sort_impl="torch"):
-    """s: scene dict of CUDA tensors (rasterizer.synthetic.scene_to_torch)."""
+def run_view_bindings(C, s, backward=True, sort_impl="torch", binning="reference"):
+    """s: scene dict of CUDA tensors (rasterizer.synthetic.scene_to_torch).
+    binning="tight" (ours only) lists only the (Gaussian, tile) pairs that can reach alpha >= 1/255."""
     H, W, bw = s["img_height"], s["img_width"], s["block_width"]
     N = s["means3d"].shape[0]
     tb = _tile_bounds(W, H, bw)
@@ -29,14 +30,21 @@ def run_view_bindings(C, s, backward=True, sort_impl="torch"):
     cov3d, xys, depths, radii, conics, comp, nth = C.project_gaussians_forward(
         N, s["means3d"], s["scales"], s["glob_scale"], s["quats"], s["viewmat"], s["projmat"], s["fx"], s["fy"],
         s["cx"], s["cy"], H, W, bw, s["clip_thresh"])
-    cum = torch.cumsum(nth, dim=0, dtype=torch.int32)
+    opac = s["opacities"].reshape(-1, 1).contiguous()
+    if binning == "tight":
+        tiles = C.count_tiles_tight(xys, radii, conics, opac.reshape(-1), H, W, bw)
+        cum = torch.cumsum(tiles, dim=0, dtype=torch.int32)
+    else:
+        cum = torch.cumsum(nth, dim=0, dtype=torch.int32)
     M = int(cum[-1].item())
     out = dict(rgb_sh=rgb_sh, colors=colors, cov3d=cov3d, xys=xys, depths=depths, radii=radii, conics=conics,
                compensation=comp, num_tiles_hit=nth, cum_tiles_hit=cum, num_intersects=M)
-    opac = s["opacities"].reshape(-1, 1).contiguous()
     if M < 1:
         return out
-    isect, gids = C.map_gaussian_to_intersects(N, M, xys, depths, radii, cum, tb, bw)
+    if binning == "tight":
+        isect, gids = C.map_gaussian_to_intersects_tight(N, M, xys, depths, radii, conics, opac.reshape(-1), cum, H, W, bw)
+    else:
+        isect, gids = C.map_gaussian_to_intersects(N, M, xys, depths, radii, cum, tb, bw)
     if sort_impl == "torch":
         ks, order = torch.sort(isect)
         vs = torch.gather(gids, 0, order)

@@ -272,3 +272,48 @@ def test_cov2d_bounds_and_cumsum(oracle):
     assert m == int(nth.sum()) and torch.equal(cum.cpu(), torch.cumsum(nth, 0, dtype=torch.int32))
     m0, cum0 = rasterizer.compute_cumulative_intersects(torch.zeros(0, dtype=torch.int32, device="cuda"))
     assert m0 == 0 and cum0.numel() == 0
+
+
+@pytest.mark.parametrize("name", ["cfg1_10k_256", "dense_3k_160x160_opaque", "ragged_4k_200x120_bw12_rot"])
+def test_tight_binning_is_exact(oracle, name):
+    """Exact tile culling: the kept (Gaussian, tile) pairs are a subset of the reference's bounding-box list, and
+    the image / final_Ts are BITWISE the same as with the reference list (dropped pairs are `continue`d on every
+    pixel by the reference); gradients agree to atomic-order noise."""
+    from pipelines import run_view_bindings
+    from rasterizer import cuda as C
+    from rasterizer.synthetic import scene_to_torch
+
+    scene = _scenes()[name]()
+    s = scene_to_torch(scene, "cuda")
+    a = run_view_bindings(C, s, sort_impl="gsr", binning="reference")
+    b = run_view_bindings(C, s, sort_impl="gsr", binning="tight")
+    assert b["num_intersects"] <= a["num_intersects"]
+    print(f"[tight] {name}: M {a['num_intersects']} -> {b['num_intersects']}")
+    tiles = C.count_tiles_tight(a["xys"], a["radii"], a["conics"], s["opacities"].contiguous(), s["img_height"],
+                                s["img_width"], s["block_width"])
+    assert bool((tiles <= a["num_tiles_hit"]).all()) and bool((tiles >= 0).all())
+    assert torch.equal(a["out_img"], b["out_img"]) and torch.equal(a["final_Ts"], b["final_Ts"])
+    # kept pairs form a subset: per tile, the tight list is a subsequence of the reference list
+    ka, kb = a["isect_ids_sorted"], b["isect_ids_sorted"]
+    pa = (ka >> 32) * (1 << 31) + a["gaussian_ids_sorted"].long()
+    pb = (kb >> 32) * (1 << 31) + b["gaussian_ids_sorted"].long()
+    assert bool(torch.isin(pb, pa).all())
+    for k in ("v_xy", "v_conic", "v_colors", "v_opacity", "v_coeffs", "v_mean3d", "v_scale", "v_quat"):
+        assert_float_parity(b[k], a[k], k, max_norm_rel=1e-5, max_frac_bad=1e-3)
+    ref = oracle.render_view(scene, scene["v_out_img"], scene["v_out_alpha"])
+    clean = ref["ambiguous"] == 0
+    assert_float_parity(b["out_img"], ref["out_img"], "out_img", mask=np.broadcast_to(clean[..., None], ref["out_img"].shape), max_frac_bad=1e-5)
+
+
+def test_tight_binning_degenerate_inputs_are_never_culled():
+    """Non-positive-definite conics / NaN opacity must not be culled (the reference evaluates them)."""
+    from rasterizer import cuda as C
+
+    n = 4
+    xys = torch.tensor([[20.0, 20.0]] * n, device="cuda")
+    radii = torch.full((n,), 40, dtype=torch.int32, device="cuda")
+    conics = torch.tensor([[1.0, 2.0, 1.0], [-1.0, 0.0, 1.0], [1.0, 0.0, 1.0], [50.0, 0.0, 50.0]], device="cuda")
+    opac = torch.tensor([0.9, 0.9, float("nan"), 0.9], device="cuda")
+    tiles = C.count_tiles_tight(xys, radii, conics, opac, 64, 64, 16)
+    assert tiles.tolist()[:3] == [16, 16, 16]   # whole 4x4 bounding box kept
+    assert tiles.tolist()[3] == 1               # a 0.5-pixel opaque blob at (20,20): only its own tile can see it
