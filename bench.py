@@ -168,15 +168,9 @@ class ResidentView:
             N, s["means3d"], s["scales"], s["glob_scale"], s["quats"], s["viewmat"], s["projmat"], s["fx"], s["fy"],
             s["cx"], s["cy"], H, W, bw, s["clip_thresh"])
         self._mark(rec)
-        # internal binning of rasterize_gaussians: exact tile culling (subset of the reference's bbox list)
-        opac_flat = self.opac.reshape(-1)
-        tiles = C.count_tiles_tight(xys, radii, conics, opac_flat, H, W, bw)
-        cum = C.cumsum_tiles_hit(tiles, self.pin_total)
-        torch.cuda.current_stream().synchronize()
-        M = self.M = int(self.pin_total.item())
-        isect, gids = C.map_gaussian_to_intersects_tight(N, M, xys, depths, radii, conics, opac_flat, cum, H, W, bw)
-        ks, vs = C.sort_intersects(isect, gids, self.tb[0] * self.tb[1])
-        bins = C.get_tile_bin_edges(M, ks, self.tb)
+        # internal binning of rasterize_gaussians: two-level sort + exact tile culling (same per-tile order)
+        M, vs, bins = C.bin_gaussians_fast(xys, depths, radii, conics, self.opac.reshape(-1), H, W, bw)
+        self.M = M
         self._mark(rec)
         img, fT, fi = C.rasterize_forward(self.tb, (bw, bw, 1), (W, H, 1), vs, bins, xys, conics, colors, self.opac,
                                           s["background"])
@@ -207,7 +201,12 @@ class ResidentView:
 
 
 class PublicApiView:
-    """One view through the public autograd API with HOST buffers for the per-view inputs/outputs (`e2e`)."""
+    """One view through the public autograd API with HOST buffers for the per-view inputs/outputs (`e2e`).
+
+    Every step copies that step's inputs (camera matrices, upstream image gradients) from pinned host memory and
+    reads the rendered image + alpha back into pinned host memory.  The two large transfers run on dedicated copy
+    streams so that PCIe traffic overlaps the kernels (H2D of the upstream gradients under the forward pass, D2H of
+    the image under the backward pass); device-side input buffers are double-buffered across steps."""
 
     def __init__(self, s, scene_np):
         import torch
@@ -226,7 +225,13 @@ class PublicApiView:
         self.h_img = torch.empty((H, W, 3), dtype=torch.float32).pin_memory()
         self.h_alpha = torch.empty((H, W), dtype=torch.float32).pin_memory()
         self.d_viewmat = torch.empty_like(s["viewmat"]); self.d_projmat = torch.empty_like(s["projmat"])
-        self.d_vimg = torch.empty((H, W, 3), device=dev); self.d_valpha = torch.empty((H, W), device=dev)
+        self.d_vimg = [torch.empty((H, W, 3), device=dev) for _ in range(2)]
+        self.d_valpha = [torch.empty((H, W), device=dev) for _ in range(2)]
+        self.h2d_stream, self.d2h_stream = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        self.buf_free = [torch.cuda.Event(), torch.cuda.Event()]
+        for e in self.buf_free:
+            e.record()
+        self.k = 0
         self.h2d = sum(t.numel() * t.element_size() for t in (self.h_viewmat, self.h_projmat, self.h_vimg, self.h_valpha))
         self.d2h = sum(t.numel() * t.element_size() for t in (self.h_img, self.h_alpha))
 
@@ -236,10 +241,18 @@ class PublicApiView:
 
         torch, s = self.torch, self.s
         H, W, bw = s["img_height"], s["img_width"], s["block_width"]
+        main = torch.cuda.current_stream()
+        i = self.k & 1
+        self.k += 1
+        # this step's inputs: cameras on the compute stream (128 B), upstream gradients on the H2D stream
         self.d_viewmat.copy_(self.h_viewmat, non_blocking=True)
         self.d_projmat.copy_(self.h_projmat, non_blocking=True)
-        self.d_vimg.copy_(self.h_vimg, non_blocking=True)
-        self.d_valpha.copy_(self.h_valpha, non_blocking=True)
+        self.h2d_stream.wait_event(self.buf_free[i])
+        with torch.cuda.stream(self.h2d_stream):
+            self.d_vimg[i].copy_(self.h_vimg, non_blocking=True)
+            self.d_valpha[i].copy_(self.h_valpha, non_blocking=True)
+            in_ready = torch.cuda.Event()
+            in_ready.record()
         for p in (self.means, self.scales, self.quats, self.coeffs, self.opac):
             p.grad = None
         xys, depths, radii, conics, comp, nth, cov3d = rasterizer.project_gaussians(
@@ -249,13 +262,28 @@ class PublicApiView:
         rgbs = torch.clamp(spherical_harmonics(s["degrees_to_use"], viewdirs, self.coeffs) + 0.5, min=0.0)
         img, alpha = rasterizer.rasterize_gaussians(xys, depths, radii, conics, nth, rgbs, self.opac, H, W, bw,
                                                     background=s["background"], return_alpha=True)
-        self.h_img.copy_(img.detach(), non_blocking=True)
-        self.h_alpha.copy_(alpha.detach(), non_blocking=True)
-        torch.autograd.backward([img, alpha], [self.d_vimg, self.d_valpha])
+        # this step's result goes back to the host on the D2H stream, under the backward pass
+        fwd_done = torch.cuda.Event()
+        fwd_done.record()
+        self.d2h_stream.wait_event(fwd_done)
+        with torch.cuda.stream(self.d2h_stream):
+            img_d, alpha_d = img.detach(), alpha.detach()
+            self.h_img.copy_(img_d, non_blocking=True)
+            self.h_alpha.copy_(alpha_d, non_blocking=True)
+            img_d.record_stream(self.d2h_stream)
+            alpha_d.record_stream(self.d2h_stream)
+        main.wait_event(in_ready)
+        torch.autograd.backward([img, alpha], [self.d_vimg[i], self.d_valpha[i]])
+        self.buf_free[i].record()
         return (self.coeffs.grad, self.means.grad, self.scales.grad, self.quats.grad, self.opac.grad)
 
+    def finish(self):
+        """Called inside the timed region after the last step: all transfers of all steps have landed."""
+        self.torch.cuda.current_stream().wait_stream(self.d2h_stream)
+        self.torch.cuda.current_stream().wait_stream(self.h2d_stream)
 
-def timed_loop(torch, dist, world, fn, steps, warmup):
+
+def timed_loop(torch, dist, world, fn, steps, warmup, finish=None):
     """W untimed + exactly K timed steps, barrier + synchronize on both sides, CUDA events, max over ranks."""
     for _ in range(warmup):
         fn()
@@ -267,6 +295,8 @@ def timed_loop(torch, dist, world, fn, steps, warmup):
     e0.record()
     for _ in range(steps):
         fn()
+    if finish is not None:
+        finish()
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -408,7 +438,7 @@ def main():
         grads = pv.step()
         allreduce(grads)
 
-    e2e_ms = timed_loop(torch, dist, world, e2e_step, args.steps, args.warmup)
+    e2e_ms = timed_loop(torch, dist, world, e2e_step, args.steps, args.warmup, finish=pv.finish)
     e2e_value = world * args.steps / (e2e_ms * 1e-3)
 
     if rank == 0:
@@ -440,8 +470,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": pv.h2d,
                     "d2h_bytes_per_step": pv.d2h,
                     "api": "rasterizer.project_gaussians + spherical_harmonics + rasterize_gaussians + autograd backward"},
-            "gpu_launches": 8 * args.steps,
-            "gpu_launches_note": "own kernels per step: sh_fwd, project_fwd, map_intersects, tile_bin_edges, blend_fwd, "
+            "gpu_launches": 10 * args.steps,
+            "gpu_launches_note": "own kernels per step: sh_fwd, project_fwd, depth_keys, count_sorted, emit_sorted, bin_edges, blend_fwd, "
                                  "blend_bwd, sh_bwd, project_bwd (+ CUB scan/sort and cudaMemset not counted) ; counted for the "
                                  "resident leg only",
             "clocks": clocks, "roofline": roofline,

@@ -21,17 +21,7 @@ _TIGHT = os.environ.get("GSR_TIGHT_BINNING", "1") != "0"
 def _bin_tight(xys, depths, radii, conics, opacity, img_height, img_width, block_width, tile_bounds):
     """Internal binning with exact tile culling: only (Gaussian, tile) pairs in which some pixel can reach
     alpha >= 1/255 are listed (a subset of the reference's bounding-box list, in the same order)."""
-    opac = opacity.reshape(-1)
-    tiles = _C.count_tiles_tight(xys, radii, conics, opac, img_height, img_width, block_width)
-    num_intersects, cum = compute_cumulative_intersects(tiles)
-    if num_intersects < 1:
-        return 0, None, None
-    isect_ids, gaussian_ids = _C.map_gaussian_to_intersects_tight(
-        xys.size(0), num_intersects, xys, depths, radii, conics, opac, cum, img_height, img_width, block_width)
-    num_tiles = tile_bounds[0] * tile_bounds[1]
-    isect_ids_sorted, gaussian_ids_sorted = _C.sort_intersects(isect_ids, gaussian_ids, num_tiles)
-    tile_bins = get_tile_bin_edges(num_intersects, isect_ids_sorted, tile_bounds)
-    return num_intersects, gaussian_ids_sorted, tile_bins
+    return _C.bin_gaussians_fast(xys, depths, radii, conics, opacity.reshape(-1), img_height, img_width, block_width)
 
 
 def rasterize_gaussians(xys: Tensor, depths: Tensor, radii: Tensor, conics: Tensor, num_tiles_hit: Tensor,

@@ -142,6 +142,28 @@ GSR_API int gsr_map_gaussian_to_intersects_tight(int num_points, int num_interse
                                                  const float *opacities, const int32_t *cum_tiles_touched,
                                                  unsigned img_height, unsigned img_width, unsigned block_width,
                                                  int64_t *isect_ids, int32_t *gaussian_ids, void *stream);
+/* Fast internal binning of rasterize_gaussians (replaces, as a whole, the reference's forward orchestration
+ * cumsum -> map_gaussian_to_intersects -> torch.sort(int64) -> torch.gather -> get_tile_bin_edges,
+ * rasterizer/rasterize.py:106-138 + utils.py:106-182).  Same per-tile order as the reference (depth ascending,
+ * ties in Gaussian-index order) obtained with a two-level sort: Gaussians by depth (32-bit keys), then the
+ * emitted (tile, id) pairs stably by tile id only (ceil(log2 T) bits); with exact tile culling as above.
+ *   gsr_bin_prepare   : perm [N] i32 (Gaussian ids in depth order), cum_tiles [N] i32 (inclusive scan of the kept
+ *                       tile counts in that order), masks [N] u64 (kept tiles of each bounding box);
+ *                       the total M is copied to *total_host_pinned (pinned host int32) on `stream`.
+ *   gsr_bin_emit_sort : after the caller has read M: gaussian_ids_sorted [M] i32, tile_bins [T,2] i32. */
+GSR_API size_t gsr_bin_prepare_workspace_bytes(int num_points);
+GSR_API int gsr_bin_prepare(int num_points, const float *xys, const float *depths, const int32_t *radii,
+                            const float *conics, const float *opacities, unsigned img_height,
+                            unsigned img_width, unsigned block_width, int32_t *perm, int32_t *cum_tiles,
+                            uint64_t *masks, int32_t *total_host_pinned, void *workspace, size_t workspace_bytes,
+                            void *stream);
+GSR_API size_t gsr_bin_emit_workspace_bytes(int num_intersects);
+GSR_API int gsr_bin_emit_sort(int num_points, int num_intersects, const float *xys, const int32_t *radii,
+                              const float *conics, const float *opacities, const int32_t *perm,
+                              const int32_t *cum_tiles, const uint64_t *masks,
+                              unsigned img_height, unsigned img_width, unsigned block_width,
+                              int32_t *gaussian_ids_sorted, int32_t *tile_bins, void *workspace,
+                              size_t workspace_bytes, void *stream);
 GSR_API size_t gsr_sort_workspace_bytes(int num_intersects);
 GSR_API int gsr_sort_intersects(int num_intersects, int num_tiles, const int64_t *isect_ids,
                                 const int32_t *gaussian_ids, int64_t *isect_ids_sorted,

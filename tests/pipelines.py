@@ -39,18 +39,26 @@ def run_view_bindings(C, s, backward=True, sort_impl="torch", binning="reference
     M = int(cum[-1].item())
     out = dict(rgb_sh=rgb_sh, colors=colors, cov3d=cov3d, xys=xys, depths=depths, radii=radii, conics=conics,
                compensation=comp, num_tiles_hit=nth, cum_tiles_hit=cum, num_intersects=M)
+    if binning == "fast":  # the product path of rasterize_gaussians: two-level sort + exact tile culling
+        M, vs, bins = C.bin_gaussians_fast(xys, depths, radii, conics, opac.reshape(-1), H, W, bw)
+        out["num_intersects"] = M
     if M < 1:
         return out
-    if binning == "tight":
+    if binning == "fast":
+        isect = gids = ks = None
+    elif binning == "tight":
         isect, gids = C.map_gaussian_to_intersects_tight(N, M, xys, depths, radii, conics, opac.reshape(-1), cum, H, W, bw)
     else:
         isect, gids = C.map_gaussian_to_intersects(N, M, xys, depths, radii, cum, tb, bw)
-    if sort_impl == "torch":
+    if binning == "fast":
+        pass
+    elif sort_impl == "torch":
         ks, order = torch.sort(isect)
         vs = torch.gather(gids, 0, order)
     else:
         ks, vs = C.sort_intersects(isect, gids, tb[0] * tb[1])
-    bins = C.get_tile_bin_edges(M, ks, tb)
+    if binning != "fast":
+        bins = C.get_tile_bin_edges(M, ks, tb)
     img, fT, fi = C.rasterize_forward(tb, (bw, bw, 1), (W, H, 1), vs, bins, xys, conics, colors, opac,
                                       s["background"])
     out.update(isect_ids=isect, gaussian_ids=gids, isect_ids_sorted=ks, gaussian_ids_sorted=vs, tile_bins=bins,

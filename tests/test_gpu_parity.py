@@ -317,3 +317,43 @@ def test_tight_binning_degenerate_inputs_are_never_culled():
     tiles = C.count_tiles_tight(xys, radii, conics, opac, 64, 64, 16)
     assert tiles.tolist()[:3] == [16, 16, 16]   # whole 4x4 bounding box kept
     assert tiles.tolist()[3] == 1               # a 0.5-pixel opaque blob at (20,20): only its own tile can see it
+
+
+@pytest.mark.parametrize("name", ["cfg1_10k_256", "dense_3k_160x160_opaque", "ragged_4k_200x120_bw12_rot", "deg0_700_80x48_bw2"])
+def test_fast_binning_matches_key_sort(name):
+    """The two-level sort (depth sort of Gaussians, then stable tile sort) yields exactly the list the reference
+    order defines: identical gaussian_ids_sorted and tile_bins as sorting the 64-bit (tile | depth) keys."""
+    from pipelines import run_view_bindings
+    from rasterizer import cuda as C
+    from rasterizer.synthetic import scene_to_torch
+
+    s = scene_to_torch(_scenes()[name](), "cuda")
+    a = run_view_bindings(C, s, backward=False, sort_impl="gsr", binning="tight")
+    m, ids, bins = C.bin_gaussians_fast(a["xys"], a["depths"], a["radii"], a["conics"], s["opacities"].contiguous(),
+                                        s["img_height"], s["img_width"], s["block_width"])
+    assert m == a["num_intersects"]
+    assert torch.equal(ids, a["gaussian_ids_sorted"])
+    assert torch.equal(bins, a["tile_bins"])
+
+
+def test_fast_binning_large_boxes_and_ties():
+    """Bounding boxes with more than 64 tiles (mask overflow path) and exact depth ties (stable order)."""
+    from rasterizer import cuda as C
+
+    n = 64
+    g = torch.Generator().manual_seed(5)
+    xys = (torch.rand(n, 2, generator=g) * 300).cuda()
+    depths = torch.full((n,), 3.0).cuda()          # all tied: order must be Gaussian-index order
+    depths[::7] = 2.0
+    radii = torch.randint(1, 200, (n,), generator=g, dtype=torch.int32).cuda()   # many boxes > 64 tiles
+    conics = torch.tensor([[1e-4, 0.0, 1e-4]]).repeat(n, 1).cuda()
+    opac = torch.full((n,), 0.8).cuda()
+    H = W = 320
+    tiles = C.count_tiles_tight(xys, radii, conics, opac, H, W, 16)
+    cum = torch.cumsum(tiles, 0, dtype=torch.int32)
+    M = int(cum[-1])
+    isect, gids = C.map_gaussian_to_intersects_tight(n, M, xys, depths, radii, conics, opac, cum, H, W, 16)
+    ks, vs = C.sort_intersects(isect, gids, 400)
+    bins = C.get_tile_bin_edges(M, ks, (20, 20, 1))
+    m, ids, bins2 = C.bin_gaussians_fast(xys, depths, radii, conics, opac, H, W, 16)
+    assert m == M and torch.equal(ids, vs) and torch.equal(bins2, bins)
