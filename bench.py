@@ -133,7 +133,7 @@ class ResidentView:
 
     STAGES = ["sh_fwd", "project_fwd", "binning", "blend_fwd", "blend_bwd", "sh_bwd", "project_bwd"]
 
-    def __init__(self, s, flat_grads=None):
+    def __init__(self, s, bucket=None):
         import torch
         from rasterizer import cuda as C
 
@@ -148,7 +148,7 @@ class ResidentView:
         self.pin_total = torch.zeros(1, dtype=torch.int32).pin_memory()
         self.events = []
         self.M = 0
-        self.flat = flat_grads
+        self.bucket = bucket  # view_parallel.GradientBucket: backward kernels write straight into its segments
 
     def _mark(self, rec):
         if rec is not None:
@@ -176,16 +176,20 @@ class ResidentView:
                                           s["background"])
         alpha = 1 - fT
         self._mark(rec)
-        v_xy, v_conic, v_colors, v_opacity = C.rasterize_backward(H, W, bw, vs, bins, xys, conics, colors, self.opac,
-                                                                  s["background"], fT, fi, s["v_out_img"],
-                                                                  s["v_out_alpha"])
+        bk = self.bucket
+        v_xy, v_conic, v_colors, v_opacity = C.rasterize_backward(
+            H, W, bw, vs, bins, xys, conics, colors, self.opac, s["background"], fT, fi, s["v_out_img"],
+            s["v_out_alpha"], out_opacity=None if bk is None else bk["v_opacity"])
         self._mark(rec)
         v_rgb_sh = torch.where(rgb_sh + 0.5 > 0, v_colors, torch.zeros_like(v_colors))
-        v_coeffs = C.compute_sh_backward(N, self.degree, s["degrees_to_use"], self.viewdirs, v_rgb_sh)
+        v_coeffs = C.compute_sh_backward(N, self.degree, s["degrees_to_use"], self.viewdirs, v_rgb_sh,
+                                         out=None if bk is None else bk["v_coeffs"])
         self._mark(rec)
         _, _, v_mean, v_scale, v_quat = C.project_gaussians_backward(
             N, s["means3d"], s["scales"], s["glob_scale"], s["quats"], s["viewmat"], s["projmat"], s["fx"], s["fy"],
-            s["cx"], s["cy"], H, W, cov3d, radii, conics, comp, v_xy, self.zeros_n, v_conic, self.zeros_n)
+            s["cx"], s["cy"], H, W, cov3d, radii, conics, comp, v_xy, self.zeros_n, v_conic, self.zeros_n,
+            out_mean3d=None if bk is None else bk["v_mean3d"], out_scale=None if bk is None else bk["v_scale"],
+            out_quat=None if bk is None else bk["v_quat"])
         self._mark(rec)
         if rec is not None:
             self.events.append(rec)
@@ -392,25 +396,31 @@ def main():
     H, W, bw = s["img_height"], s["img_width"], s["block_width"]
     P, T = H * W, ((W + bw - 1) // bw) * ((H + bw - 1) // bw)
 
-    # flat gradient bucket for the view-parallel all-reduce: 48 (SH) + 3 + 3 + 4 + 1 = 59 floats / Gaussian
-    flat = torch.zeros(59 * N, device=s["means3d"].device) if world > 1 else None
+    # flat gradient bucket for the view-parallel all-reduce: 48 (SH) + 3 + 3 + 4 + 1 = 59 floats / Gaussian; the
+    # backward kernels of the resident leg write straight into its segments, the autograd leg packs into it
+    from rasterizer.view_parallel import SEGMENTS, GradientBucket
 
-    def allreduce(grads):
+    bucket = GradientBucket(N, s["sh_coeffs"].shape[1], device=s["means3d"].device) if world > 1 else None
+    ar_events = []
+
+    def allreduce(grads, timed=False):
         if world == 1:
             return
-        off = 0
-        for g in grads:
-            n = g.numel()
-            flat[off:off + n].copy_(g.reshape(-1))
-            off += n
-        dist.all_reduce(flat)
+        bucket.pack(dict(zip(SEGMENTS, grads)))
+        if timed:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        bucket.all_reduce()
+        if timed:
+            e1.record()
+            ar_events.append((e0, e1))
 
-    rv = ResidentView(s)
+    rv = ResidentView(s, bucket)
     recording = {"on": False}
 
     def resident_step():
         _, _, grads = rv.step(record=recording["on"])
-        allreduce(grads)
+        allreduce(grads, timed=recording["on"])
 
     sampler = ClockSampler(local_rank)
     # warm-up outside, then the timed region with stage events
@@ -424,6 +434,8 @@ def main():
     ms_per_step = ms_total / args.steps
     value = world * args.steps / (ms_total * 1e-3)
     stages = rv.stage_ms()
+    if ar_events:
+        stages["grad_allreduce"] = sum(a.elapsed_time(b) for a, b in ar_events) / len(ar_events)
     M = rv.M
     with torch.no_grad():
         _nth = rv.C.project_gaussians_forward(N, s["means3d"], s["scales"], s["glob_scale"], s["quats"], s["viewmat"],
@@ -471,7 +483,7 @@ def main():
                     "d2h_bytes_per_step": pv.d2h,
                     "api": "rasterizer.project_gaussians + spherical_harmonics + rasterize_gaussians + autograd backward"},
             "gpu_launches": 10 * args.steps,
-            "gpu_launches_note": "own kernels per step: sh_fwd, project_fwd, depth_keys, count_sorted, emit_sorted, bin_edges, blend_fwd, "
+            "gpu_launches_note": "own kernels per step: sh_fwd, project_fwd, depth_keys, count_tiles, emit_sorted, bin_edges, blend_fwd, "
                                  "blend_bwd, sh_bwd, project_bwd (+ CUB scan/sort and cudaMemset not counted) ; counted for the "
                                  "resident leg only",
             "clocks": clocks, "roofline": roofline,

@@ -6,15 +6,18 @@
 // 16-byte pairs.  The order it defines is: tile ascending, then depth ascending, ties in Gaussian-index order
 // (CUB's radix sort is stable).  The same order is produced here with far less traffic by a two-level sort:
 //   1. sort the N Gaussians once by depth (32-bit keys, stable => ties stay in index order);
-//   2. count, per Gaussian in depth order, the tiles of its bounding box that can be reached with
+//   2. count, per Gaussian, the tiles of its bounding box that can be reached with
 //      alpha >= 1/255 (exact tile culling, see binning.cu) and remember them in a 64-bit mask;
-//   3. exclusive scan -> offsets; the total M goes to a pinned host word;
+//   3. inclusive scan of the counts read through the depth permutation -> offsets in depth order; the total M
+//      goes to a pinned host word;
 //   4. emit (tile id, Gaussian id) pairs in depth order;
 //   5. STABLE radix sort of the pairs by tile id only: ceil(log2(T)) bits = 2 passes over 8-byte pairs;
 //   6. bin edges.
 // All of it is HBM-bound integer work; see DESIGN.md for the byte counts.
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+
+#include <thrust/iterator/permutation_iterator.h>
 
 #include "common.cuh"
 
@@ -51,17 +54,16 @@ depth_keys_kernel(int n, const float *__restrict__ depths, const int *__restrict
   ids[i] = i;
 }
 
-// per depth-sorted slot j: number of reachable tiles of Gaussian perm[j] and their mask (bit k = k-th tile of the
-// bounding box in row-major order; only meaningful for boxes of at most 64 tiles — larger boxes are re-tested
-// tile by tile when emitting).
+// per Gaussian g (original order => coalesced loads): number of reachable tiles and their mask (bit k = k-th tile
+// of the bounding box in row-major order; only meaningful for boxes of at most 64 tiles — larger boxes are
+// re-tested tile by tile when emitting).
 __global__ void __launch_bounds__(FB_THREADS)
-count_sorted_kernel(int n, const int *__restrict__ perm, const float2 *__restrict__ xys,
-                    const int *__restrict__ radii, const float *__restrict__ conics,
-                    const float *__restrict__ opacities, int tiles_x, int tiles_y, int block_width, int img_w,
-                    int img_h, int *__restrict__ counts, unsigned long long *__restrict__ masks) {
-  const int j = blockIdx.x * FB_THREADS + threadIdx.x;
-  if (j >= n) return;
-  const int g = perm[j];
+count_tiles_kernel(int n, const float2 *__restrict__ xys, const int *__restrict__ radii,
+                   const float *__restrict__ conics, const float *__restrict__ opacities, int tiles_x, int tiles_y,
+                   int block_width, int img_w, int img_h, int *__restrict__ counts,
+                   unsigned long long *__restrict__ masks) {
+  const int g = blockIdx.x * FB_THREADS + threadIdx.x;
+  if (g >= n) return;
   const int r = radii[g];
   int count = 0;
   unsigned long long mask = 0ull;
@@ -91,8 +93,8 @@ count_sorted_kernel(int n, const int *__restrict__ perm, const float2 *__restric
       }
     }
   }
-  counts[j] = count;
-  masks[j] = mask;
+  counts[g] = count;
+  masks[g] = mask;
 }
 
 __global__ void __launch_bounds__(FB_THREADS)
@@ -133,7 +135,7 @@ emit_sorted_kernel(int n, const int *__restrict__ perm, const float2 *__restrict
       }
     }
   } else {
-    unsigned long long m = masks[j];
+    unsigned long long m = masks[g];
     while (m) {
       const int k = __ffsll((long long)m) - 1;
       m &= m - 1;
@@ -177,7 +179,9 @@ GSR_API size_t gsr_bin_prepare_workspace_bytes(int num_points) {
   size_t sort_b = 0, scan_b = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, sort_b, (const unsigned *)nullptr, (unsigned *)nullptr,
                                   (const int *)nullptr, (int *)nullptr, (int)n, 0, 32);
-  cub::DeviceScan::InclusiveSum(nullptr, scan_b, (const int *)nullptr, (int *)nullptr, (int)n);
+  cub::DeviceScan::InclusiveSum(nullptr, scan_b,
+                                thrust::make_permutation_iterator((const int *)nullptr, (const int *)nullptr),
+                                (int *)nullptr, (int)n);
   // keys_in, keys_out, ids_in, counts + cub temp
   return 4 * align256(4 * n) + align256(sort_b > scan_b ? sort_b : scan_b) + 256;
 }
@@ -215,13 +219,16 @@ GSR_API int gsr_bin_prepare(int num_points, const float *xys, const float *depth
   GSR_CHECK_LAUNCH("depth_keys_kernel");
   GSR_CUDA(cub::DeviceRadixSort::SortPairs(cub_ws, cub_bytes, keys_in, keys_out, ids_in, perm, num_points, 0, 32, st));
   const int tiles_x = cdiv(img_width, block_width), tiles_y = cdiv(img_height, block_width);
-  count_sorted_kernel<<<grid, FB_THREADS, 0, st>>>(num_points, perm, reinterpret_cast<const float2 *>(xys), radii,
-                                                   conics, opacities, tiles_x, tiles_y, (int)block_width,
-                                                   (int)img_width, (int)img_height, counts,
-                                                   reinterpret_cast<unsigned long long *>(masks));
-  GSR_CHECK_LAUNCH("count_sorted_kernel");
+  count_tiles_kernel<<<grid, FB_THREADS, 0, st>>>(num_points, reinterpret_cast<const float2 *>(xys), radii, conics,
+                                                  opacities, tiles_x, tiles_y, (int)block_width, (int)img_width,
+                                                  (int)img_height, counts,
+                                                  reinterpret_cast<unsigned long long *>(masks));
+  GSR_CHECK_LAUNCH("count_tiles_kernel");
+  // inclusive scan of the counts read THROUGH the depth permutation: cum[j] = sum_{i<=j} counts[perm[i]]
   cub_bytes = workspace_bytes - (size_t)(ws - (char *)workspace);
-  GSR_CUDA(cub::DeviceScan::InclusiveSum(cub_ws, cub_bytes, counts, cum_tiles, num_points, st));
+  GSR_CUDA(cub::DeviceScan::InclusiveSum(cub_ws, cub_bytes,
+                                         thrust::make_permutation_iterator((const int *)counts, (const int *)perm),
+                                         cum_tiles, num_points, st));
   if (total_host_pinned)
     GSR_CUDA(cudaMemcpyAsync(total_host_pinned, cum_tiles + (num_points - 1), sizeof(int32_t),
                              cudaMemcpyDeviceToHost, st));

@@ -74,7 +74,22 @@ def compute_sh_forward(num_points: int, degree: int, degrees_to_use: int, viewdi
     return colors
 
 
-def compute_sh_backward(num_points: int, degree: int, degrees_to_use: int, viewdirs: Tensor, v_colors: Tensor) -> Tensor:
+def _out_or_empty(out, shape, dev, name):
+    """Optional caller-provided output (e.g. a segment of view_parallel.GradientBucket): must be a contiguous
+    float32 CUDA tensor with the right number of elements."""
+    if out is None:
+        return torch.empty(shape, dtype=torch.float32, device=dev)
+    _check_input(out, name, torch.float32)
+    n = 1
+    for d in shape:
+        n *= d
+    if out.numel() != n or out.device != dev:
+        raise RuntimeError(f"{name}: expected {n} float32 elements on {dev}")
+    return out.view(shape)
+
+
+def compute_sh_backward(num_points: int, degree: int, degrees_to_use: int, viewdirs: Tensor, v_colors: Tensor, *,
+                        out: Tensor = None) -> Tensor:
     _check_input(viewdirs, "viewdirs", torch.float32)
     _check_input(v_colors, "v_colors", torch.float32)
     if viewdirs.dim() != 2 or viewdirs.size(0) != num_points or viewdirs.size(1) != 3:
@@ -82,7 +97,7 @@ def compute_sh_backward(num_points: int, degree: int, degrees_to_use: int, viewd
     if v_colors.dim() != 2 or v_colors.size(0) != num_points or v_colors.size(1) != 3:
         raise RuntimeError("v_colors must have dimensions (N, 3)")
     nb = num_sh_bases(degree)
-    v_coeffs = torch.empty((num_points, nb, 3), dtype=torch.float32, device=v_colors.device)
+    v_coeffs = _out_or_empty(out, (num_points, nb, 3), v_colors.device, "out")
     with _Guard(v_colors) as st:
         _lib.check(_lib.load().gsr_compute_sh_backward(num_points, degree, degrees_to_use, _ptr(viewdirs),
                                                        _ptr(v_colors), _ptr(v_coeffs), st), "compute_sh_backward")
@@ -131,7 +146,8 @@ def project_gaussians_backward(num_points: int, means3d: Tensor, scales: Tensor,
                                viewmat: Tensor, projmat: Tensor, fx: float, fy: float, cx: float, cy: float,
                                img_height: int, img_width: int, cov3d: Tensor, radii: Tensor, conics: Tensor,
                                compensation: Tensor, v_xy: Tensor, v_depth: Tensor, v_conic: Tensor,
-                               v_compensation: Tensor):
+                               v_compensation: Tensor, *, out_mean3d: Tensor = None, out_scale: Tensor = None,
+                               out_quat: Tensor = None):
     for t, n in ((means3d, "means3d"), (scales, "scales"), (quats, "quats"), (viewmat, "viewmat"),
                  (projmat, "projmat"), (cov3d, "cov3d"), (conics, "conics"), (compensation, "compensation"),
                  (v_xy, "v_xy"), (v_depth, "v_depth"), (v_conic, "v_conic"), (v_compensation, "v_compensation")):
@@ -141,9 +157,9 @@ def project_gaussians_backward(num_points: int, means3d: Tensor, scales: Tensor,
     f32 = dict(dtype=torch.float32, device=dev)
     v_cov2d = torch.empty((num_points, 3), **f32)
     v_cov3d = torch.empty((num_points, 6), **f32)
-    v_mean3d = torch.empty((num_points, 3), **f32)
-    v_scale = torch.empty((num_points, 3), **f32)
-    v_quat = torch.empty((num_points, 4), **f32)
+    v_mean3d = _out_or_empty(out_mean3d, (num_points, 3), dev, "out_mean3d")
+    v_scale = _out_or_empty(out_scale, (num_points, 3), dev, "out_scale")
+    v_quat = _out_or_empty(out_quat, (num_points, 4), dev, "out_quat")
     with _Guard(means3d) as st:
         _lib.check(_lib.load().gsr_project_gaussians_backward(
             num_points, _ptr(means3d), _ptr(scales), float(glob_scale), _ptr(quats), _ptr(viewmat), _ptr(projmat),
@@ -352,7 +368,8 @@ def nd_rasterize_forward(tile_bounds, block, img_size, gaussian_ids_sorted, tile
 
 
 def _rasterize_backward(nd: bool, img_height, img_width, block_width, gaussians_ids_sorted, tile_bins, xys, conics,
-                        colors, opacities, background, final_Ts, final_idx, v_output, v_output_alpha):
+                        colors, opacities, background, final_Ts, final_idx, v_output, v_output_alpha,
+                        out_opacity=None):
     _check_input(xys, "xys", torch.float32)
     _check_input(colors, "colors", torch.float32)
     if xys.dim() != 2 or xys.size(1) != 2:
@@ -371,7 +388,7 @@ def _rasterize_backward(nd: bool, img_height, img_width, block_width, gaussians_
     v_xy = torch.empty((num_points, 2), dtype=torch.float32, device=dev)
     v_conic = torch.empty((num_points, 3), dtype=torch.float32, device=dev)
     v_colors = torch.empty((num_points, channels), dtype=torch.float32, device=dev)
-    v_opacity = torch.empty((num_points, 1), dtype=torch.float32, device=dev)
+    v_opacity = _out_or_empty(out_opacity, (num_points, 1), dev, "out_opacity")
     lib = _lib.load()
     with _Guard(xys) as st:
         args = (_ptr(gaussians_ids_sorted), _ptr(tile_bins), _ptr(xys), _ptr(conics), _ptr(colors), _ptr(opacities),
@@ -387,9 +404,10 @@ def _rasterize_backward(nd: bool, img_height, img_width, block_width, gaussians_
 
 
 def rasterize_backward(img_height, img_width, block_width, gaussians_ids_sorted, tile_bins, xys, conics, colors,
-                       opacities, background, final_Ts, final_idx, v_output, v_output_alpha):
+                       opacities, background, final_Ts, final_idx, v_output, v_output_alpha, *, out_opacity=None):
     return _rasterize_backward(False, img_height, img_width, block_width, gaussians_ids_sorted, tile_bins, xys,
-                               conics, colors, opacities, background, final_Ts, final_idx, v_output, v_output_alpha)
+                               conics, colors, opacities, background, final_Ts, final_idx, v_output, v_output_alpha,
+                               out_opacity=out_opacity)
 
 
 def nd_rasterize_backward(img_height, img_width, block_width, gaussians_ids_sorted, tile_bins, xys, conics, colors,

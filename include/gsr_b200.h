@@ -148,7 +148,7 @@ GSR_API int gsr_map_gaussian_to_intersects_tight(int num_points, int num_interse
  * ties in Gaussian-index order) obtained with a two-level sort: Gaussians by depth (32-bit keys), then the
  * emitted (tile, id) pairs stably by tile id only (ceil(log2 T) bits); with exact tile culling as above.
  *   gsr_bin_prepare   : perm [N] i32 (Gaussian ids in depth order), cum_tiles [N] i32 (inclusive scan of the kept
- *                       tile counts in that order), masks [N] u64 (kept tiles of each bounding box);
+ *                       tile counts in that order), masks [N] u64 (kept tiles of each bounding box, indexed by Gaussian id);
  *                       the total M is copied to *total_host_pinned (pinned host int32) on `stream`.
  *   gsr_bin_emit_sort : after the caller has read M: gaussian_ids_sorted [M] i32, tile_bins [T,2] i32. */
 GSR_API size_t gsr_bin_prepare_workspace_bytes(int num_points);
