@@ -182,8 +182,10 @@ class ResidentView:
             s["v_out_alpha"], out_opacity=None if bk is None else bk["v_opacity"])
         self._mark(rec)
         v_rgb_sh = torch.where(rgb_sh + 0.5 > 0, v_colors, torch.zeros_like(v_colors))
-        v_coeffs = C.compute_sh_backward(N, self.degree, s["degrees_to_use"], self.viewdirs, v_rgb_sh,
-                                         out=None if bk is None else bk["v_coeffs"])
+        if bk is None:
+            v_coeffs = C.compute_sh_backward(N, self.degree, s["degrees_to_use"], self.viewdirs, v_rgb_sh)
+        else:
+            v_coeffs = v_rgb_sh  # view-parallel: the SH adjoint is evaluated for all ranks' views in the exchange
         self._mark(rec)
         _, _, v_mean, v_scale, v_quat = C.project_gaussians_backward(
             N, s["means3d"], s["scales"], s["glob_scale"], s["quats"], s["viewmat"], s["projmat"], s["fx"], s["fy"],
@@ -212,10 +214,10 @@ class PublicApiView:
     streams so that PCIe traffic overlaps the kernels (H2D of the upstream gradients under the forward pass, D2H of
     the image under the backward pass); device-side input buffers are double-buffered across steps."""
 
-    def __init__(self, s, scene_np):
+    def __init__(self, s, scene_np, bucket=None):
         import torch
 
-        self.torch, self.s = torch, s
+        self.torch, self.s, self.bucket = torch, s, bucket
         dev = s["means3d"].device
         self.means = s["means3d"].clone().requires_grad_(True)
         self.scales = s["scales"].clone().requires_grad_(True)
@@ -262,8 +264,14 @@ class PublicApiView:
         xys, depths, radii, conics, comp, nth, cov3d = rasterizer.project_gaussians(
             self.means, self.scales, s["glob_scale"], self.quats, self.d_viewmat, self.d_projmat, s["fx"], s["fy"],
             s["cx"], s["cy"], H, W, bw, s["clip_thresh"])
-        viewdirs = self.means.detach() - s["cam_pos"][None, :]
-        rgbs = torch.clamp(spherical_harmonics(s["degrees_to_use"], viewdirs, self.coeffs) + 0.5, min=0.0)
+        if self.bucket is None:
+            viewdirs = self.means.detach() - s["cam_pos"][None, :]
+            sh = spherical_harmonics(s["degrees_to_use"], viewdirs, self.coeffs)
+        else:  # view-parallel: coeffs.grad comes out already summed over the ranks
+            from rasterizer.view_parallel import spherical_harmonics_view_parallel
+
+            sh = spherical_harmonics_view_parallel(s["degrees_to_use"], self.means, s["cam_pos"], self.coeffs)
+        rgbs = torch.clamp(sh + 0.5, min=0.0)
         img, alpha = rasterizer.rasterize_gaussians(xys, depths, radii, conics, nth, rgbs, self.opac, H, W, bw,
                                                     background=s["background"], return_alpha=True)
         # this step's result goes back to the host on the D2H stream, under the backward pass
@@ -279,6 +287,14 @@ class PublicApiView:
         main.wait_event(in_ready)
         torch.autograd.backward([img, alpha], [self.d_vimg[i], self.d_valpha[i]])
         self.buf_free[i].record()
+        if self.bucket is not None:
+            # the remaining 11 floats / Gaussian: pack + one all-reduce over the non-SH part of the bucket
+            import torch.distributed as dist
+
+            bk = self.bucket
+            for name, p in (("v_mean3d", self.means), ("v_scale", self.scales), ("v_quat", self.quats), ("v_opacity", self.opac)):
+                bk[name].copy_(p.grad.reshape(bk[name].shape))
+            dist.all_reduce(bk.flat[bk.offsets["v_coeffs"][1]:])
         return (self.coeffs.grad, self.means.grad, self.scales.grad, self.quats.grad, self.opac.grad)
 
     def finish(self):
@@ -398,29 +414,27 @@ def main():
 
     # flat gradient bucket for the view-parallel all-reduce: 48 (SH) + 3 + 3 + 4 + 1 = 59 floats / Gaussian; the
     # backward kernels of the resident leg write straight into its segments, the autograd leg packs into it
-    from rasterizer.view_parallel import SEGMENTS, GradientBucket
+    from rasterizer.view_parallel import GradientBucket
 
     bucket = GradientBucket(N, s["sh_coeffs"].shape[1], device=s["means3d"].device) if world > 1 else None
     ar_events = []
-
-    def allreduce(grads, timed=False):
-        if world == 1:
-            return
-        bucket.pack(dict(zip(SEGMENTS, grads)))
-        if timed:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-        bucket.all_reduce()
-        if timed:
-            e1.record()
-            ar_events.append((e0, e1))
+    from rasterizer.view_parallel import exchange_gradients
 
     rv = ResidentView(s, bucket)
     recording = {"on": False}
 
     def resident_step():
         _, _, grads = rv.step(record=recording["on"])
-        allreduce(grads, timed=recording["on"])
+        if world == 1:
+            return
+        # grads[0] is the masked colour gradient v_rgb_sh; the other four already sit in the bucket
+        if recording["on"]:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        exchange_gradients(bucket, grads[0], s["means3d"], s["cam_pos"], rv.degree, s["degrees_to_use"])
+        if recording["on"]:
+            e1.record()
+            ar_events.append((e0, e1))
 
     sampler = ClockSampler(local_rank)
     # warm-up outside, then the timed region with stage events
@@ -435,7 +449,8 @@ def main():
     value = world * args.steps / (ms_total * 1e-3)
     stages = rv.stage_ms()
     if ar_events:
-        stages["grad_allreduce"] = sum(a.elapsed_time(b) for a, b in ar_events) / len(ar_events)
+        stages["grad_exchange(allgather v_rgb + multiview SH adjoint + allreduce 11N)"] = (
+            sum(a.elapsed_time(b) for a, b in ar_events) / len(ar_events))
     M = rv.M
     with torch.no_grad():
         _nth = rv.C.project_gaussians_forward(N, s["means3d"], s["scales"], s["glob_scale"], s["quats"], s["viewmat"],
@@ -444,11 +459,10 @@ def main():
         M_ref = int(_nth.sum().item())
 
     # e2e through the public API with host buffers
-    pv = PublicApiView(s, scene_np)
+    pv = PublicApiView(s, scene_np, bucket)
 
     def e2e_step():
-        grads = pv.step()
-        allreduce(grads)
+        pv.step()
 
     e2e_ms = timed_loop(torch, dist, world, e2e_step, args.steps, args.warmup, finish=pv.finish)
     e2e_value = world * args.steps / (e2e_ms * 1e-3)

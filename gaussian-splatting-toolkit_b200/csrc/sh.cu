@@ -190,9 +190,93 @@ sh_backward_kernel(int n, int K, int deg_use, const float *__restrict__ viewdirs
   stage_out(v_coeffs + (size_t)g0 * row_len, smem, rows * row_len, row_len, stride, vec_ok != 0);
 }
 
+// Multi-view SH adjoint: v_coeffs[n,k,c] = sum_v Y_k(means[n] - cam[v]) * v_colors_v[n,c].
+// This is the compute half of the view-parallel gradient exchange: instead of all-reducing the
+// 3K-float SH gradient of every rank (192 B per Gaussian at degree 3), ranks exchange only the 3-float colour
+// gradients (12 B) and every rank evaluates the outer products of ALL views while writing v_coeffs once.  The
+// per-view colour gradients are addressed through a pointer table, so they may live in an all-gathered buffer or
+// in peer GPUs' memory mapped over NVLink (P2P loads).
+constexpr int SH_MAX_VIEWS = 16;
+struct ShViews {
+  const float *v_colors[SH_MAX_VIEWS];
+};
+
+__global__ void __launch_bounds__(SH_THREADS)
+sh_backward_multiview_kernel(int n, int K, int deg_use, int num_views, const float *__restrict__ means3d,
+                             const float *__restrict__ cams, const ShViews views, float *__restrict__ v_coeffs,
+                             int vec_ok) {
+  extern __shared__ float smem[];
+  __shared__ float s_cam[SH_MAX_VIEWS * 3];
+  if (threadIdx.x < 3 * num_views) s_cam[threadIdx.x] = cams[threadIdx.x];
+  __syncthreads();
+  const int row_len = 3 * K, stride = sh_row_stride(row_len);
+  const int g0 = blockIdx.x * SH_THREADS;
+  const int rows = min(SH_THREADS, n - g0);
+  const int tid = threadIdx.x;
+  const int Ku = num_sh_bases(deg_use);
+  if (tid < rows) {
+    const int g = g0 + tid;
+    const float mx = means3d[3 * (size_t)g], my = means3d[3 * (size_t)g + 1], mz = means3d[3 * (size_t)g + 2];
+    float *o = smem + tid * stride;
+    for (int v = 0; v < num_views; ++v) {
+      float Y[25];
+      Y[0] = GSR_SH_C0;
+      sh_basis(deg_use, mx - s_cam[3 * v], my - s_cam[3 * v + 1], mz - s_cam[3 * v + 2], Y);
+      const float *vc = views.v_colors[v] + 3 * (size_t)g;
+      const float v0 = vc[0], v1 = vc[1], v2 = vc[2];
+#pragma unroll
+      for (int k = 0; k < 25; ++k) {
+        if (k < K) {
+          const float y = (k < Ku) ? Y[k] : 0.f;
+          if (v == 0) {
+            o[3 * k] = y * v0;
+            o[3 * k + 1] = y * v1;
+            o[3 * k + 2] = y * v2;
+          } else {
+            o[3 * k] += y * v0;
+            o[3 * k + 1] += y * v1;
+            o[3 * k + 2] += y * v2;
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  stage_out(v_coeffs + (size_t)g0 * row_len, smem, rows * row_len, row_len, stride, vec_ok != 0);
+}
+
 }  // namespace gsr
 
 extern "C" {
+
+GSR_API int gsr_compute_sh_backward_multiview(int num_points, int degree, int degrees_to_use, int num_views,
+                                              const float *means3d, const float *cam_positions,
+                                              const float *const *v_colors_views_host, float *v_coeffs,
+                                              void *stream) {
+  using namespace gsr;
+  GSR_REQUIRE(num_points >= 0, GSR_ERR_INVALID_ARGUMENT, "compute_sh_backward_multiview: num_points < 0");
+  GSR_REQUIRE(degree >= 0 && degree <= 4, GSR_ERR_UNSUPPORTED, "compute_sh_backward_multiview: degree %d not in [0,4]", degree);
+  GSR_REQUIRE(degrees_to_use >= 0 && degrees_to_use <= degree, GSR_ERR_INVALID_ARGUMENT,
+              "compute_sh_backward_multiview: degrees_to_use %d not in [0,%d]", degrees_to_use, degree);
+  GSR_REQUIRE(num_views >= 1 && num_views <= SH_MAX_VIEWS, GSR_ERR_UNSUPPORTED,
+              "compute_sh_backward_multiview: num_views %d not in [1,%d]", num_views, SH_MAX_VIEWS);
+  if (num_points == 0) return GSR_OK;
+  GSR_REQUIRE(means3d && cam_positions && v_colors_views_host && v_coeffs, GSR_ERR_INVALID_ARGUMENT,
+              "compute_sh_backward_multiview: null pointer");
+  ShViews views;
+  for (int v = 0; v < num_views; ++v) {
+    GSR_REQUIRE(v_colors_views_host[v] != nullptr, GSR_ERR_INVALID_ARGUMENT, "compute_sh_backward_multiview: null view pointer");
+    views.v_colors[v] = v_colors_views_host[v];
+  }
+  const int K = num_sh_bases(degree);
+  const size_t smem = (size_t)SH_THREADS * sh_row_stride(3 * K) * sizeof(float);
+  const int vec_ok = ((uintptr_t)v_coeffs % 16 == 0) ? 1 : 0;
+  sh_backward_multiview_kernel<<<cdiv(num_points, SH_THREADS), SH_THREADS, smem, (cudaStream_t)stream>>>(
+      num_points, K, degrees_to_use, num_views, means3d, cam_positions, views, v_coeffs, vec_ok);
+  GSR_CHECK_LAUNCH("sh_backward_multiview_kernel");
+  return GSR_OK;
+}
+
 
 GSR_API int gsr_compute_sh_forward(int num_points, int degree, int degrees_to_use, const float *viewdirs,
                                    const float *coeffs, float *colors, void *stream) {

@@ -83,6 +83,77 @@ class GradientBucket:
             self.flat.div_(world)
 
 
+def exchange_gradients(bucket: GradientBucket, v_rgb_sh: torch.Tensor, means3d: torch.Tensor, cam_pos: torch.Tensor,
+                       degree: int, degrees_to_use: int, group=None, average: bool = False) -> None:
+    """The view-parallel gradient exchange with the SH segment computed instead of communicated.
+
+    v_coeffs of rank r is the outer product Y(means - cam_r) (x) v_rgb_r, so the SUM over ranks can be evaluated
+    locally from every rank's 3-float colour gradient: ranks all-gather v_rgb_sh (12 B / Gaussian / rank) and their
+    camera centres, one kernel (gsr_compute_sh_backward_multiview) writes the summed SH gradient into the bucket,
+    and only the remaining 11 floats / Gaussian (means, scales, quats, opacity) go through an all-reduce:
+    12 W + 44 bytes per Gaussian on the wire instead of 236 (W = world size).  The caller must have put v_mean3d,
+    v_scale, v_quat, v_opacity into `bucket` (the SH segment is overwritten here)."""
+    from . import cuda as _C
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        _C.compute_sh_backward_multiview(degree, degrees_to_use, means3d, cam_pos.reshape(1, 3).contiguous(),
+                                         [v_rgb_sh.contiguous()], out=bucket["v_coeffs"])
+        return
+    world = dist.get_world_size(group)
+    v_all = torch.empty((world,) + tuple(v_rgb_sh.shape), dtype=torch.float32, device=v_rgb_sh.device)
+    cams = torch.empty((world, 3), dtype=torch.float32, device=v_rgb_sh.device)
+    dist.all_gather_into_tensor(v_all, v_rgb_sh.contiguous(), group=group)
+    dist.all_gather_into_tensor(cams, cam_pos.reshape(3).contiguous(), group=group)
+    lo, hi = bucket.offsets["v_coeffs"]
+    dist.all_reduce(bucket.flat[hi:], group=group)
+    _C.compute_sh_backward_multiview(degree, degrees_to_use, means3d, cams, v_all, out=bucket["v_coeffs"])
+    if average:
+        bucket.flat.div_(world)
+
+
+class _SphericalHarmonicsViewParallel(torch.autograd.Function):
+    """spherical_harmonics whose backward returns the coefficient gradient already SUMMED over the ranks of
+    `group` (all-gather of the 3-float colour gradients + multi-view adjoint kernel), see exchange_gradients."""
+
+    @staticmethod
+    def forward(ctx, degrees_to_use, means3d, cam_pos, coeffs, group, average):
+        from . import cuda as _C
+        from .sh import deg_from_sh
+
+        ctx.degrees_to_use, ctx.degree, ctx.group, ctx.average = degrees_to_use, deg_from_sh(coeffs.shape[-2]), group, average
+        viewdirs = (means3d - cam_pos.reshape(1, 3)).contiguous()
+        ctx.save_for_backward(means3d, cam_pos)
+        return _C.compute_sh_forward(coeffs.shape[0], ctx.degree, degrees_to_use, viewdirs, coeffs)
+
+    @staticmethod
+    def backward(ctx, v_colors):
+        from . import cuda as _C
+
+        means3d, cam_pos = ctx.saved_tensors
+        v_colors = v_colors.contiguous()
+        world = dist.get_world_size(ctx.group) if (dist.is_available() and dist.is_initialized()) else 1
+        if world == 1:
+            v_all, cams = [v_colors], cam_pos.reshape(1, 3).contiguous()
+        else:
+            v_all = torch.empty((world,) + tuple(v_colors.shape), dtype=torch.float32, device=v_colors.device)
+            cams = torch.empty((world, 3), dtype=torch.float32, device=v_colors.device)
+            dist.all_gather_into_tensor(v_all, v_colors, group=ctx.group)
+            dist.all_gather_into_tensor(cams, cam_pos.reshape(3).contiguous(), group=ctx.group)
+        v_coeffs = _C.compute_sh_backward_multiview(ctx.degree, ctx.degrees_to_use, means3d, cams, v_all)
+        if ctx.average and world > 1:
+            v_coeffs.div_(world)
+        return None, None, None, v_coeffs, None, None
+
+
+def spherical_harmonics_view_parallel(degrees_to_use: int, means3d: torch.Tensor, cam_pos: torch.Tensor,
+                                      coeffs: torch.Tensor, group=None, average: bool = False) -> torch.Tensor:
+    """Drop-in for `spherical_harmonics(degrees_to_use, means3d - cam_pos, coeffs)` in a view-parallel job:
+    same colours; `coeffs.grad` comes out already reduced over `group`, so the SH coefficients must be left out
+    of the gradient all-reduce (only 11 of the 59 floats per Gaussian remain to be reduced)."""
+    return _SphericalHarmonicsViewParallel.apply(degrees_to_use, means3d.detach().contiguous(), cam_pos.contiguous(),
+                                                 coeffs.contiguous(), group, average)
+
+
 def view_for_rank(step: int, rank: int, world_size: int, num_views: int) -> int:
     """Round-robin view assignment: rank r renders view (step * world + r) mod num_views."""
     return (step * world_size + rank) % num_views

@@ -71,6 +71,19 @@ GSR_API int gsr_compute_sh_backward(int num_points, int degree, int degrees_to_u
                                     const float *viewdirs, const float *v_colors, float *v_coeffs,
                                     void *stream);
 
+/* Multi-view SH adjoint — the compute half of the view-parallel gradient exchange (no counterpart in the
+ * reference, whose multi-GPU path is torch DDP's all-reduce of every parameter gradient,
+ * gs_toolkit/pipelines/base_pipeline.py:202-207):  v_coeffs[n,k,c] = sum_v Y_k(means3d[n] - cam_v) v_colors_v[n,c].
+ * Ranks exchange the 3-float colour gradients (12 B / Gaussian) instead of all-reducing the 3K-float SH gradients
+ * (192 B / Gaussian at degree 3); every rank then evaluates all views' outer products while writing v_coeffs once.
+ * cam_positions [V,3] is a DEVICE array (e.g. the all-gathered camera centres); v_colors_views_host [V] is a HOST
+ * array (read before return) of V DEVICE pointers, each to [N,3] floats — local memory, slices of an all-gathered
+ * buffer, or peer-GPU memory mapped over NVLink.  1 <= num_views <= 16. */
+GSR_API int gsr_compute_sh_backward_multiview(int num_points, int degree, int degrees_to_use, int num_views,
+                                              const float *means3d, const float *cam_positions,
+                                              const float *const *v_colors_views_host, float *v_coeffs,
+                                              void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * EWA projection — replaces project_gaussians_forward / project_gaussians_backward
  * (bindings.h:35-55, bindings.cu:105-216, kernels forward.cu:13-90, backward.cu:305-453)
