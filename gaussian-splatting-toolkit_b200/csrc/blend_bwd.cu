@@ -167,42 +167,41 @@ blend_backward_kernel(int tiles_x, int img_w, int img_h, int block_width,
       const bool valid = inside && (batch_end - t <= bin_final) && !(power > 0.f || alpha < 1.f / 255.f);
       if (!__any_sync(full, valid)) continue;
 
-      float v[8];
-      float v_opac_l = 0.f;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = 0.f;
+      // Branch-free body: lanes that are not valid run the same arithmetic with alpha = vis = 0, which leaves
+      // T and the running sums untouched (ra = 1, fac = 0) and makes all nine partial sums exactly zero.
+      const float alpha_e = valid ? alpha : 0.f;
+      const float vis_e = valid ? vis : 0.f;
       const float4 q2 = s_rec[buf][2][t];
-      if (valid) {
-        const float ra = 1.f / (1.f - alpha);
-        T *= ra;
-        const float fac = alpha * T;
-        v[0] = fac * vo_r;
-        v[1] = fac * vo_g;
-        v[2] = fac * vo_b;
-        float v_alpha = (q2.x * T - buf_r * ra) * vo_r;
-        v_alpha += (q2.y * T - buf_g * ra) * vo_g;
-        v_alpha += (q2.z * T - buf_b * ra) * vo_b;
-        v_alpha += ra * c_final;
-        buf_r += q2.x * fac;
-        buf_g += q2.y * fac;
-        buf_b += q2.z * fac;
-        const float v_sigma = -opac * vis * v_alpha;
-        // conic = -(2A, B, 2C) ln2 : v_conic = (0.5 v_sigma dx^2, v_sigma dx dy, 0.5 v_sigma dy^2)
-        const float hs = 0.5f * v_sigma;
-        v[3] = hs * dx * dx;
-        v[4] = v_sigma * dx * dy;
-        v[5] = hs * dy * dy;
-        // v_xy = v_sigma * (a dx + b dy, b dx + c dy) with a = -2A ln2, b = -B ln2, c = -2C ln2
-        const float ws = -kLn2 * v_sigma;
-        v[6] = ws * (2.f * gx + q1.y * dy);
-        v[7] = ws * (q1.y * dx + 2.f * gy);
-        v_opac_l = vis * v_alpha;
-      }
+      float v[8];
+      const float ra = 1.f / (1.f - alpha_e);
+      T *= ra;
+      const float fac = alpha_e * T;
+      v[0] = fac * vo_r;
+      v[1] = fac * vo_g;
+      v[2] = fac * vo_b;
+      float v_alpha = (q2.x * T - buf_r * ra) * vo_r;
+      v_alpha += (q2.y * T - buf_g * ra) * vo_g;
+      v_alpha += (q2.z * T - buf_b * ra) * vo_b;
+      v_alpha += ra * c_final;
+      buf_r += q2.x * fac;
+      buf_g += q2.y * fac;
+      buf_b += q2.z * fac;
+      const float v_sigma = -opac * vis_e * v_alpha;
+      // conic = -(2A, B, 2C) ln2 : v_conic = (0.5 v_sigma dx^2, v_sigma dx dy, 0.5 v_sigma dy^2)
+      const float hs = 0.5f * v_sigma;
+      v[3] = hs * dx * dx;
+      v[4] = v_sigma * dx * dy;
+      v[5] = hs * dy * dy;
+      // v_xy = v_sigma * (a dx + b dy, b dx + c dy) with a = -2A ln2, b = -B ln2, c = -2C ln2
+      const float ws = -kLn2 * v_sigma;
+      v[6] = ws * (2.f * gx + q1.y * dy);
+      v[7] = ws * (q1.y * dx + 2.f * gy);
+      const float v_opac_l = vis_e * v_alpha;
       const float tot8 = warp_transpose_reduce8(v, lane);
       const float tot_op = warp_sum(v_opac_l);
       if (dst_base != nullptr) {
-        const int g = __float_as_int(q2.w);
-        atomicAdd(dst_base + (size_t)g * dst_stride, lane == 1 ? tot_op : tot8);
+        const unsigned g = (unsigned)__float_as_int(q2.w);
+        atomicAdd(dst_base + g * (unsigned)dst_stride, lane == 1 ? tot_op : tot8);  // 32-bit element offset
       }
     }
   }
