@@ -20,6 +20,7 @@ from typing import Any
 
 import torch
 
+from .gaussian_rasterizer import GaussianRasterizationSettings, GaussianRasterizer
 from .project_gaussians import project_gaussians
 from .rasterize import rasterize_gaussians
 from .sh import spherical_harmonics
@@ -51,6 +52,9 @@ __all__ = [
     "MapGaussiansToIntersects",
     "SphericalHarmonics",
     "NDRasterizeGaussians",
+    # Inria-style façade (not part of the reference package; see gaussian_rasterizer.py)
+    "GaussianRasterizer",
+    "GaussianRasterizationSettings",
 ]
 
 

@@ -86,3 +86,78 @@ def test_cfg2_ours_vs_reference_extension():
     json.dump(rep, open(os.path.join(ROOT, "gpurun_out", "perf_vs_ref.json"), "w"), indent=1)
     d = (o_ours["out_img"] - o_ref["out_img"]).abs()
     assert float((d > 1e-4 * o_ref["out_img"].abs() + 1e-5).float().mean()) < 2e-3
+
+
+def test_cfg4_render_ours_vs_reference_extension():
+    """BASELINE configs[3]: 5 M Gaussians, 3840x2160, rgb + depth + alpha outputs (inference render).  The reference
+    path = what gs_toolkit/models/vanilla_gs.py:765-855 does in eval mode: SH, projection, then TWO complete
+    rasterize_gaussians calls (colour; depth as colour), each with its own cumsum/.item()/emit/sort/gather/bin-edges.
+    Ours = the public API of this package called the same way (the second call hits the binning cache)."""
+    import rasterizer
+    from oracle.build_ref import load_ref
+    from rasterizer.sh import spherical_harmonics
+    from rasterizer.synthetic import make_config_scene, scene_to_torch
+
+    ref_ext = load_ref()
+    if ref_ext is None:
+        pytest.skip("oracle/_ref/rasterizer_ref_cuda.so not present")
+    s = scene_to_torch(make_config_scene("cfg4"), "cuda")
+    H, W, bw, N = s["img_height"], s["img_width"], s["block_width"], s["means3d"].shape[0]
+    tb = ((W + bw - 1) // bw, (H + bw - 1) // bw, 1)
+    viewdirs = (s["means3d"] - s["cam_pos"][None]).contiguous()
+    opac = s["opacities"].reshape(-1, 1).contiguous()
+    zeros3 = torch.zeros(3, device="cuda")
+
+    def ref_render():
+        rgb_sh = ref_ext.compute_sh_forward(N, 3, 3, viewdirs, s["sh_coeffs"])
+        colors = torch.clamp(rgb_sh + 0.5, min=0.0)
+        cov3d, xys, depths, radii, conics, comp, nth = ref_ext.project_gaussians_forward(
+            N, s["means3d"], s["scales"], 1.0, s["quats"], s["viewmat"], s["projmat"], s["fx"], s["fy"], s["cx"], s["cy"],
+            H, W, bw, 0.01)
+        outs = []
+        for cols, bg in ((colors, s["background"]), (depths[:, None].repeat(1, 3), zeros3)):
+            cum = torch.cumsum(nth, 0, dtype=torch.int32)
+            M = int(cum[-1].item())
+            isect, gids = ref_ext.map_gaussian_to_intersects(N, M, xys, depths, radii, cum, tb, bw)
+            ks, order = torch.sort(isect)
+            vs = torch.gather(gids, 0, order)
+            bins = ref_ext.get_tile_bin_edges(M, ks, tb)
+            img, fT, fi = ref_ext.rasterize_forward(tb, (bw, bw, 1), (W, H, 1), vs, bins, xys, conics, cols, opac, bg)
+            outs.append((img, 1 - fT))
+        return outs[0][0], outs[0][1], outs[1][0][..., 0:1], M
+
+    def our_render():
+        with torch.no_grad():
+            xys, depths, radii, conics, comp, nth, cov3d = rasterizer.project_gaussians(
+                s["means3d"], s["scales"], 1.0, s["quats"], s["viewmat"], s["projmat"], s["fx"], s["fy"], s["cx"], s["cy"],
+                H, W, bw)
+            colors = torch.clamp(spherical_harmonics(3, viewdirs, s["sh_coeffs"]) + 0.5, min=0.0)
+            rgb, alpha = rasterizer.rasterize_gaussians(xys, depths, radii, conics, nth, colors, opac, H, W, bw,
+                                                        background=s["background"], return_alpha=True)
+            depth = rasterizer.rasterize_gaussians(xys, depths, radii, conics, nth, depths[:, None].repeat(1, 3), opac,
+                                                   H, W, bw, background=zeros3)[..., 0:1]
+        return rgb, alpha, depth
+
+    def timeit(fn, iters=10, warm=3):
+        ts = []
+        for i in range(warm + iters):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn()
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= warm:
+                ts.append(e0.elapsed_time(e1))
+        return statistics.median(ts), out
+
+    t_ref, o_ref = timeit(ref_render)
+    t_ours, o_ours = timeit(our_render)
+    rep = {"workload": "cfg4 5M Gaussians 3840x2160 SH3, render rgb+alpha+depth (forward)", "M_reference_bbox": o_ref[3],
+           "reference_ext_ms_per_frame": t_ref, "ours_ms_per_frame": t_ours, "speedup": t_ref / t_ours,
+           "reference_ext_fps": 1e3 / t_ref, "ours_fps": 1e3 / t_ours}
+    print(json.dumps(rep, indent=1))
+    json.dump(rep, open(os.path.join(ROOT, "gpurun_out", "perf_vs_ref_cfg4.json"), "w"), indent=1)
+    for a, b, name in ((o_ours[0], o_ref[0], "rgb"), (o_ours[1], o_ref[1], "alpha"), (o_ours[2], o_ref[2], "depth")):
+        bad = ((a - b).abs() > 1e-4 * b.abs() + 1e-5).float().mean()
+        print(f"[cfg4 vs reference ext] {name}: elements outside 1e-4: {float(bad):.2e}")
+        assert float(bad) < 2e-4
