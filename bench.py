@@ -133,7 +133,7 @@ class ResidentView:
 
     STAGES = ["sh_fwd", "project_fwd", "binning", "blend_fwd", "blend_bwd", "sh_bwd", "project_bwd"]
 
-    def __init__(self, s, bucket=None):
+    def __init__(self, s, bucket=None, exchange=None):
         import torch
         from rasterizer import cuda as C
 
@@ -149,6 +149,7 @@ class ResidentView:
         self.events = []
         self.M = 0
         self.bucket = bucket  # view_parallel.GradientBucket: backward kernels write straight into its segments
+        self.exchange = exchange  # view_parallel.GradientExchange (world > 1)
 
     def _mark(self, rec):
         if rec is not None:
@@ -186,6 +187,8 @@ class ResidentView:
             v_coeffs = C.compute_sh_backward(N, self.degree, s["degrees_to_use"], self.viewdirs, v_rgb_sh)
         else:
             v_coeffs = v_rgb_sh  # view-parallel: the SH adjoint is evaluated for all ranks' views in the exchange
+            if self.exchange is not None:
+                self.exchange.start_sh(v_rgb_sh, s["cam_pos"], s["degrees_to_use"])
         self._mark(rec)
         _, _, v_mean, v_scale, v_quat = C.project_gaussians_backward(
             N, s["means3d"], s["scales"], s["glob_scale"], s["quats"], s["viewmat"], s["projmat"], s["fx"], s["fy"],
@@ -418,9 +421,12 @@ def main():
 
     bucket = GradientBucket(N, s["sh_coeffs"].shape[1], device=s["means3d"].device) if world > 1 else None
     ar_events = []
-    from rasterizer.view_parallel import exchange_gradients
+    from rasterizer.view_parallel import GradientExchange, PeerColorGrads
 
-    rv = ResidentView(s, bucket)
+    peer = PeerColorGrads.try_create(N, device=s["means3d"].device) if (world > 1 and os.environ.get("GSR_NO_P2P") != "1") else None
+    exchange = GradientExchange(bucket, s["means3d"], {1: 0, 4: 1, 9: 2, 16: 3, 25: 4}[s["sh_coeffs"].shape[1]], peer) if world > 1 else None
+
+    rv = ResidentView(s, bucket, exchange)
     recording = {"on": False}
 
     def resident_step():
@@ -431,7 +437,7 @@ def main():
         if recording["on"]:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        exchange_gradients(bucket, grads[0], s["means3d"], s["cam_pos"], rv.degree, s["degrees_to_use"])
+        exchange.finish()
         if recording["on"]:
             e1.record()
             ar_events.append((e0, e1))
@@ -449,7 +455,7 @@ def main():
     value = world * args.steps / (ms_total * 1e-3)
     stages = rv.stage_ms()
     if ar_events:
-        stages["grad_exchange(allgather v_rgb + multiview SH adjoint + allreduce 11N)"] = (
+        stages["grad_exchange_tail(allreduce 11N + join of the %s SH adjoint started after blend_bwd)" % ("NVLink-peer-load" if peer is not None else "NCCL-allgather")] = (
             sum(a.elapsed_time(b) for a, b in ar_events) / len(ar_events))
     M = rv.M
     with torch.no_grad():

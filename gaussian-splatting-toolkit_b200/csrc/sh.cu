@@ -199,15 +199,15 @@ sh_backward_kernel(int n, int K, int deg_use, const float *__restrict__ viewdirs
 constexpr int SH_MAX_VIEWS = 16;
 struct ShViews {
   const float *v_colors[SH_MAX_VIEWS];
+  const float *cam[SH_MAX_VIEWS];  // each -> 3 floats (camera centre of that view), possibly in peer memory
 };
 
 __global__ void __launch_bounds__(SH_THREADS)
 sh_backward_multiview_kernel(int n, int K, int deg_use, int num_views, const float *__restrict__ means3d,
-                             const float *__restrict__ cams, const ShViews views, float *__restrict__ v_coeffs,
-                             int vec_ok) {
+                             const ShViews views, float *__restrict__ v_coeffs, int vec_ok) {
   extern __shared__ float smem[];
   __shared__ float s_cam[SH_MAX_VIEWS * 3];
-  if (threadIdx.x < 3 * num_views) s_cam[threadIdx.x] = cams[threadIdx.x];
+  if (threadIdx.x < 3 * num_views) s_cam[threadIdx.x] = views.cam[threadIdx.x / 3][threadIdx.x % 3];
   __syncthreads();
   const int row_len = 3 * K, stride = sh_row_stride(row_len);
   const int g0 = blockIdx.x * SH_THREADS;
@@ -253,7 +253,24 @@ GSR_API int gsr_compute_sh_backward_multiview(int num_points, int degree, int de
                                               const float *means3d, const float *cam_positions,
                                               const float *const *v_colors_views_host, float *v_coeffs,
                                               void *stream) {
+  // contiguous camera array -> pointer table
+  if (num_views < 1 || num_views > gsr::SH_MAX_VIEWS || cam_positions == nullptr) {
+    gsr::set_error("compute_sh_backward_multiview: num_views %d not in [1,%d] or null cam_positions", num_views,
+                   gsr::SH_MAX_VIEWS);
+    return GSR_ERR_INVALID_ARGUMENT;
+  }
+  const float *cams[gsr::SH_MAX_VIEWS];
+  for (int v = 0; v < num_views; ++v) cams[v] = cam_positions + 3 * v;
+  return gsr_compute_sh_backward_multiview_ptrs(num_points, degree, degrees_to_use, num_views, means3d, cams,
+                                                v_colors_views_host, v_coeffs, stream);
+}
+
+GSR_API int gsr_compute_sh_backward_multiview_ptrs(int num_points, int degree, int degrees_to_use, int num_views,
+                                                   const float *means3d, const float *const *cam_views_host,
+                                                   const float *const *v_colors_views_host, float *v_coeffs,
+                                                   void *stream) {
   using namespace gsr;
+  const float *const *cam_positions = cam_views_host;
   GSR_REQUIRE(num_points >= 0, GSR_ERR_INVALID_ARGUMENT, "compute_sh_backward_multiview: num_points < 0");
   GSR_REQUIRE(degree >= 0 && degree <= 4, GSR_ERR_UNSUPPORTED, "compute_sh_backward_multiview: degree %d not in [0,4]", degree);
   GSR_REQUIRE(degrees_to_use >= 0 && degrees_to_use <= degree, GSR_ERR_INVALID_ARGUMENT,
@@ -266,13 +283,15 @@ GSR_API int gsr_compute_sh_backward_multiview(int num_points, int degree, int de
   ShViews views;
   for (int v = 0; v < num_views; ++v) {
     GSR_REQUIRE(v_colors_views_host[v] != nullptr, GSR_ERR_INVALID_ARGUMENT, "compute_sh_backward_multiview: null view pointer");
+    GSR_REQUIRE(cam_views_host[v] != nullptr, GSR_ERR_INVALID_ARGUMENT, "compute_sh_backward_multiview: null camera pointer");
     views.v_colors[v] = v_colors_views_host[v];
+    views.cam[v] = cam_views_host[v];
   }
   const int K = num_sh_bases(degree);
   const size_t smem = (size_t)SH_THREADS * sh_row_stride(3 * K) * sizeof(float);
   const int vec_ok = ((uintptr_t)v_coeffs % 16 == 0) ? 1 : 0;
   sh_backward_multiview_kernel<<<cdiv(num_points, SH_THREADS), SH_THREADS, smem, (cudaStream_t)stream>>>(
-      num_points, K, degrees_to_use, num_views, means3d, cam_positions, views, v_coeffs, vec_ok);
+      num_points, K, degrees_to_use, num_views, means3d, views, v_coeffs, vec_ok);
   GSR_CHECK_LAUNCH("sh_backward_multiview_kernel");
   return GSR_OK;
 }

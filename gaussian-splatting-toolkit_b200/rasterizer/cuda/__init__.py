@@ -104,19 +104,22 @@ def compute_sh_backward(num_points: int, degree: int, degrees_to_use: int, viewd
     return v_coeffs
 
 
-def compute_sh_backward_multiview(degree: int, degrees_to_use: int, means3d: Tensor, cam_positions: Tensor,
+def compute_sh_backward_multiview(degree: int, degrees_to_use: int, means3d: Tensor, cam_positions,
                                   v_colors_views, *, out: Tensor = None) -> Tensor:
     """v_coeffs [N,K,3] = sum over views v of Y(means3d - cam_positions[v]) (x) v_colors_views[v]  (each [N,3]).
-    `cam_positions`: CUDA tensor [V,3]; `v_colors_views`: sequence of V CUDA tensors (or one [V,N,3] tensor) —
-    they may alias peer-GPU memory."""
+    `cam_positions`: CUDA tensor [V,3] or a sequence of V CUDA tensors of 3 floats; `v_colors_views`: sequence of V
+    CUDA tensors (or one [V,N,3] tensor).  Per-view tensors may alias peer-GPU memory (symmetric memory)."""
     import ctypes
 
     _check_input(means3d, "means3d", torch.float32)
-    _check_input(cam_positions, "cam_positions", torch.float32)
     views = list(v_colors_views.unbind(0)) if isinstance(v_colors_views, Tensor) else list(v_colors_views)
+    cams = list(cam_positions.reshape(-1, 3).unbind(0)) if isinstance(cam_positions, Tensor) else list(cam_positions)
     n, V = means3d.size(0), len(views)
-    if cam_positions.numel() != 3 * V:
+    if len(cams) != V:
         raise RuntimeError("cam_positions and v_colors_views must have the same number of views")
+    for i, c in enumerate(cams):
+        if not c.is_cuda or c.dtype != torch.float32 or c.numel() != 3 or not c.is_contiguous():
+            raise RuntimeError(f"cam_positions[{i}] must be 3 contiguous float32 values on the GPU")
     for i, v in enumerate(views):
         _check_input(v, f"v_colors_views[{i}]", torch.float32)
         if v.numel() != 3 * n:
@@ -124,9 +127,10 @@ def compute_sh_backward_multiview(degree: int, degrees_to_use: int, means3d: Ten
     nb = num_sh_bases(degree)
     v_coeffs = _out_or_empty(out, (n, nb, 3), means3d.device, "out")
     ptrs = (ctypes.c_void_p * V)(*[v.data_ptr() for v in views])
+    cam_ptrs = (ctypes.c_void_p * V)(*[c.data_ptr() for c in cams])
     with _Guard(means3d) as st:
-        _lib.check(_lib.load().gsr_compute_sh_backward_multiview(n, degree, degrees_to_use, V, _ptr(means3d),
-                                                                 _ptr(cam_positions), ptrs,
+        _lib.check(_lib.load().gsr_compute_sh_backward_multiview_ptrs(n, degree, degrees_to_use, V, _ptr(means3d),
+                                                                      cam_ptrs, ptrs,
                                                                  _ptr(v_coeffs), st), "compute_sh_backward_multiview")
     return v_coeffs
 

@@ -83,16 +83,50 @@ class GradientBucket:
             self.flat.div_(world)
 
 
+class PeerColorGrads:
+    """NVLink peer-memory mailbox for the colour gradients: every rank owns one symmetric-memory buffer
+    [N*3 colour-gradient floats | 3 camera-centre floats | pad] that all peers map into their address space
+    (torch.distributed._symmetric_memory: CUDA VMM handles exchanged once at rendezvous).  The multi-view SH adjoint
+    kernel then LOADS the peers' colour gradients straight over NVLink while it writes the summed SH gradient —
+    all-gather and compute are one kernel, there is no staging buffer and no NCCL call for the SH segment.
+    Two device-side barriers per exchange (signal pads, stream-ordered, no host sync): "all published" before the
+    kernel, "all consumed" after it."""
+
+    def __init__(self, num_points: int, group=None, device=None):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.num_points = num_points
+        group = group if group is not None else dist.group.WORLD
+        device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.buf = symm_mem.empty(num_points * 3 + 4, dtype=torch.float32, device=device)
+        self.hdl = symm_mem.rendezvous(self.buf, group)
+        self.world, self.rank = self.hdl.world_size, self.hdl.rank
+        self.local_rgb = self.buf[: 3 * num_points].view(num_points, 3)
+        self.local_cam = self.buf[3 * num_points: 3 * num_points + 3]
+        self.peer_rgb = [self.hdl.get_buffer(r, (num_points, 3), torch.float32, 0) for r in range(self.world)]
+        self.peer_cam = [self.hdl.get_buffer(r, (3,), torch.float32, 3 * num_points) for r in range(self.world)]
+
+    @staticmethod
+    def try_create(num_points: int, group=None, device=None):
+        """None when symmetric memory is unavailable (no P2P mapping): callers fall back to the NCCL all-gather."""
+        try:
+            return PeerColorGrads(num_points, group, device)
+        except Exception:  # pragma: no cover - depends on the platform
+            return None
+
+
 def exchange_gradients(bucket: GradientBucket, v_rgb_sh: torch.Tensor, means3d: torch.Tensor, cam_pos: torch.Tensor,
-                       degree: int, degrees_to_use: int, group=None, average: bool = False) -> None:
+                       degree: int, degrees_to_use: int, group=None, average: bool = False,
+                       peer: "PeerColorGrads" = None) -> None:
     """The view-parallel gradient exchange with the SH segment computed instead of communicated.
 
     v_coeffs of rank r is the outer product Y(means - cam_r) (x) v_rgb_r, so the SUM over ranks can be evaluated
-    locally from every rank's 3-float colour gradient: ranks all-gather v_rgb_sh (12 B / Gaussian / rank) and their
-    camera centres, one kernel (gsr_compute_sh_backward_multiview) writes the summed SH gradient into the bucket,
-    and only the remaining 11 floats / Gaussian (means, scales, quats, opacity) go through an all-reduce:
-    12 W + 44 bytes per Gaussian on the wire instead of 236 (W = world size).  The caller must have put v_mean3d,
-    v_scale, v_quat, v_opacity into `bucket` (the SH segment is overwritten here)."""
+    locally from every rank's 3-float colour gradient: one kernel (gsr_compute_sh_backward_multiview) reads all ranks'
+    v_rgb_sh (12 B / Gaussian / rank) and camera centres and writes the summed SH gradient into the bucket; only the
+    remaining 11 floats / Gaussian (means, scales, quats, opacity) go through an all-reduce: 12 W + 44 bytes per
+    Gaussian on the wire instead of 236 (W = world size).  With `peer` (PeerColorGrads) the kernel loads the peers'
+    colour gradients directly over NVLink from symmetric memory; without it they are all-gathered with NCCL first.
+    The caller must have put v_mean3d, v_scale, v_quat, v_opacity into `bucket` (the SH segment is overwritten)."""
     from . import cuda as _C
 
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
@@ -100,13 +134,24 @@ def exchange_gradients(bucket: GradientBucket, v_rgb_sh: torch.Tensor, means3d: 
                                          [v_rgb_sh.contiguous()], out=bucket["v_coeffs"])
         return
     world = dist.get_world_size(group)
-    v_all = torch.empty((world,) + tuple(v_rgb_sh.shape), dtype=torch.float32, device=v_rgb_sh.device)
-    cams = torch.empty((world, 3), dtype=torch.float32, device=v_rgb_sh.device)
-    dist.all_gather_into_tensor(v_all, v_rgb_sh.contiguous(), group=group)
-    dist.all_gather_into_tensor(cams, cam_pos.reshape(3).contiguous(), group=group)
     lo, hi = bucket.offsets["v_coeffs"]
-    dist.all_reduce(bucket.flat[hi:], group=group)
-    _C.compute_sh_backward_multiview(degree, degrees_to_use, means3d, cams, v_all, out=bucket["v_coeffs"])
+    if peer is not None:
+        # NVLink peer-memory path: publish, barrier, [NCCL all-reduce of the 11 N rest] + fused gather/adjoint kernel
+        if v_rgb_sh.data_ptr() != peer.local_rgb.data_ptr():
+            peer.local_rgb.copy_(v_rgb_sh)
+        peer.local_cam.copy_(cam_pos.reshape(3))
+        peer.hdl.barrier(channel=0)
+        dist.all_reduce(bucket.flat[hi:], group=group)
+        _C.compute_sh_backward_multiview(degree, degrees_to_use, means3d, peer.peer_cam, peer.peer_rgb,
+                                         out=bucket["v_coeffs"])
+        peer.hdl.barrier(channel=1)
+    else:
+        v_all = torch.empty((world,) + tuple(v_rgb_sh.shape), dtype=torch.float32, device=v_rgb_sh.device)
+        cams = torch.empty((world, 3), dtype=torch.float32, device=v_rgb_sh.device)
+        dist.all_gather_into_tensor(v_all, v_rgb_sh.contiguous(), group=group)
+        dist.all_gather_into_tensor(cams, cam_pos.reshape(3).contiguous(), group=group)
+        dist.all_reduce(bucket.flat[hi:], group=group)
+        _C.compute_sh_backward_multiview(degree, degrees_to_use, means3d, cams, v_all, out=bucket["v_coeffs"])
     if average:
         bucket.flat.div_(world)
 
@@ -152,6 +197,56 @@ def spherical_harmonics_view_parallel(degrees_to_use: int, means3d: torch.Tensor
     of the gradient all-reduce (only 11 of the 59 floats per Gaussian remain to be reduced)."""
     return _SphericalHarmonicsViewParallel.apply(degrees_to_use, means3d.detach().contiguous(), cam_pos.contiguous(),
                                                  coeffs.contiguous(), group, average)
+
+
+class GradientExchange:
+    """The exchange of `exchange_gradients` split in two so that it overlaps the tail of the backward pass:
+
+        ex.start_sh(v_rgb_sh, cam_pos)     # right after the blend adjoint: publish colour gradients, fused
+                                           # gather + SH adjoint on a SIDE stream (NVLink peer loads)
+        ... projection adjoint writes v_mean3d / v_scale / v_quat into the bucket on the main stream ...
+        ex.finish()                        # NCCL all-reduce of the 11 N remaining floats on the main stream,
+                                           # concurrently with the side-stream kernel; then join
+
+    Without a PeerColorGrads mailbox (no symmetric memory) start_sh() only remembers its arguments and finish()
+    runs the NCCL all-gather variant."""
+
+    def __init__(self, bucket: GradientBucket, means3d: torch.Tensor, degree: int, peer: "PeerColorGrads" = None,
+                 group=None):
+        self.bucket, self.means3d, self.degree, self.peer, self.group = bucket, means3d, degree, peer, group
+        self.side = torch.cuda.Stream(means3d.device) if peer is not None else None
+        self._pending = None
+
+    def start_sh(self, v_rgb_sh: torch.Tensor, cam_pos: torch.Tensor, degrees_to_use: int) -> None:
+        from . import cuda as _C
+
+        if self.peer is None:
+            self._pending = (v_rgb_sh, cam_pos, degrees_to_use)
+            return
+        peer, cur = self.peer, torch.cuda.current_stream()
+        self.side.wait_stream(cur)
+        with torch.cuda.stream(self.side):
+            if v_rgb_sh.data_ptr() != peer.local_rgb.data_ptr():
+                peer.local_rgb.copy_(v_rgb_sh)
+                v_rgb_sh.record_stream(self.side)
+            peer.local_cam.copy_(cam_pos.reshape(3))
+            peer.hdl.barrier(channel=0)
+            _C.compute_sh_backward_multiview(self.degree, degrees_to_use, self.means3d, peer.peer_cam, peer.peer_rgb,
+                                             out=self.bucket["v_coeffs"])
+
+    def finish(self, average: bool = False) -> None:
+        bucket = self.bucket
+        if self.peer is None:
+            v_rgb_sh, cam_pos, degrees_to_use = self._pending
+            self._pending = None
+            exchange_gradients(bucket, v_rgb_sh, self.means3d, cam_pos, self.degree, degrees_to_use, self.group, average)
+            return
+        hi = bucket.offsets["v_coeffs"][1]
+        dist.all_reduce(bucket.flat[hi:], group=self.group)
+        torch.cuda.current_stream().wait_stream(self.side)
+        self.peer.hdl.barrier(channel=1)
+        if average:
+            bucket.flat.div_(dist.get_world_size(self.group))
 
 
 def view_for_rank(step: int, rank: int, world_size: int, num_views: int) -> int:

@@ -83,6 +83,13 @@ GSR_API int gsr_compute_sh_backward_multiview(int num_points, int degree, int de
                                               const float *means3d, const float *cam_positions,
                                               const float *const *v_colors_views_host, float *v_coeffs,
                                               void *stream);
+/* Same, with the camera centres also addressed through a HOST table of V DEVICE pointers (3 floats each): this is
+ * the form used when every rank publishes {v_colors, camera centre} in NVLink-mapped symmetric memory and the kernel
+ * loads the peers' data directly (fused all-gather + adjoint, no staging copy). */
+GSR_API int gsr_compute_sh_backward_multiview_ptrs(int num_points, int degree, int degrees_to_use, int num_views,
+                                                   const float *means3d, const float *const *cam_views_host,
+                                                   const float *const *v_colors_views_host, float *v_coeffs,
+                                                   void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * EWA projection — replaces project_gaussians_forward / project_gaussians_backward

@@ -387,7 +387,7 @@ def _exchange_worker(rank, world, port, results):
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     from rasterizer import cuda as C
-    from rasterizer.view_parallel import GradientBucket, exchange_gradients
+    from rasterizer.view_parallel import GradientBucket, PeerColorGrads, exchange_gradients
 
     N, K = 20_000, 16
     g = torch.Generator().manual_seed(50)
@@ -409,7 +409,20 @@ def _exchange_worker(rank, world, port, results):
     exchange_gradients(fused, v_rgb, means, cam, 3, 3)
     torch.cuda.synchronize()
     err = float((fused.flat - plain.flat).norm() / plain.flat.norm())
-    results[rank] = err
+    # (c) the same exchange with the peers' colour gradients loaded over NVLink from symmetric memory, twice in a
+    #     row (the second round checks the "all consumed" barrier: buffers are overwritten with new values)
+    peer = PeerColorGrads.try_create(N, device=torch.device("cuda", rank))
+    err_p2p = -1.0
+    if peer is not None:
+        for rnd in range(2):
+            scale = float(rnd + 1)
+            p2p = GradientBucket(N, K, device="cuda")
+            for k, v in rest.items():
+                p2p[k].copy_(v * scale)
+            exchange_gradients(p2p, v_rgb * scale, means, cam, 3, 3, peer=peer)
+            torch.cuda.synchronize()
+            err_p2p = max(err_p2p, float((p2p.flat - plain.flat * scale).norm() / (plain.flat.norm() * scale)))
+    results[rank] = (err, err_p2p)
     dist.destroy_process_group()
 
 
@@ -421,8 +434,9 @@ def test_exchange_gradients_matches_plain_allreduce_2gpu():
     mgr = mp.Manager()
     results = mgr.dict()
     mp.spawn(_exchange_worker, args=(2, 29600 + os.getpid() % 1000, results), nprocs=2, join=True)
-    print("[exchange vs all-reduce] normwise rel err per rank:", dict(results))
-    assert all(results[r] < 1e-6 for r in range(2))
+    print("[exchange vs all-reduce] normwise rel err per rank (nccl all-gather path, NVLink peer path):", dict(results))
+    assert all(results[r][0] < 1e-6 for r in range(2))
+    assert all(results[r][1] < 1e-6 for r in range(2))   # -1 = symmetric memory unavailable on this box
 
 
 def test_gaussian_rasterizer_facade_matches_operators(oracle):
