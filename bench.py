@@ -5,8 +5,9 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
 
 One "step" = one view of SURVEY §8(d): SH fwd -> project fwd -> bin/sort -> blend fwd (rgb + alpha) ->
-[fixed synthetic upstream gradients] -> blend bwd -> SH bwd -> project bwd [-> NCCL all-reduce of the
-59 N parameter-gradient floats when N_gpus > 1].  Workload at N=1: cfg2 = 1 M Gaussians, 1920x1080,
+[fixed synthetic upstream gradients] -> blend bwd -> SH bwd -> project bwd [-> view-parallel gradient exchange
+when N_gpus > 1: fused gather + SH adjoint over NVLink peer memory and an NCCL all-reduce of the other 11 N floats,
+rasterizer/view_parallel.py].  Workload at N=1: cfg2 = 1 M Gaussians, 1920x1080,
 SH degree 3 (BASELINE.json configs[1]).  Multi-GPU is view-parallel (weak scaling): every rank renders
 its own camera of the same replicated scene.
 
