@@ -445,3 +445,96 @@ def nd_rasterize_backward(img_height, img_width, block_width, gaussians_ids_sort
                           opacities, background, final_Ts, final_idx, v_output, v_output_alpha):
     return _rasterize_backward(True, img_height, img_width, block_width, gaussians_ids_sorted, tile_bins, xys,
                                conics, colors, opacities, background, final_Ts, final_idx, v_output, v_output_alpha)
+
+
+# ---------------------------------------------------------------------------------------------------
+# fused render operator; see include/gsr_b200.h "FUSED render operator"
+def fused_preprocess_forward(means3d: Tensor, scales_raw: Tensor, quats_raw: Tensor, opacities_raw: Tensor,
+                             features_dc: Tensor, features_rest: Tensor, viewmat: Tensor, projmat: Tensor,
+                             glob_scale: float, fx: float, fy: float, cx: float, cy: float, img_height: int,
+                             img_width: int, block_width: int, degrees_to_use: int, clip_thresh: float = 0.01):
+    """-> (records [3,N,4], xys [N,2], depths [N], radii [N] i32, conics [N,3], opacities [N], clamp_mask [N] i32)"""
+    for t, nm in ((means3d, "means3d"), (scales_raw, "scales"), (quats_raw, "quats"), (opacities_raw, "opacities"),
+                  (features_dc, "features_dc"), (features_rest, "features_rest"), (viewmat, "viewmat"),
+                  (projmat, "projmat")):
+        _check_input(t, nm, torch.float32)
+    n, dev = means3d.size(0), means3d.device
+    k_rest = features_rest.size(1) if features_rest.dim() == 3 else 0
+    sh_degree = {0: 0, 3: 1, 8: 2, 15: 3, 24: 4}.get(k_rest)
+    if sh_degree is None or features_dc.numel() != 3 * n or features_rest.numel() != 3 * n * k_rest:
+        raise RuntimeError("features_dc must be [N,3] and features_rest [N,(d+1)^2-1,3]")
+    f32 = dict(dtype=torch.float32, device=dev)
+    i32 = dict(dtype=torch.int32, device=dev)
+    rec = torch.empty((3, n, 4), **f32)
+    xys, depths = torch.empty((n, 2), **f32), torch.empty((n,), **f32)
+    radii, conics = torch.empty((n,), **i32), torch.empty((n, 3), **f32)
+    opac, mask = torch.empty((n,), **f32), torch.empty((n,), **i32)
+    with _Guard(means3d) as st:
+        _lib.check(_lib.load().gsr_fused_preprocess_forward(
+            n, sh_degree, int(degrees_to_use), _ptr(means3d), _ptr(scales_raw), _ptr(quats_raw), _ptr(opacities_raw),
+            _ptr(features_dc), _ptr(features_rest), _ptr(viewmat), _ptr(projmat), float(glob_scale), float(fx), float(fy),
+            float(cx), float(cy), int(img_height), int(img_width), int(block_width), float(clip_thresh), _ptr(rec),
+            _ptr(xys), _ptr(depths), _ptr(radii), _ptr(conics), _ptr(opac), _ptr(mask), st), "fused_preprocess_forward")
+    return rec, xys, depths, radii, conics, opac, mask
+
+
+def fused_preprocess_backward(means3d, scales_raw, quats_raw, opacities_raw, k_rest: int, degrees_to_use: int, viewmat,
+                              projmat, glob_scale, fx, fy, img_height, img_width, radii, conics, clamp_mask, grad_rec,
+                              v_xys_extra=None, out=None):
+    """-> (v_means3d, v_scales_raw, v_quats_raw, v_opacities_raw [N,1], v_features_dc [N,3], v_features_rest [N,k_rest,3]).
+    `out`: optional dict of preallocated outputs with those names (e.g. views of a GradientBucket)."""
+    _check_input(grad_rec, "grad_rec", torch.float32)
+    n, dev = means3d.size(0), means3d.device
+    sh_degree = {0: 0, 3: 1, 8: 2, 15: 3, 24: 4}[k_rest]
+    out = out or {}
+    v_means = _out_or_empty(out.get("v_means3d"), (n, 3), dev, "v_means3d")
+    v_scales = _out_or_empty(out.get("v_scales"), (n, 3), dev, "v_scales")
+    v_quats = _out_or_empty(out.get("v_quats"), (n, 4), dev, "v_quats")
+    v_opac = _out_or_empty(out.get("v_opacities"), (n, 1), dev, "v_opacities")
+    v_dc = _out_or_empty(out.get("v_features_dc"), (n, 3), dev, "v_features_dc")
+    v_rest = _out_or_empty(out.get("v_features_rest"), (n, k_rest, 3), dev, "v_features_rest")
+    with _Guard(means3d) as st:
+        _lib.check(_lib.load().gsr_fused_preprocess_backward(
+            n, sh_degree, int(degrees_to_use), _ptr(means3d), _ptr(scales_raw), _ptr(quats_raw), _ptr(opacities_raw),
+            _ptr(viewmat), _ptr(projmat), float(glob_scale), float(fx), float(fy), int(img_height), int(img_width),
+            _ptr(radii), _ptr(conics), _ptr(clamp_mask), _ptr(grad_rec),
+            _ptr(v_xys_extra) if v_xys_extra is not None else None, _ptr(v_means), _ptr(v_scales), _ptr(v_quats),
+            _ptr(v_opac), _ptr(v_dc), _ptr(v_rest), st), "fused_preprocess_backward")
+    return v_means, v_scales, v_quats, v_opac, v_dc, v_rest
+
+
+def blend_packed_forward(img_height: int, img_width: int, block_width: int, gaussian_ids_sorted: Tensor,
+                         tile_bins: Tensor, records: Tensor, background: Tensor, with_depth: bool):
+    """-> (out_img [H,W,3], out_depth [H,W] | None, final_Ts [H,W], final_idx [H,W] i32)"""
+    _check_input(records, "records", torch.float32)
+    _check_input(background, "background", torch.float32)
+    n, dev = records.size(1), records.device
+    out_img = torch.empty((img_height, img_width, 3), dtype=torch.float32, device=dev)
+    out_depth = torch.empty((img_height, img_width), dtype=torch.float32, device=dev) if with_depth else None
+    final_Ts = torch.empty((img_height, img_width), dtype=torch.float32, device=dev)
+    final_idx = torch.empty((img_height, img_width), dtype=torch.int32, device=dev)
+    with _Guard(records) as st:
+        _lib.check(_lib.load().gsr_blend_packed_forward(
+            int(img_height), int(img_width), int(block_width), n, _ptr(gaussian_ids_sorted), _ptr(tile_bins),
+            _ptr(records), _ptr(background), _ptr(out_img), _ptr(out_depth) if with_depth else None, _ptr(final_Ts),
+            _ptr(final_idx), st), "blend_packed_forward")
+    return out_img, out_depth, final_Ts, final_idx
+
+
+def blend_packed_backward(img_height: int, img_width: int, block_width: int, gaussian_ids_sorted: Tensor,
+                          tile_bins: Tensor, records: Tensor, background: Tensor, final_Ts: Tensor, final_idx: Tensor,
+                          v_output: Tensor, v_output_depth, v_output_alpha: Tensor) -> Tensor:
+    """-> grad_rec [N,12] = {v_x, v_y, v_opacity, v_depth | v_a, v_b, v_c, - | v_r, v_g, v_b, -}"""
+    for t, nm in ((v_output, "v_output"), (v_output_alpha, "v_output_alpha")):
+        _check_input(t, nm, torch.float32)
+    if v_output_depth is not None:
+        _check_input(v_output_depth, "v_output_depth", torch.float32)
+    n, dev = records.size(1), records.device
+    grad_rec = torch.empty((n, 12), dtype=torch.float32, device=dev)
+    with _Guard(records) as st:
+        _lib.check(_lib.load().gsr_blend_packed_backward(
+            int(img_height), int(img_width), int(block_width), n, _ptr(gaussian_ids_sorted), _ptr(tile_bins),
+            _ptr(records), _ptr(background), _ptr(final_Ts), _ptr(final_idx), _ptr(v_output),
+            _ptr(v_output_depth) if v_output_depth is not None else None, _ptr(v_output_alpha), _ptr(grad_rec), st),
+            "blend_packed_backward")
+    return grad_rec

@@ -232,6 +232,48 @@ GSR_API int gsr_nd_rasterize_backward(unsigned img_height, unsigned img_width, u
                                       const float *v_output, const float *v_output_alpha, float *v_xy,
                                       float *v_conic, float *v_colors, float *v_opacity, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * FUSED render operator (SURVEY 8(f1) — the model-side glue folded into the operator; no single counterpart in the
+ * reference: it replaces the sequence gs_toolkit/models/vanilla_gs.py:759-855 issues per view).
+ *
+ * gsr_fused_preprocess_forward: per Gaussian, from the RAW model parameters — exp(scales_raw), normalised
+ *   quats_raw, sigmoid(opacities_raw), SH colour from {features_dc [N,3], features_rest [N,K-1,3]} in direction
+ *   means3d - camera centre, clamp(rgb + 0.5, min=0), EWA projection — to packed blend records
+ *   `records` [3][N] float4 planes {x,y,ext_x,ext_y | A,B,C,opacity | r,g,b,depth} plus xys [N,2], depths [N],
+ *   radii [N] i32, conics [N,3], opacities [N] (activated), clamp_mask [N] i32 (bit c set iff rgb_c + 0.5 > 0).
+ * gsr_blend_packed_forward / _backward: compositing of RGB and (if out_depth / v_output_depth != NULL) depth as a
+ *   fourth channel in the same pass (the reference models run a second rasterize_gaussians call for depth,
+ *   vanilla_gs.py:839-855); the adjoint accumulates grad_records [N,12] =
+ *   {v_x, v_y, v_opacity, v_depth | v_a, v_b, v_c, - | v_r, v_g, v_b, -} (zero-filled by the call).
+ * gsr_fused_preprocess_backward: grad_records (+ optional v_xys_extra [N,2]) -> gradients of the six raw parameter
+ *   tensors (chain rules of exp / normalise / sigmoid / clamp included).
+ * ---------------------------------------------------------------------------------------------- */
+GSR_API int gsr_fused_preprocess_forward(int num_points, int sh_degree, int degrees_to_use, const float *means3d,
+                                         const float *scales_raw, const float *quats_raw, const float *opacities_raw,
+                                         const float *features_dc, const float *features_rest, const float *viewmat,
+                                         const float *projmat, float glob_scale, float fx, float fy, float cx, float cy,
+                                         unsigned img_height, unsigned img_width, unsigned block_width,
+                                         float clip_thresh, float *records, float *xys, float *depths, int32_t *radii,
+                                         float *conics, float *opacities, int32_t *clamp_mask, void *stream);
+GSR_API int gsr_fused_preprocess_backward(int num_points, int sh_degree, int degrees_to_use, const float *means3d,
+                                          const float *scales_raw, const float *quats_raw, const float *opacities_raw,
+                                          const float *viewmat, const float *projmat, float glob_scale, float fx,
+                                          float fy, unsigned img_height, unsigned img_width, const int32_t *radii,
+                                          const float *conics, const int32_t *clamp_mask, const float *grad_records,
+                                          const float *v_xys_extra /*nullable*/, float *v_means3d, float *v_scales_raw,
+                                          float *v_quats_raw, float *v_opacities_raw, float *v_features_dc,
+                                          float *v_features_rest, void *stream);
+GSR_API int gsr_blend_packed_forward(unsigned img_height, unsigned img_width, unsigned block_width, int num_points,
+                                     const int32_t *gaussian_ids_sorted, const int32_t *tile_bins,
+                                     const float *records, const float *background, float *out_img,
+                                     float *out_depth /*nullable*/, float *final_Ts, int32_t *final_idx, void *stream);
+GSR_API int gsr_blend_packed_backward(unsigned img_height, unsigned img_width, unsigned block_width, int num_points,
+                                      const int32_t *gaussian_ids_sorted, const int32_t *tile_bins,
+                                      const float *records, const float *background, const float *final_Ts,
+                                      const int32_t *final_idx, const float *v_output,
+                                      const float *v_output_depth /*nullable*/, const float *v_output_alpha,
+                                      float *grad_records, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

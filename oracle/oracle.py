@@ -272,3 +272,72 @@ def render_view(scene, v_out_img=None, v_out_alpha=None, backward=True, tile_row
     out.update(v_xy=v_xy, v_conic=v_conic, v_colors=v_colors, v_opacity=v_opacity, v_coeffs=v_coeffs,
                v_mean3d=v_mean, v_scale=v_scale, v_quat=v_quat, v_cov2d=v_cov2d, v_cov3d=v_cov3d)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------
+def raw_parameters(scene, seed=0):
+    """The model's RAW parameters (log-scales, unnormalised quaternions, logit opacities, features_dc / features_rest,
+    gs_toolkit/models/vanilla_gs.py:150-175) that activate to the tensors of a synthetic scene."""
+    rng = np.random.default_rng(seed)
+    n = scene["means3d"].shape[0]
+    o = np.clip(scene["opacities"].astype(np.float64), 1e-6, 1 - 1e-6)
+    return dict(
+        scales_raw=np.log(scene["scales"]).astype(np.float32),
+        quats_raw=(scene["quats"] * rng.uniform(0.5, 2.0, size=(n, 1))).astype(np.float32),
+        opacities_raw=np.log(o / (1 - o)).astype(np.float32).reshape(n, 1),
+        features_dc=np.ascontiguousarray(scene["sh_coeffs"][:, 0, :]),
+        features_rest=np.ascontiguousarray(scene["sh_coeffs"][:, 1:, :]),
+    )
+
+
+def render_fused_reference(scene, raw, v_rgb=None, v_depth=None, v_alpha=None):
+    """What the reference model computes per view from its raw parameters (models/vanilla_gs.py:759-855: activations,
+    SH colour + clamp, projection, colour rasterization with alpha, depth rasterization), restated with the oracle's
+    operators and numpy glue, and the gradients of the six raw parameter tensors for upstream gradients of
+    (rgb [H,W,3], depth [H,W], alpha [H,W]).  Depth is composited as a 4th FP32 channel — per pixel the same
+    arithmetic as the model's second rasterize_gaussians call."""
+    s = scene
+    H, W, bw = s["img_height"], s["img_width"], s["block_width"]
+    tb = ((W + bw - 1) // bw, (H + bw - 1) // bw, 1)
+    n = s["means3d"].shape[0]
+    scales = np.exp(raw["scales_raw"]).astype(np.float32)
+    qnorm = np.linalg.norm(raw["quats_raw"].astype(np.float64), axis=1, keepdims=True)
+    qn = (raw["quats_raw"] / qnorm).astype(np.float32)
+    opac = (1.0 / (1.0 + np.exp(-raw["opacities_raw"].astype(np.float64)))).astype(np.float32).reshape(-1)
+    coeffs = np.concatenate([raw["features_dc"][:, None, :], raw["features_rest"]], axis=1).astype(np.float32)
+    viewdirs = s["means3d"] - s["cam_pos"][None, :]
+    rgb_sh = sh_forward(s["degrees_to_use"], viewdirs, coeffs)
+    colors = np.maximum(rgb_sh + 0.5, 0.0).astype(np.float32)
+    cov3d, xys, depths, radii, conics, comp, nth = project_forward(
+        s["means3d"], scales, s["glob_scale"], qn, s["viewmat"], s["projmat"], s["fx"], s["fy"], s["cx"], s["cy"], H, W,
+        bw, s["clip_thresh"])
+    m, cum = compute_cumulative_intersects(nth)
+    _, _, _, vs, bins = bin_and_sort_gaussians(n, m, xys, depths, radii, cum, tb, bw)
+    colors4 = np.concatenate([colors, depths[:, None]], axis=1).astype(np.float32)
+    bg4 = np.concatenate([s["background"], np.zeros(1, np.float32)]).astype(np.float32)
+    img4, fT, fi, amb = rasterize_forward(H, W, bw, vs, bins, xys, conics, colors4, opac, bg4, nd_numerics=False,
+                                          want_ambiguous=True)
+    out = dict(rgb=img4[..., :3], depth=img4[..., 3], alpha=1.0 - fT, ambiguous=amb, radii=radii, xys=xys,
+               num_intersects=m)
+    if v_rgb is None:
+        return out
+    v_out4 = np.concatenate([v_rgb, v_depth[..., None]], axis=-1).astype(np.float32)
+    v_xy, v_conic, v_colors4, v_opacity = rasterize_backward(
+        H, W, bw, vs, bins, xys, conics, colors4, opac, bg4, fT, fi, v_out4, v_alpha, nd_numerics=False, dtype=np.float32)
+    v_rgb_sh = np.where(rgb_sh + 0.5 > 0.0, v_colors4[:, :3], 0.0).astype(np.float32)
+    v_coeffs = sh_backward(deg_from_sh(coeffs.shape[1]), s["degrees_to_use"], viewdirs, v_rgb_sh)
+    zeros_n = np.zeros((n,), np.float32)
+    _, _, v_mean, v_scale, v_quat = project_backward(
+        s["means3d"], scales, s["glob_scale"], qn, s["viewmat"], s["projmat"], s["fx"], s["fy"], s["cx"], s["cy"], H, W,
+        cov3d, radii, conics, comp, v_xy, np.ascontiguousarray(v_colors4[:, 3]), v_conic, zeros_n)
+    # chain rules of the activations (autograd of torch.exp / quats / quats.norm / torch.sigmoid in the model)
+    vq = v_quat.astype(np.float64)
+    qh = qn.astype(np.float64)
+    v_quats_raw = (vq - qh * np.sum(qh * vq, axis=1, keepdims=True)) / qnorm
+    o = opac.astype(np.float64).reshape(-1, 1)
+    out.update(v_means3d=v_mean, v_scales_raw=(v_scale * scales).astype(np.float32),
+               v_quats_raw=v_quats_raw.astype(np.float32),
+               v_opacities_raw=(v_opacity.astype(np.float64) * o * (1 - o)).astype(np.float32),
+               v_features_dc=np.ascontiguousarray(v_coeffs[:, 0, :]), v_features_rest=np.ascontiguousarray(v_coeffs[:, 1:, :]),
+               v_xy=v_xy)
+    return out

@@ -161,3 +161,89 @@ def test_cfg4_render_ours_vs_reference_extension():
         bad = ((a - b).abs() > 1e-4 * b.abs() + 1e-5).float().mean()
         print(f"[cfg4 vs reference ext] {name}: elements outside 1e-4: {float(bad):.2e}")
         assert float(bad) < 2e-4
+
+
+def test_cfg2_model_style_step_fused_vs_reference():
+    """one model-style training view from the RAW parameters (activations, SH colour + clamp, projection,
+    colour + alpha rasterization, DEPTH rasterization, backward of everything — vanilla_gs.py:759-855 with
+    output_depth_during_training) at cfg2, three ways on the same inputs:
+      (1) the reference extension behind reference-style autograd wrappers + torch glue,
+      (2) this package's separate operators + the same torch glue,
+      (3) this package's fused operator render_gaussians (depth as the 4th channel of the colour pass)."""
+    import rasterizer
+    from oracle import oracle as orc
+    from oracle.build_ref import load_ref
+    from rasterizer.fused import render_gaussians
+    from rasterizer.sh import spherical_harmonics
+    from rasterizer.synthetic import make_config_scene, scene_to_torch
+    from ref_autograd import make_ops
+
+    ref_ext = load_ref()
+    if ref_ext is None:
+        pytest.skip("oracle/_ref/rasterizer_ref_cuda.so not present")
+    scene = make_config_scene("cfg2")
+    raw_np = orc.raw_parameters(scene)
+    s = scene_to_torch(scene, "cuda")
+    raw = {k: torch.from_numpy(v).cuda() for k, v in raw_np.items()}
+    H, W, bw = s["img_height"], s["img_width"], 16
+    params = [s["means3d"].clone().requires_grad_(True)] + [raw[k].clone().requires_grad_(True) for k in
+                                                           ("scales_raw", "quats_raw", "features_dc", "features_rest", "opacities_raw")]
+    w_rgb, w_a = s["v_out_img"], s["v_out_alpha"]
+    w_d = (s["v_out_alpha"] * 0.1)[..., None].contiguous()
+    zeros3 = torch.zeros(3, device="cuda")
+    r_sh, r_proj, r_rast = make_ops(ref_ext)
+
+    def glue_step(sh_fn, proj_fn, rast_fn):
+        means, sc, q, dc, rest, op = params
+        scales, quats = torch.exp(sc), q / q.norm(dim=-1, keepdim=True)
+        coeffs = torch.cat((dc[:, None, :], rest), dim=1)
+        xys, depths, radii, conics, comp, nth, cov3d = proj_fn(means, scales, 1.0, quats, s["viewmat"], s["projmat"],
+                                                               s["fx"], s["fy"], s["cx"], s["cy"], H, W, bw, 0.01)
+        viewdirs = means.detach() - s["cam_pos"][None]
+        rgbs = torch.clamp(sh_fn(3, viewdirs, coeffs) + 0.5, min=0.0)
+        opac = torch.sigmoid(op)
+        rgb, alpha = rast_fn(xys, depths, radii, conics, nth, rgbs, opac, s["background"], True)
+        depth = rast_fn(xys, depths, radii, conics, nth, depths[:, None].repeat(1, 3), opac, zeros3, False)[..., 0:1]
+        torch.autograd.backward([rgb, depth, alpha], [w_rgb, w_d, w_a])
+
+    def ref_step():
+        glue_step(r_sh, r_proj, lambda *a: (lambda o: o if a[-1] else o[0])(r_rast(*a[:7], H, W, bw, a[7])))
+
+    def ours_step():
+        glue_step(spherical_harmonics, rasterizer.project_gaussians,
+                  lambda xys, d, r, c, n_, col, op_, bg, ra: rasterizer.rasterize_gaussians(
+                      xys, d, r, c, n_, col, op_, H, W, bw, background=bg, return_alpha=ra))
+
+    def fused_step():
+        rgb, depth, alpha = render_gaussians(*params, s["viewmat"], s["projmat"], s["fx"], s["fy"], s["cx"], s["cy"], H, W, 3,
+                                             background=s["background"], render_depth=True)
+        torch.autograd.backward([rgb, depth, alpha], [w_rgb, w_d, w_a[..., None]])
+
+    def timeit(fn, iters=15, warm=4):
+        ts = []
+        for i in range(warm + iters):
+            for p in params:
+                p.grad = None
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= warm:
+                ts.append(e0.elapsed_time(e1))
+        return statistics.median(ts), [p.grad.clone() for p in params]
+
+    t_ref, g_ref = timeit(ref_step)
+    t_ours, g_ours = timeit(ours_step)
+    t_fused, g_fused = timeit(fused_step)
+    rep = {"workload": "cfg2 model-style view from raw parameters: rgb + alpha + depth, fwd+bwd", "reference_ext_ms": t_ref,
+           "ours_separate_ops_ms": t_ours, "ours_fused_ms": t_fused, "speedup_separate": t_ref / t_ours,
+           "speedup_fused": t_ref / t_fused, "reference_views_per_s": 1e3 / t_ref, "fused_views_per_s": 1e3 / t_fused}
+    print(json.dumps(rep, indent=1))
+    json.dump(rep, open(os.path.join(ROOT, "gpurun_out", "perf_model_step.json"), "w"), indent=1)
+    names = ("means3d", "scales_raw", "quats_raw", "features_dc", "features_rest", "opacities_raw")
+    for nme, a, b, c in zip(names, g_ref, g_ours, g_fused):
+        for tag, x in (("separate", b), ("fused", c)):
+            rel = float((x - a).norm() / a.norm())
+            print(f"[model step] grad {nme:14s} {tag:8s} vs reference ext: normwise rel {rel:.2e}")
+            assert rel < 5e-4
