@@ -52,6 +52,16 @@ def parse_args():
     return ap.parse_args()
 
 
+def ncu_facts(kernel):
+    """Per-launch DRAM traffic etc. of `kernel` from the committed ncu --set full capture (profiles/ncu_traffic.json)."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        d = json.load(open(path))
+        return d["kernels"].get(kernel), d.get("source")
+    except Exception:
+        return None, None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -479,9 +489,12 @@ def main():
         ab = algorithmic_bytes(N, M, P, T)
         t_bwd = stages["blend_bwd"] * 1e-3
         achieved = ab["blend_bwd"] / t_bwd / 1e9
+        facts, facts_src = ncu_facts("blend_backward_kernel")
         roofline = {
             "kernel": "blend_backward_kernel (gsr_rasterize_backward)", "bound": "hbm", "achieved": achieved, "peak": peak,
-            "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+            "unit": "GB/s", "frac": achieved / peak, "traffic": facts["dram_bytes"] if facts else None,
+            "traffic_source": facts_src, "peak_source": peak_src,
+            "ncu_issue_slot_utilization": (facts["issue_active_pct"] / 100.0) if facts else None,
             "algorithmic_bytes_per_launch": ab["blend_bwd"], "avg_launch_ms": stages["blend_bwd"],
             "note": "blend kernels are FP32-issue bound (>=100 flop/B); a low HBM fraction is expected (SURVEY 8d). "
                     "Algorithmic bytes use the M the kernel actually walks (after exact tile culling), not the reference's "
