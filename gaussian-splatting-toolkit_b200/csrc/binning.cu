@@ -14,6 +14,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include "common.cuh"
+#include "tile_cull.cuh"
 
 namespace gsr {
 
@@ -43,42 +44,7 @@ map_intersects_kernel(int n, const float2 *__restrict__ xys, const float *__rest
   }
 }
 
-// ---- exact (conservative) tile culling --------------------------------------------------------------
-// A (Gaussian, tile) pair of the reference's bounding-box list can only change a pixel if some pixel p of the
-// tile has alpha = min(0.999, o * exp(-sigma(p))) >= 1/255 (forward.cu:360-363), i.e. q(p) = 2 sigma(p) <=
-// 2 ln(255 o).  q is a convex quadratic, so its minimum over the tile's pixel rectangle is 0 if the centre lies
-// inside, else it is attained on one of the four edges (1-D clamped minimisation).  Pairs whose minimum exceeds
-// the threshold (with a 0.1 % + 1e-3 margin) are dropped: the reference would `continue` on every pixel.
-// Degenerate inputs (non-PD conic, NaN) are never culled.
-__device__ __forceinline__ bool tile_can_contribute(float mx, float my, float a, float b, float c, float thr,
-                                                    float x0, float x1, float y0, float y1) {
-  const float dx0 = x0 - mx, dx1 = x1 - mx, dy0 = y0 - my, dy1 = y1 - my;
-  if (dx0 <= 0.f && dx1 >= 0.f && dy0 <= 0.f && dy1 >= 0.f) return true;  // centre inside the rectangle
-  float best = 3.0e38f;
-  const float rc = 1.f / c, ra = 1.f / a;
-  {
-    float dy = fminf(fmaxf(-b * dx0 * rc, dy0), dy1);
-    best = fminf(best, a * dx0 * dx0 + 2.f * b * dx0 * dy + c * dy * dy);
-    dy = fminf(fmaxf(-b * dx1 * rc, dy0), dy1);
-    best = fminf(best, a * dx1 * dx1 + 2.f * b * dx1 * dy + c * dy * dy);
-    float dx = fminf(fmaxf(-b * dy0 * ra, dx0), dx1);
-    best = fminf(best, a * dx * dx + 2.f * b * dx * dy0 + c * dy0 * dy0);
-    dx = fminf(fmaxf(-b * dy1 * ra, dx0), dx1);
-    best = fminf(best, a * dx * dx + 2.f * b * dx * dy1 + c * dy1 * dy1);
-  }
-  return !(best > thr);
-}
-
-// threshold on q = 2 sigma; returns false when the Gaussian can never reach alpha >= 1/255
-__device__ __forceinline__ bool alpha_threshold(float a, float b, float c, float opac, float &thr, bool &never_cull) {
-  never_cull = !(a > 0.f && c > 0.f && a * c - b * b > 0.f) || !(opac == opac);
-  thr = 3.0e38f;
-  if (never_cull) return true;
-  if (255.f * opac < 0.999f) return false;
-  thr = 2.f * __logf(255.f * opac) * 1.001f + 1e-3f;
-  return true;
-}
-
+// exact (conservative) tile culling: see tile_cull.cuh
 template <bool EMIT>
 __global__ void __launch_bounds__(BIN_THREADS)
 tight_tiles_kernel(int n, const float2 *__restrict__ xys, const float *__restrict__ depths,
@@ -94,10 +60,9 @@ tight_tiles_kernel(int n, const float2 *__restrict__ xys, const float *__restric
     const float2 ctr = xys[idx];
     int x0, y0, x1, y1;
     tile_bbox(ctr.x, ctr.y, (float)r, tiles_x, tiles_y, block_width, x0, y0, x1, y1);
-    const float a = conics[3 * (size_t)idx], b = conics[3 * (size_t)idx + 1], c = conics[3 * (size_t)idx + 2];
-    float thr;
-    bool never_cull;
-    if (alpha_threshold(a, b, c, opacities[idx], thr, never_cull)) {
+    const CullEllipse e = make_cull_ellipse(conics[3 * (size_t)idx], conics[3 * (size_t)idx + 1],
+                                            conics[3 * (size_t)idx + 2], opacities[idx]);
+    if (!e.empty) {
       int cur = 0;
       int64_t depth_id = 0;
       if (EMIT) {
@@ -105,18 +70,16 @@ tight_tiles_kernel(int n, const float2 *__restrict__ xys, const float *__restric
         depth_id = (int64_t)__float_as_int(depths[idx]);
       }
       for (int i = y0; i < y1; ++i) {
-        const float ry0 = (float)(i * block_width), ry1 = (float)(min((i + 1) * block_width, img_h) - 1);
-        for (int j = x0; j < x1; ++j) {
-          const float rx0 = (float)(j * block_width), rx1 = (float)(min((j + 1) * block_width, img_w) - 1);
-          if (never_cull || tile_can_contribute(ctr.x, ctr.y, a, b, c, thr, rx0, rx1, ry0, ry1)) {
-            if (EMIT) {
-              isect_ids[cur] = ((int64_t)(i * tiles_x + j) << 32) | depth_id;
-              gaussian_ids[cur] = idx;
-              ++cur;
-            }
-            ++count;
+        int j0, j1;
+        cull_row_range(e, ctr.x, ctr.y, i, x0, x1, block_width, j0, j1);
+        if (EMIT) {
+          for (int j = j0; j < j1; ++j) {
+            isect_ids[cur] = ((int64_t)(i * tiles_x + j) << 32) | depth_id;
+            gaussian_ids[cur] = idx;
+            ++cur;
           }
         }
+        count += j1 - j0;
       }
     }
   }

@@ -20,28 +20,11 @@
 #include <thrust/iterator/permutation_iterator.h>
 
 #include "common.cuh"
+#include "tile_cull.cuh"
 
 namespace gsr {
 
 constexpr int FB_THREADS = 256;
-
-// duplicated from binning.cu (kept in one translation unit each on purpose: both are tiny and inlined)
-__device__ __forceinline__ bool fb_tile_can_contribute(float mx, float my, float a, float b, float c, float thr,
-                                                       float x0, float x1, float y0, float y1) {
-  const float dx0 = x0 - mx, dx1 = x1 - mx, dy0 = y0 - my, dy1 = y1 - my;
-  if (dx0 <= 0.f && dx1 >= 0.f && dy0 <= 0.f && dy1 >= 0.f) return true;
-  float best = 3.0e38f;
-  const float rc = 1.f / c, ra = 1.f / a;
-  float dy = fminf(fmaxf(-b * dx0 * rc, dy0), dy1);
-  best = fminf(best, a * dx0 * dx0 + 2.f * b * dx0 * dy + c * dy * dy);
-  dy = fminf(fmaxf(-b * dx1 * rc, dy0), dy1);
-  best = fminf(best, a * dx1 * dx1 + 2.f * b * dx1 * dy + c * dy * dy);
-  float dx = fminf(fmaxf(-b * dy0 * ra, dx0), dx1);
-  best = fminf(best, a * dx * dx + 2.f * b * dx * dy0 + c * dy0 * dy0);
-  dx = fminf(fmaxf(-b * dy1 * ra, dx0), dx1);
-  best = fminf(best, a * dx * dx + 2.f * b * dx * dy1 + c * dy1 * dy1);
-  return !(best > thr);
-}
 
 // depth keys: visible Gaussians sort by the IEEE bits of their (positive) depth, exactly the low 32 bits of the
 // reference key (forward.cu:116); culled ones go to the end
@@ -72,24 +55,21 @@ count_tiles_kernel(int n, const float2 *__restrict__ xys, const int *__restrict_
     int x0, y0, x1, y1;
     tile_bbox(ctr.x, ctr.y, (float)r, tiles_x, tiles_y, block_width, x0, y0, x1, y1);
     const int bw_tiles = x1 - x0, area = bw_tiles * (y1 - y0);
-    const float a = conics[3 * (size_t)g], b = conics[3 * (size_t)g + 1], c = conics[3 * (size_t)g + 2];
-    const float opac = opacities[g];
-    const bool never_cull = !(a > 0.f && c > 0.f && a * c - b * b > 0.f) || !(opac == opac);
-    if (never_cull) {
+    const CullEllipse e = make_cull_ellipse(conics[3 * (size_t)g], conics[3 * (size_t)g + 1], conics[3 * (size_t)g + 2],
+                                            opacities[g]);
+    if (e.never_cull) {
       count = area;
       mask = ~0ull;
-    } else if (!(255.f * opac < 0.999f)) {
-      const float thr = 2.f * __logf(255.f * opac) * 1.001f + 1e-3f;
-      int k = 0;
+    } else if (!e.empty) {
       for (int i = y0; i < y1; ++i) {
-        const float ry0 = (float)(i * block_width), ry1 = (float)(min((i + 1) * block_width, img_h) - 1);
-        for (int jx = x0; jx < x1; ++jx, ++k) {
-          const float rx0 = (float)(jx * block_width), rx1 = (float)(min((jx + 1) * block_width, img_w) - 1);
-          if (fb_tile_can_contribute(ctr.x, ctr.y, a, b, c, thr, rx0, rx1, ry0, ry1)) {
-            if (k < 64) mask |= 1ull << k;  // boxes with more than 64 tiles are re-tested by the emit kernel
-            ++count;
-          }
+        int j0, j1;
+        cull_row_range(e, ctr.x, ctr.y, i, x0, x1, block_width, j0, j1);
+        const int cnt = j1 - j0;
+        if (cnt > 0 && area <= 64) {  // boxes with more than 64 tiles are re-derived row by row by the emit kernel
+          const int k0 = (i - y0) * bw_tiles + (j0 - x0);
+          mask |= ((cnt >= 64) ? ~0ull : ((1ull << cnt) - 1ull)) << k0;
         }
+        count += cnt;
       }
     }
   }
@@ -120,18 +100,16 @@ emit_sorted_kernel(int n, const int *__restrict__ perm, const float2 *__restrict
         gaussian_ids[cur] = g;
         ++cur;
       }
-  } else if (area > 64) {  // big box, partially culled: repeat the count kernel's test
-    const float a = conics[3 * (size_t)g], b = conics[3 * (size_t)g + 1], c = conics[3 * (size_t)g + 2];
-    const float thr = 2.f * __logf(255.f * opacities[g]) * 1.001f + 1e-3f;
+  } else if (area > 64) {  // big box, partially culled: repeat the count kernel's row ranges
+    const CullEllipse e = make_cull_ellipse(conics[3 * (size_t)g], conics[3 * (size_t)g + 1], conics[3 * (size_t)g + 2],
+                                            opacities[g]);
     for (int i = y0; i < y1; ++i) {
-      const float ry0 = (float)(i * block_width), ry1 = (float)(min((i + 1) * block_width, img_h) - 1);
-      for (int jx = x0; jx < x1 && cur < end; ++jx) {
-        const float rx0 = (float)(jx * block_width), rx1 = (float)(min((jx + 1) * block_width, img_w) - 1);
-        if (fb_tile_can_contribute(ctr.x, ctr.y, a, b, c, thr, rx0, rx1, ry0, ry1)) {
-          tile_keys[cur] = (unsigned)(i * tiles_x + jx);
-          gaussian_ids[cur] = g;
-          ++cur;
-        }
+      int j0, j1;
+      cull_row_range(e, ctr.x, ctr.y, i, x0, x1, block_width, j0, j1);
+      for (int jx = j0; jx < j1 && cur < end; ++jx) {
+        tile_keys[cur] = (unsigned)(i * tiles_x + jx);
+        gaussian_ids[cur] = g;
+        ++cur;
       }
     }
   } else {
