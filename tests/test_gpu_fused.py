@@ -134,3 +134,35 @@ def test_fused_render_empty_and_no_depth():
     assert torch.allclose(rgb3, s["background"].expand(32, 48, 3)) and float(alpha3.abs().sum()) == 0.0
     (rgb3.sum() + depth3.sum()).backward()
     assert float(behind.grad.abs().sum()) == 0.0
+
+
+def test_fused_render_vs_reference_cuda_golden():
+    """Fused operator vs what the unmodified reference extension + torch autograd glue produced on a B200 for the
+    model-level view (committed fixture tests/golden/refcuda_modelstep_*.npz)."""
+    import glob
+    import os
+
+    from rasterizer.fused import render_gaussians
+
+    paths = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "refcuda_modelstep_*.npz")))
+    assert paths, "model-step golden fixture missing"
+    for path in paths:
+        z = np.load(path)
+        s = {k[3:]: (z[k] if z[k].ndim else z[k].item()) for k in z.files if k.startswith("in_")}
+        d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+        p = {k[4:]: d(z[k]).requires_grad_(True) for k in z.files if k.startswith("raw_")}
+        means = d(s["means3d"]).requires_grad_(True)
+        H, W = s["img_height"], s["img_width"]
+        rgb, depth, alpha = render_gaussians(means, p["scales_raw"], p["quats_raw"], p["features_dc"], p["features_rest"],
+                                             p["opacities_raw"], d(s["viewmat"]), d(s["projmat"]), s["fx"], s["fy"], s["cx"],
+                                             s["cy"], H, W, s["degrees_to_use"], background=d(s["background"]),
+                                             block_width=s["block_width"])
+        assert_float_parity(rgb, z["ref_rgb"], "rgb", max_frac_bad=2e-4)
+        assert_float_parity(depth[..., 0], z["ref_depth"], "depth", max_frac_bad=2e-4)
+        assert_float_parity(alpha[..., 0], z["ref_alpha"], "alpha", max_frac_bad=2e-4, atol=1e-6)
+        torch.autograd.backward([rgb, depth, alpha], [d(z["up_v_rgb"]), d(z["up_v_depth"])[..., None], d(z["up_v_alpha"])[..., None]])
+        got = dict(v_means3d=means.grad, v_scales_raw=p["scales_raw"].grad, v_quats_raw=p["quats_raw"].grad,
+                   v_opacities_raw=p["opacities_raw"].grad, v_features_dc=p["features_dc"].grad,
+                   v_features_rest=p["features_rest"].grad)
+        for k, v in got.items():
+            assert_float_parity(to_np(v).reshape(z["ref_" + k].shape), z["ref_" + k], k, max_norm_rel=3e-4, max_frac_bad=3e-3)

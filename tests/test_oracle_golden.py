@@ -20,7 +20,8 @@ def _scene_from_npz(z):
 
 
 TORCH_IMPL = sorted(glob.glob(os.path.join(GOLD, "torch_impl_*.npz")))
-REFCUDA = sorted(glob.glob(os.path.join(GOLD, "refcuda_*.npz")))
+REFCUDA = sorted(p for p in glob.glob(os.path.join(GOLD, "refcuda_*.npz")) if "modelstep" not in p)
+MODELSTEP = sorted(glob.glob(os.path.join(GOLD, "refcuda_modelstep_*.npz")))
 
 
 def test_golden_fixtures_present():
@@ -72,4 +73,21 @@ def test_oracle_vs_reference_cuda_ext(oracle, path):
     assert_int_equal(out["final_idx"], z["ref_final_idx"], "final_idx", mask=clean, max_frac_bad=1e-4)
     # gradients: the reference sums with order-nondeterministic FP32 atomics
     for k in ("v_xy", "v_conic", "v_colors", "v_opacity", "v_coeffs", "v_mean3d", "v_scale", "v_quat"):
+        assert_float_parity(out[k], z["ref_" + k].reshape(out[k].shape), k, max_norm_rel=2e-4, max_frac_bad=2e-3)
+
+
+@pytest.mark.parametrize("path", MODELSTEP, ids=[os.path.basename(p) for p in MODELSTEP])
+def test_oracle_model_step_vs_reference_cuda_ext(oracle, path):
+    """The oracle's restatement of the model-level view (raw parameters -> rgb / depth / alpha) and of
+    the six raw-parameter gradients against the reference extension + torch autograd glue on a B200."""
+    z = np.load(path)
+    s = _scene_from_npz(z)
+    raw = {k[4:]: z[k] for k in z.files if k.startswith("raw_")}
+    out = oracle.render_fused_reference(s, raw, z["up_v_rgb"], z["up_v_depth"], z["up_v_alpha"])
+    clean = out["ambiguous"] == 0
+    assert_float_parity(out["rgb"], z["ref_rgb"], "rgb", mask=np.broadcast_to(clean[..., None], out["rgb"].shape))
+    assert_float_parity(out["depth"], z["ref_depth"], "depth", mask=clean)
+    assert_float_parity(out["alpha"], z["ref_alpha"], "alpha", mask=clean, atol=1e-6)
+    assert_int_equal(out["radii"], z["ref_radii"], "radii", max_frac_bad=1e-3)
+    for k in ("v_means3d", "v_scales_raw", "v_quats_raw", "v_opacities_raw", "v_features_dc", "v_features_rest"):
         assert_float_parity(out[k], z["ref_" + k].reshape(out[k].shape), k, max_norm_rel=2e-4, max_frac_bad=2e-3)
