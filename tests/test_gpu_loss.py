@@ -1,0 +1,59 @@
+"""GPU parity of the fused L1 + SSIM loss (rasterizer.losses.l1_ssim_loss) against the torch
+restatement of the reference's loss (oracle/ssim_ref.py: vanilla_gs.py:926-934 + pytorch_msssim's algorithm) in FP64,
+value and gradient; tolerance 1e-4 relative (FP32 kernel vs FP64 reference)."""
+import numpy as np
+import pytest
+import torch
+
+from parity import assert_float_parity
+
+pytestmark = pytest.mark.gpu
+
+
+def _images(H, W, seed, smooth=True):
+    g = torch.Generator().manual_seed(seed)
+    a = torch.rand(H, W, 3, generator=g)
+    b = torch.rand(H, W, 3, generator=g)
+    if smooth:  # structured images (blurred noise) with a related ground truth: SSIM away from 0
+        k = torch.ones(3, 1, 5, 5) / 25
+        a = torch.nn.functional.conv2d(a.permute(2, 0, 1)[None], k, padding=2, groups=3)[0].permute(1, 2, 0).contiguous()
+        b = (0.7 * a + 0.3 * b).clamp(0, 1).contiguous()
+    return a, b
+
+
+@pytest.mark.parametrize("H,W,lam,smooth", [(11, 11, 0.2, False), (37, 53, 0.2, True), (64, 48, 0.5, False),
+                                            (240, 320, 0.2, True), (1080, 1920, 0.2, True)])
+def test_l1_ssim_loss_value_and_gradient(H, W, lam, smooth):
+    from oracle.ssim_ref import l1_ssim_loss as ref_loss
+    from rasterizer.losses import l1_ssim_loss
+
+    pred_c, gt_c = _images(H, W, seed=H * 1000 + W, smooth=smooth)
+    pred = pred_c.cuda().requires_grad_(True)
+    gt = gt_c.cuda()
+    loss, l1, ssim = l1_ssim_loss(pred, gt, lam, return_terms=True)
+    (loss * 3.0).backward()  # non-unit upstream gradient
+    p64 = pred_c.double().cuda().requires_grad_(True)
+    rl, rl1, rs = ref_loss(p64, gt_c.double().cuda(), lam)
+    (rl * 3.0).backward()
+    print(f"[loss {H}x{W}] ours {float(loss):.8f} ref {float(rl):.8f}  l1 {float(l1):.6f}/{float(rl1):.6f}  ssim {float(ssim):.6f}/{float(rs):.6f}")
+    assert abs(float(loss) - float(rl)) <= 1e-5 * abs(float(rl)) + 1e-7
+    assert abs(float(l1) - float(rl1)) <= 1e-5 * abs(float(rl1)) + 1e-7
+    assert abs(float(ssim) - float(rs)) <= 2e-5 * abs(float(rs)) + 1e-6
+    assert_float_parity(pred.grad, p64.grad, "d loss / d pred", max_norm_rel=1e-4, max_frac_bad=1e-4)
+
+
+def test_l1_ssim_loss_errors_and_determinism():
+    from rasterizer.losses import l1_ssim_loss
+
+    a, b = _images(40, 50, 3)
+    with pytest.raises(ValueError):
+        l1_ssim_loss(a.cuda()[:10], b.cuda()[:10])
+    with pytest.raises(ValueError):
+        l1_ssim_loss(a.cuda(), b.cuda()[:, :40])
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        l1_ssim_loss(a, b)
+    x = l1_ssim_loss(a.cuda(), b.cuda())
+    y = l1_ssim_loss(a.cuda(), b.cuda())
+    assert torch.equal(x, y)
+    same = l1_ssim_loss(a.cuda(), a.cuda())
+    assert abs(float(same)) < 1e-6     # identical images: L1 = 0, SSIM = 1

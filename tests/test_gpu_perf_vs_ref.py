@@ -247,3 +247,42 @@ def test_cfg2_model_style_step_fused_vs_reference():
             rel = float((x - a).norm() / a.norm())
             print(f"[model step] grad {nme:14s} {tag:8s} vs reference ext: normwise rel {rel:.2e}")
             assert rel < 5e-4
+
+
+def test_l1_ssim_loss_timing_1080p():
+    """fused L1+SSIM (one stencil kernel each way) vs the torch formulation the reference model runs
+    (pytorch_msssim's grouped convolutions, restated in oracle/ssim_ref.py), forward + backward at 1920x1080, FP32."""
+    from oracle.ssim_ref import l1_ssim_loss as ref_loss
+    from rasterizer.losses import l1_ssim_loss
+
+    g = torch.Generator(device="cuda").manual_seed(0)
+    pred = torch.rand(1080, 1920, 3, device="cuda", generator=g).requires_grad_(True)
+    gt = torch.rand(1080, 1920, 3, device="cuda", generator=g)
+
+    def run(fn):
+        pred.grad = None
+        out = fn(pred, gt, 0.2)
+        loss = out[0] if isinstance(out, tuple) else out
+        loss.backward()
+        return loss
+
+    def timeit(fn, iters=20, warm=5):
+        ts = []
+        for i in range(warm + iters):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            run(fn)
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= warm:
+                ts.append(e0.elapsed_time(e1))
+        return statistics.median(ts)
+
+    t_ref, t_ours = timeit(ref_loss), timeit(l1_ssim_loss)
+    P = 1080 * 1920
+    algo_bytes = 24 * P + 36 * (1070 * 1910) + 36 * (1070 * 1910) + 24 * P + 12 * P
+    rep = {"workload": "L1 + 0.2 (1 - SSIM) forward+backward, 1920x1080x3 FP32", "torch_formulation_ms": t_ref,
+           "fused_ms": t_ours, "speedup": t_ref / t_ours, "fused_algorithmic_GBps": algo_bytes / (t_ours * 1e-3) / 1e9}
+    print(json.dumps(rep, indent=1))
+    json.dump(rep, open(os.path.join(ROOT, "gpurun_out", "perf_loss.json"), "w"), indent=1)
+    assert t_ours < t_ref

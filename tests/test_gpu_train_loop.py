@@ -4,7 +4,8 @@ comet_ml, pytorch_msssim, torchmetrics are absent): a short training run of the 
 multi-view scene, three times from the same initial state:
   (ref)   the unmodified reference CUDA extension behind reference-style autograd wrappers + torch glue,
   (ours)  this package's drop-in operators + the same torch glue,
-  (fused) this package's fused operator.
+  (fused) this package's fused operator,
+  (fused+loss) the fused operator and the fused L1+SSIM loss kernel.
 Loss = 0.8 L1 + 0.2 (1 - SSIM) (SSIM restated from pytorch_msssim defaults: 11x11 Gaussian window, sigma 1.5, valid
 padding), six Adam groups with the reference learning rates, no densification (f2 is out of scope).  Checks: the loss
 goes down, the three runs reach the same PSNR, and records iterations/s (gpurun_out/train_loop.json)."""
@@ -60,6 +61,7 @@ def test_short_training_run_three_backends():
     from oracle import oracle as orc
     from oracle.build_ref import load_ref
     from rasterizer.fused import render_gaussians
+    from rasterizer.losses import l1_ssim_loss
     from rasterizer.sh import spherical_harmonics
     from rasterizer.synthetic import make_scene
     from ref_autograd import make_ops
@@ -97,7 +99,7 @@ def test_short_training_run_three_backends():
 
     ours_ops = (spherical_harmonics, rasterizer.project_gaussians,
                 lambda xys, d, r, c, n_, col, op_: rasterizer.rasterize_gaussians(xys, d, r, c, n_, col, op_, H, W, BW, background=bg))
-    backends = {"ours": render_glue(ours_ops), "fused": render_fused}
+    backends = {"ours": render_glue(ours_ops), "fused": render_fused, "fused+loss": render_fused}
     ref_ext = load_ref()
     if ref_ext is not None:
         r_sh, r_proj, r_rast = make_ops(ref_ext)
@@ -120,9 +122,12 @@ def test_short_training_run_three_backends():
             cam, gt = cams[it % len(cams)], gts[it % len(cams)]
             opt.zero_grad(set_to_none=True)
             pred = torch.clamp(render(p, cam), max=1.0)
-            l1 = (gt - pred).abs().mean()
-            sim = 1 - _ssim(gt.permute(2, 0, 1)[None], pred.permute(2, 0, 1)[None])
-            loss = 0.8 * l1 + 0.2 * sim
+            if name == "fused+loss":   # the fused photometric loss kernel (f3) instead of the torch formulation
+                loss = l1_ssim_loss(pred, gt, 0.2)
+            else:
+                l1 = (gt - pred).abs().mean()
+                sim = 1 - _ssim(gt.permute(2, 0, 1)[None], pred.permute(2, 0, 1)[None])
+                loss = 0.8 * l1 + 0.2 * sim
             loss.backward()
             opt.step()
             if it % 20 == 0 or it == iters + warm - 1:
@@ -138,6 +143,7 @@ def test_short_training_run_three_backends():
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(report, open(os.path.join(ROOT, "gpurun_out", "train_loop.json"), "w"), indent=1)
     assert abs(report["ours"]["psnr"] - report["fused"]["psnr"]) < 0.3
+    assert abs(report["fused+loss"]["psnr"] - report["fused"]["psnr"]) < 0.3
     if "ref" in report:
         assert abs(report["ours"]["psnr"] - report["ref"]["psnr"]) < 0.3
         assert abs(report["fused"]["psnr"] - report["ref"]["psnr"]) < 0.3
