@@ -60,7 +60,7 @@ SIGNATURES = {
     "gsr_blend_packed_forward": (_i, [_u, _u, _u, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "gsr_blend_packed_backward": (_i, [_u, _u, _u, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "gsr_l1_ssim_num_partials": (_i, [_u, _u]),
-    "gsr_l1_ssim_forward": (_i, [_u, _u, _p, _p, _p, _p, _p]),
+    "gsr_l1_ssim_forward": (_i, [_u, _u, _f, _p, _p, _p, _p, _p, _p]),
     "gsr_l1_ssim_backward": (_i, [_u, _u, _f, _p, _p, _p, _p, _p, _p]),
 }
 

@@ -36,12 +36,11 @@ class _L1SSIM(Function):
         n = lib.gsr_l1_ssim_num_partials(H, W)
         maps = torch.empty((3, H - 10, W - 10, 3), dtype=torch.float32, device=pred.device)
         partials = torch.empty((n, 2), dtype=torch.float32, device=pred.device)
+        out = torch.empty((3,), dtype=torch.float32, device=pred.device)
         with _Guard(pred) as st:
-            _lib.check(lib.gsr_l1_ssim_forward(H, W, _ptr(pred), _ptr(gt), _ptr(maps), _ptr(partials), st), "l1_ssim_forward")
-        sums = partials.sum(dim=0, dtype=torch.float64)
-        ssim = (sums[0] / (3.0 * (H - 10) * (W - 10))).float()
-        l1 = (sums[1] / (3.0 * H * W)).float()
-        loss = (1.0 - ssim_lambda) * l1 + ssim_lambda * (1.0 - ssim)
+            _lib.check(lib.gsr_l1_ssim_forward(H, W, ssim_lambda, _ptr(pred), _ptr(gt), _ptr(maps), _ptr(partials), _ptr(out),
+                                               st), "l1_ssim_forward")
+        loss, l1, ssim = out[0], out[1], out[2]
         ctx.ssim_lambda = ssim_lambda
         ctx.save_for_backward(pred, gt, maps)
         ctx.mark_non_differentiable(l1, ssim)

@@ -279,14 +279,14 @@ GSR_API int gsr_blend_packed_backward(unsigned img_height, unsigned img_width, u
  *   loss = (1 - ssim_lambda) * mean|gt - pred| + ssim_lambda * (1 - SSIM(gt, pred))
  * with SSIM = pytorch_msssim.SSIM(data_range=1.0, size_average=True, channel=3) (third-party, not vendored in the
  * reference; algorithm restated in csrc/loss.cu).  pred, gt: [H,W,3] (the rasterizer's layout), H, W >= 11.
- *   gsr_l1_ssim_forward : maps [3][H-10][W-10][3] (derivative maps kept for the adjoint) and partials [n][2] with
- *                         n = gsr_l1_ssim_num_partials(H, W): per-CTA {sum SSIM, sum |pred-gt|}; the caller sums them
- *                         (deterministic) and forms the loss.
+ *   gsr_l1_ssim_forward : maps [3][H-10][W-10][3] (derivative maps kept for the adjoint), partials [n][2] scratch with
+ *                         n = gsr_l1_ssim_num_partials(H, W) (per-CTA {sum SSIM, sum |pred-gt|}, reduced in FP64 by a
+ *                         one-CTA finalisation kernel => deterministic), loss_l1_ssim [3] = {loss, L1, SSIM}.
  *   gsr_l1_ssim_backward: v_pred [H,W,3] = v_loss * d loss / d pred  (v_loss: device scalar, NULL = 1).
  * ---------------------------------------------------------------------------------------------- */
 GSR_API int gsr_l1_ssim_num_partials(unsigned img_height, unsigned img_width);
-GSR_API int gsr_l1_ssim_forward(unsigned img_height, unsigned img_width, const float *pred, const float *gt,
-                                float *maps, float *partials, void *stream);
+GSR_API int gsr_l1_ssim_forward(unsigned img_height, unsigned img_width, float ssim_lambda, const float *pred,
+                                const float *gt, float *maps, float *partials, float *loss_l1_ssim, void *stream);
 GSR_API int gsr_l1_ssim_backward(unsigned img_height, unsigned img_width, float ssim_lambda, const float *pred,
                                  const float *gt, const float *maps, const float *v_loss /*nullable: 1.0*/,
                                  float *v_pred, void *stream);
