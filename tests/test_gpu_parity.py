@@ -542,3 +542,48 @@ def test_public_api_nd_colors_forward_backward(oracle):
     assert_float_parity(alpha, 1 - fT, "nd alpha", atol=1e-6)
     assert_float_parity(cols.grad, g[2], "nd v_colors", max_norm_rel=5e-3, max_frac_bad=1.0)
     assert_float_parity(opac.grad, g[3], "nd v_opacity", max_norm_rel=5e-3, max_frac_bad=1.0)
+
+
+def test_antialiased_mode_and_depth_supervision_gradients(oracle):
+    """The autograd contract of SURVEY 8(b): `compensation` carries gradient in rasterize_mode="antialiased"
+    (opacity * compensation, models/vanilla_gs.py:815-816) and `depths` carries gradient when rendered as colours
+    (depth supervision, models/depth_gs.py:346-361) — both reach project_gaussians' backward as v_compensation / v_depth."""
+    import rasterizer
+    from rasterizer.synthetic import look_at_viewmat, make_scene, scene_to_torch
+
+    scene = make_scene(3000, 128, 96, 0.03, 0.25, margin=1.05, seed=88, viewmat=look_at_viewmat(yaw_deg=8.0, pitch_deg=-5.0))
+    s = scene_to_torch(scene, "cuda")
+    H, W, bw, N = 96, 128, 16, 3000
+    means = s["means3d"].clone().requires_grad_(True)
+    scales = s["scales"].clone().requires_grad_(True)
+    quats = s["quats"].clone().requires_grad_(True)
+    xys, depths, radii, conics, comp, nth, cov3d = rasterizer.project_gaussians(
+        means, scales, 1.0, quats, s["viewmat"], s["projmat"], s["fx"], s["fy"], s["cx"], s["cy"], H, W, bw)
+    opac = s["opacities"].reshape(-1, 1) * comp[:, None]                    # antialiased opacity
+    depth_img = rasterizer.rasterize_gaussians(xys, depths, radii, conics, nth, depths[:, None].repeat(1, 3), opac, H, W, bw,
+                                               background=torch.zeros(3, device="cuda"))
+    (depth_img * s["v_out_img"]).sum().backward()
+
+    # oracle: same chain with numpy glue
+    cov3d_o, xys_o, depths_o, radii_o, conics_o, comp_o, nth_o = oracle.project_forward(
+        scene["means3d"], scene["scales"], 1.0, scene["quats"], scene["viewmat"], scene["projmat"], scene["fx"], scene["fy"],
+        scene["cx"], scene["cy"], H, W, bw)
+    m, cum = oracle.compute_cumulative_intersects(nth_o)
+    tb = ((W + bw - 1) // bw, (H + bw - 1) // bw, 1)
+    _, _, _, vs, bins = oracle.bin_and_sort_gaussians(N, m, xys_o, depths_o, radii_o, cum, tb, bw)
+    opac_o = (scene["opacities"] * comp_o).astype(np.float32)
+    cols_o = np.repeat(depths_o[:, None], 3, axis=1).astype(np.float32)
+    bg0 = np.zeros(3, np.float32)
+    img_o, fT, fi = oracle.rasterize_forward(H, W, bw, vs, bins, xys_o, conics_o, cols_o, opac_o, bg0)
+    v_xy, v_conic, v_cols, v_op = oracle.rasterize_backward(H, W, bw, vs, bins, xys_o, conics_o, cols_o, opac_o, bg0, fT, fi,
+                                                            scene["v_out_img"], np.zeros((H, W), np.float32), dtype=np.float32)
+    v_depth = v_cols.sum(axis=1).astype(np.float32)                       # depths[:, None].repeat(1, 3)
+    v_comp = (v_op[:, 0] * scene["opacities"]).astype(np.float32)          # opacity * compensation
+    _, _, v_mean, v_scale, v_quat = oracle.project_backward(
+        scene["means3d"], scene["scales"], 1.0, scene["quats"], scene["viewmat"], scene["projmat"], scene["fx"], scene["fy"],
+        scene["cx"], scene["cy"], H, W, cov3d_o, radii_o, conics_o, comp_o, v_xy, v_depth, v_conic, v_comp)
+    assert float(np.abs(v_comp).max()) > 0 and float(np.abs(v_depth).max()) > 0
+    assert_float_parity(depth_img, img_o, "depth image", max_frac_bad=1e-3)
+    assert_float_parity(means.grad, v_mean, "v_mean3d (with v_depth, v_compensation)", max_norm_rel=3e-4, max_frac_bad=3e-3)
+    assert_float_parity(scales.grad, v_scale, "v_scale", max_norm_rel=3e-4, max_frac_bad=3e-3)
+    assert_float_parity(quats.grad, v_quat, "v_quat", max_norm_rel=3e-4, max_frac_bad=3e-3)
