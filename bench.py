@@ -74,7 +74,7 @@ def peaks():
 
 # ----------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms during the timed region."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -88,7 +88,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -205,7 +205,7 @@ class ResidentView:
             N, s["means3d"], s["scales"], s["glob_scale"], s["quats"], s["viewmat"], s["projmat"], s["fx"], s["fy"],
             s["cx"], s["cy"], H, W, cov3d, radii, conics, comp, v_xy, self.zeros_n, v_conic, self.zeros_n,
             out_mean3d=None if bk is None else bk["v_mean3d"], out_scale=None if bk is None else bk["v_scale"],
-            out_quat=None if bk is None else bk["v_quat"])
+            out_quat=None if bk is None else bk["v_quat"], need_cov_grads=False)
         self._mark(rec)
         if rec is not None:
             self.events.append(rec)
@@ -342,6 +342,39 @@ def timed_loop(torch, dist, world, fn, steps, warmup, finish=None):
     return float(ms.item())
 
 
+def fused_leg(torch, s, scene_np, steps, warmup):
+    """Informational: the same view through the FUSED operator rasterizer.fused.render_gaussians, which also
+    folds the model's activations (exp / normalise / sigmoid / SH concat / clamp) in; rgb + alpha, same upstream gradients."""
+    import numpy as np
+    from rasterizer.fused import render_gaussians
+
+    o = np.clip(scene_np["opacities"].astype(np.float64), 1e-6, 1 - 1e-6)
+    dev = s["means3d"].device
+    raw = [s["means3d"].clone(), torch.log(s["scales"]), s["quats"].clone(), s["sh_coeffs"][:, 0, :].contiguous(),
+           s["sh_coeffs"][:, 1:, :].contiguous(), torch.from_numpy(np.log(o / (1 - o)).astype(np.float32)).to(dev)[:, None]]
+    raw = [t.requires_grad_(True) for t in raw]
+    H, W = s["img_height"], s["img_width"]
+    v_alpha = s["v_out_alpha"][..., None].contiguous()
+
+    def step():
+        for t in raw:
+            t.grad = None
+        rgb, _, alpha = render_gaussians(*raw, s["viewmat"], s["projmat"], s["fx"], s["fy"], s["cx"], s["cy"], H, W,
+                                         s["degrees_to_use"], background=s["background"], block_width=s["block_width"],
+                                         render_depth=False)
+        torch.autograd.backward([rgb, alpha], [s["v_out_img"], v_alpha])
+
+    ms = timed_loop(torch, None, 1, step, steps, warmup)
+    return {"value": steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps,
+            "what": "render_gaussians(raw parameters) fwd+bwd, resident inputs; not the headline (reference-facing API) path"}
+
+
+def workload_text(name, scene_np):
+    N, W, H = scene_np["means3d"].shape[0], scene_np["img_width"], scene_np["img_height"]
+    return (f"{name}: {N} Gaussians, {W}x{H}, SH degree {scene_np['sh_degree']}, fwd+bwd, block_width "
+            f"{scene_np['block_width']}, seeded scene of SURVEY 8(d)")
+
+
 def make_scene_for_rank(workload, rank):
     from rasterizer.synthetic import look_at_viewmat, make_config_scene
 
@@ -401,7 +434,8 @@ def main():
             "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: seeded synthetic scene of SURVEY 8(d), CPU path"},
+            "config": {"workload": workload_text(args.workload, scene_np), "path": "CPU (oracle port), all host threads",
+                       "pixels": scene_np["img_height"] * scene_np["img_width"]},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
@@ -507,8 +541,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {N} Gaussians, {W}x{H}, SH degree {s['sh_degree']}, fwd+bwd, "
-                                   f"block_width {bw}, seeded scene of SURVEY 8(d)",
+            "config": {"workload": workload_text(args.workload, scene_np),
                        "num_intersects_after_exact_tile_culling": M, "num_intersects_reference_bbox": M_ref, "pixels": P, "tiles": T, "parallelism": f"view-parallel x{world}",
                        "l2_policy": "inputs larger than L2 (192 MB SH coefficients + 192 MB SH gradients per view; "
                                     "no explicit flush)"},
@@ -522,6 +555,8 @@ def main():
                                  "resident leg only",
             "clocks": clocks, "roofline": roofline,
         }
+        if world == 1:
+            line["fused_operator"] = fused_leg(torch, s, scene_np, args.steps, args.warmup)
         if world == 1 and not args.no_cpu_baseline:
             v, desc, cores, _ = cpu_leg(scene_np, 25.0)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}

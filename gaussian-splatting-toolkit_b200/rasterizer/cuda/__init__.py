@@ -178,7 +178,9 @@ def project_gaussians_backward(num_points: int, means3d: Tensor, scales: Tensor,
                                img_height: int, img_width: int, cov3d: Tensor, radii: Tensor, conics: Tensor,
                                compensation: Tensor, v_xy: Tensor, v_depth: Tensor, v_conic: Tensor,
                                v_compensation: Tensor, *, out_mean3d: Tensor = None, out_scale: Tensor = None,
-                               out_quat: Tensor = None):
+                               out_quat: Tensor = None, need_cov_grads: bool = True):
+    """`need_cov_grads=False` skips v_cov2d / v_cov3d (the reference binding returns them, its Python wrapper discards
+    them, rasterizer/project_gaussians.py:178,203-232): the first two return values are then None."""
     for t, n in ((means3d, "means3d"), (scales, "scales"), (quats, "quats"), (viewmat, "viewmat"),
                  (projmat, "projmat"), (cov3d, "cov3d"), (conics, "conics"), (compensation, "compensation"),
                  (v_xy, "v_xy"), (v_depth, "v_depth"), (v_conic, "v_conic"), (v_compensation, "v_compensation")):
@@ -186,8 +188,8 @@ def project_gaussians_backward(num_points: int, means3d: Tensor, scales: Tensor,
     _check_input(radii, "radii", torch.int32)
     dev = means3d.device
     f32 = dict(dtype=torch.float32, device=dev)
-    v_cov2d = torch.empty((num_points, 3), **f32)
-    v_cov3d = torch.empty((num_points, 6), **f32)
+    v_cov2d = torch.empty((num_points, 3), **f32) if need_cov_grads else None
+    v_cov3d = torch.empty((num_points, 6), **f32) if need_cov_grads else None
     v_mean3d = _out_or_empty(out_mean3d, (num_points, 3), dev, "out_mean3d")
     v_scale = _out_or_empty(out_scale, (num_points, 3), dev, "out_scale")
     v_quat = _out_or_empty(out_quat, (num_points, 4), dev, "out_quat")
@@ -196,8 +198,8 @@ def project_gaussians_backward(num_points: int, means3d: Tensor, scales: Tensor,
             num_points, _ptr(means3d), _ptr(scales), float(glob_scale), _ptr(quats), _ptr(viewmat), _ptr(projmat),
             float(fx), float(fy), float(cx), float(cy), int(img_height), int(img_width), _ptr(cov3d), _ptr(radii),
             _ptr(conics), _ptr(compensation), _ptr(v_xy), _ptr(v_depth), _ptr(v_conic), _ptr(v_compensation),
-            _ptr(v_cov2d), _ptr(v_cov3d), _ptr(v_mean3d), _ptr(v_scale), _ptr(v_quat), st),
-            "project_gaussians_backward")
+            _ptr(v_cov2d) if need_cov_grads else None, _ptr(v_cov3d) if need_cov_grads else None, _ptr(v_mean3d),
+            _ptr(v_scale), _ptr(v_quat), st), "project_gaussians_backward")
     return v_cov2d, v_cov3d, v_mean3d, v_scale, v_quat
 
 

@@ -58,5 +58,6 @@ class _ProjectGaussians(Function):
         _, _, v_mean3d, v_scale, v_quat = _C.project_gaussians_backward(
             num_points, means3d, scales, glob_scale, quats, viewmat, projmat, fx, fy, cx, cy, img_height,
             img_width, cov3d, radii, conics, compensation, dense(v_xys, means3d[:, :2]),
-            dense(v_depths, compensation), dense(v_conics, conics), dense(v_compensation, compensation))
+            dense(v_depths, compensation), dense(v_conics, conics), dense(v_compensation, compensation),
+            need_cov_grads=False)
         return (v_mean3d, v_scale, None, v_quat, None, None, None, None, None, None, None, None, None, None)
