@@ -9,19 +9,30 @@
 //
 // Kernel structure = blend_fwd.cu / blend_bwd.cu (double-buffered record ring, 8x4-pixel warps, ballot compaction
 // against the alpha >= 1/255 extent box, warp-uniform loops, transposing-butterfly reduction, one RED per
-// (warp, Gaussian)); differences: the record is gathered with three 128-bit loads (no per-pair extent maths), the
-// depth rides in r2.w, and gradients land in one 48-byte record per Gaussian
+// (warp, Gaussian)); differences: the record is gathered with three 16-byte cp.async copies (LDGSTS) straight into the
+// shared-memory ring — no register staging, no per-pair extent maths —, the depth rides in r2.w, and gradients land in
+// one 48-byte record per Gaussian
 // {v_x, v_y, v_opacity, v_depth | v_a, v_b, v_c, - | v_r, v_g, v_b, -}.
 #include "blend_common.cuh"
 
 namespace gsr {
 
-__device__ __forceinline__ BlendRecord gather_packed(int g, int n, const float4 *__restrict__ rec) {
-  BlendRecord r;
-  r.r0 = __ldg(rec + g);
-  r.r1 = __ldg(rec + n + g);
-  r.r2 = __ldg(rec + 2 * (size_t)n + g);
-  return r;
+// Asynchronous global -> shared copy of one 16-byte record plane entry (cp.async / LDGSTS): the gathered record goes
+// straight into the shared-memory ring without passing through registers, and the copy of batch b+1 is in flight while
+// batch b is composited.
+__device__ __forceinline__ void cp_async16(float4 *smem_dst, const float4 *gmem_src) {
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// stage the record of Gaussian g into slot `slot` of ring buffer `buf`
+__device__ __forceinline__ void stage_packed(float4 (*s_rec)[3][BLEND_THREADS], int buf, int slot, int g, int n,
+                                             const float4 *__restrict__ rec) {
+  cp_async16(&s_rec[buf][0][slot], rec + g);
+  cp_async16(&s_rec[buf][1][slot], rec + n + g);
+  cp_async16(&s_rec[buf][2][slot], rec + 2 * (size_t)n + g);
 }
 
 template <bool DEPTH>
@@ -55,20 +66,20 @@ blend_packed_forward_kernel(int tiles_x, int img_w, int img_h, int block_width, 
   int cur_idx = 0;
   float acc_r = 0.f, acc_g = 0.f, acc_b = 0.f, acc_d = 0.f;
 
-  BlendRecord r;
-  if (num_batches > 0 && range.x + tr < range.y) r = gather_packed(gaussian_ids_sorted[range.x + tr], num_points, rec);
+  // 2-stage cp.async ring: batch b lives in buffer b & 1; its copies were issued one iteration earlier
+  if (num_batches > 0 && range.x + tr < range.y)
+    stage_packed(s_rec, 0, tr, gaussian_ids_sorted[range.x + tr], num_points, rec);
+  cp_async_commit();
   for (int b = 0; b < num_batches; ++b) {
     const int buf = b & 1;
     const int batch_start = range.x + nthreads * b;
-    if (batch_start + tr < range.y) {
-      s_rec[buf][0][tr] = r.r0;
-      s_rec[buf][1][tr] = r.r1;
-      s_rec[buf][2][tr] = r.r2;
-    }
+    cp_async_wait_all();  // this thread's copies for batch b have landed ...
+    // ... and the barrier publishes everyone's; it also tells that buffer buf ^ 1 (batch b-1) is no longer read
     if (__syncthreads_count(done) >= nthreads) break;
     {
       const int nxt = batch_start + nthreads + tr;
-      if (nxt < range.y) r = gather_packed(gaussian_ids_sorted[nxt], num_points, rec);
+      if (nxt < range.y) stage_packed(s_rec, buf ^ 1, tr, gaussian_ids_sorted[nxt], num_points, rec);
+      cp_async_commit();
     }
     if (__all_sync(full, done)) continue;
     const int batch_size = min(nthreads, range.y - batch_start);
@@ -219,28 +230,25 @@ blend_packed_backward_kernel(int tiles_x, int img_w, int img_h, int block_width,
     dst_slot = 1;
   }
 
-  BlendRecord r;
-  int gid = 0;
   if (end - 1 - tr >= range.x) {
-    gid = gaussian_ids_sorted[end - 1 - tr];
-    r = gather_packed(gid, num_points, rec);
+    const int gid = gaussian_ids_sorted[end - 1 - tr];
+    s_gid[0][tr] = gid;
+    stage_packed(s_rec, 0, tr, gid, num_points, rec);
   }
+  cp_async_commit();
   for (int b = 0; b < num_batches; ++b) {
     const int buf = b & 1;
     const int batch_end = end - 1 - nthreads * b;
-    if (batch_end - tr >= range.x) {
-      s_rec[buf][0][tr] = r.r0;
-      s_rec[buf][1][tr] = r.r1;
-      s_rec[buf][2][tr] = r.r2;
-      s_gid[buf][tr] = gid;
-    }
+    cp_async_wait_all();
     __syncthreads();
     {
       const int nxt = batch_end - nthreads - tr;
       if (nxt >= range.x) {
-        gid = gaussian_ids_sorted[nxt];
-        r = gather_packed(gid, num_points, rec);
+        const int gid = gaussian_ids_sorted[nxt];
+        s_gid[buf ^ 1][tr] = gid;
+        stage_packed(s_rec, buf ^ 1, tr, gid, num_points, rec);
       }
+      cp_async_commit();
     }
     const int batch_size = min(nthreads, batch_end + 1 - range.x);
     const int t_begin = max(0, batch_end - warp_bin_final);
