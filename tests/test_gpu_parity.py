@@ -422,7 +422,23 @@ def _exchange_worker(rank, world, port, results):
             exchange_gradients(p2p, v_rgb * scale, means, cam, 3, 3, peer=peer)
             torch.cuda.synchronize()
             err_p2p = max(err_p2p, float((p2p.flat - plain.flat * scale).norm() / (plain.flat.norm() * scale)))
-    results[rank] = (err, err_p2p)
+    # (d) the autograd form: spherical_harmonics_view_parallel returns the same colours as spherical_harmonics and a
+    #     coefficient gradient that is already the sum over ranks
+    from rasterizer.sh import spherical_harmonics
+    from rasterizer.view_parallel import spherical_harmonics_view_parallel
+
+    coeffs = torch.randn(N, K, 3, generator=torch.Generator().manual_seed(70)).cuda()
+    c1 = coeffs.clone().requires_grad_(True)
+    col1 = spherical_harmonics_view_parallel(3, means, cam, c1)
+    c2 = coeffs.clone().requires_grad_(True)
+    col2 = spherical_harmonics(3, (means - cam[None]).contiguous(), c2)
+    col1.backward(v_rgb)
+    col2.backward(v_rgb)
+    summed = c2.grad.clone()
+    dist.all_reduce(summed)
+    torch.cuda.synchronize()
+    err_ag = float((c1.grad - summed).norm() / summed.norm()) + float((col1 - col2).abs().max())
+    results[rank] = (err, err_p2p, err_ag)
     dist.destroy_process_group()
 
 
@@ -437,6 +453,7 @@ def test_exchange_gradients_matches_plain_allreduce_2gpu():
     print("[exchange vs all-reduce] normwise rel err per rank (nccl all-gather path, NVLink peer path):", dict(results))
     assert all(results[r][0] < 1e-6 for r in range(2))
     assert all(results[r][1] < 1e-6 for r in range(2))   # -1 = symmetric memory unavailable on this box
+    assert all(results[r][2] < 1e-6 for r in range(2))   # autograd form (spherical_harmonics_view_parallel)
 
 
 def test_gaussian_rasterizer_facade_matches_operators(oracle):
