@@ -76,7 +76,7 @@ blend_forward_kernel(int tiles_x, int img_w, int img_h, int block_width,
     if (__all_sync(full, done)) continue;  // this warp is finished; it still stages and syncs
 
     const int batch_size = min(nthreads, range.y - batch_start);
-    const int n_list = compact_survivors(s_rec[buf][0], 0, batch_size, fx0, fx1, fy0, fy1, s_list[warp], lane);
+    const int n_list = compact_survivors(s_rec[buf][0], s_rec[buf][1], 0, batch_size, fx0, fx1, fy0, fy1, s_list[warp], lane);
     for (int i = 0; i < n_list; ++i) {
       const int t = s_list[warp][i];
       const float4 q0 = s_rec[buf][0][t];

@@ -83,7 +83,7 @@ blend_packed_forward_kernel(int tiles_x, int img_w, int img_h, int block_width, 
     }
     if (__all_sync(full, done)) continue;
     const int batch_size = min(nthreads, range.y - batch_start);
-    const int n_list = compact_survivors(s_rec[buf][0], 0, batch_size, fx0, fx1, fy0, fy1, s_list[warp], lane);
+    const int n_list = compact_survivors(s_rec[buf][0], s_rec[buf][1], 0, batch_size, fx0, fx1, fy0, fy1, s_list[warp], lane);
     for (int i = 0; i < n_list; ++i) {
       const int t = s_list[warp][i];
       const float4 q0 = s_rec[buf][0][t];
@@ -253,7 +253,7 @@ blend_packed_backward_kernel(int tiles_x, int img_w, int img_h, int block_width,
     const int batch_size = min(nthreads, batch_end + 1 - range.x);
     const int t_begin = max(0, batch_end - warp_bin_final);
     if (t_begin >= batch_size) continue;
-    const int n_list = compact_survivors(s_rec[buf][0], t_begin, batch_size, fx0, fx1, fy0, fy1, s_list[warp], lane);
+    const int n_list = compact_survivors(s_rec[buf][0], s_rec[buf][1], t_begin, batch_size, fx0, fx1, fy0, fy1, s_list[warp], lane);
     for (int i = 0; i < n_list; ++i) {
       const int t = s_list[warp][i];
       const float4 q0 = s_rec[buf][0][t];
