@@ -19,7 +19,7 @@ CSRC_DIR = os.path.join(_ROOT, "csrc")
 _lock = threading.Lock()
 _lib = None
 
-_i, _u, _f, _p, _sz = C.c_int, C.c_uint, C.c_float, C.c_void_p, C.c_size_t
+_i, _u, _f, _d, _p, _sz = C.c_int, C.c_uint, C.c_float, C.c_double, C.c_void_p, C.c_size_t
 
 # name -> (restype, argtypes); kept in the order of include/gsr_b200.h
 SIGNATURES = {
@@ -62,6 +62,12 @@ SIGNATURES = {
     "gsr_l1_ssim_num_partials": (_i, [_u, _u]),
     "gsr_l1_ssim_forward": (_i, [_u, _u, _f, _p, _p, _p, _p, _p, _p]),
     "gsr_l1_ssim_backward": (_i, [_u, _u, _f, _p, _p, _p, _p, _p, _p]),
+    "gsr_adam_step_multi": (_i, [_i, _p, _p, _p, _p, _p, _p, _p, _d, _d, _d, _f, _p]),
+    "gsr_opacity_reset": (_i, [_i, _f, _p, _p, _p, _p]),
+    "gsr_densify_stats_update": (_i, [_i, _p, _i, _p, _f, _i, _p, _p, _p, _p]),
+    "gsr_densify_plan_workspace_bytes": (_sz, [_i]),
+    "gsr_densify_plan": (_i, [_i, _p, _p, _p, _p, _p, _i, _f, _f, _f, _i, _f, _f, _i, _f, _i, _f, _p, _p, _p, _p, _sz, _p]),
+    "gsr_densify_apply": (_i, [_i, _i, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p]),
 }
 
 

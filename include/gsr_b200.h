@@ -291,6 +291,69 @@ GSR_API int gsr_l1_ssim_backward(unsigned img_height, unsigned img_width, float 
                                  const float *gt, const float *maps, const float *v_loss /*nullable: 1.0*/,
                                  float *v_pred, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Optimizer step — replaces the six torch.optim.Adam(lr, eps=1e-15).step() calls of
+ * gs_toolkit/engine/optimizers.py:173-180 (groups / learning rates: configs/method_configs.py:98-125) by ONE launch
+ * over up to GSR_ADAM_MAX_SEGMENTS tensors.  The `_host` arrays are HOST arrays of length num_segments holding device
+ * pointers / element counts / the group's learning rate / the group's step number t >= 1 (the value of
+ * state["step"] AFTER the increment, torch/optim/adam.py).  Arithmetic of torch's Adam (amsgrad = False,
+ * weight_decay = 0): m += (g - m)(1 - beta1); v = v beta2 + (1 - beta2) g g;
+ * p -= lr / (1 - beta1^t) * m / (sqrt(v) / sqrt(1 - beta2^t) + eps), with g multiplied by `grad_scale` first
+ * (1 / world_size turns the summed view-parallel gradient into DDP's mean, pipelines/base_pipeline.py:202-207).
+ * gsr_opacity_reset: opacities = min(opacities, max_logit) and the group's Adam moments = 0
+ * (gs_toolkit/models/vanilla_gs.py:472-489).
+ * ---------------------------------------------------------------------------------------------- */
+#define GSR_ADAM_MAX_SEGMENTS 8
+GSR_API int gsr_adam_step_multi(int num_segments, float *const *params_host, const float *const *grads_host,
+                                float *const *exp_avg_host, float *const *exp_avg_sq_host,
+                                const int64_t *numels_host, const double *lrs_host, const int64_t *steps_host,
+                                double beta1, double beta2, double eps, float grad_scale, void *stream);
+GSR_API int gsr_opacity_reset(int num_points, float max_logit, float *opacities_raw, float *exp_avg /*nullable*/,
+                              float *exp_avg_sq /*nullable*/, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Adaptive density control — replaces gs_toolkit/models/vanilla_gs.py after_train :344-372,
+ * refinement_after :381-497, cull_gaussians :499-535, split_gaussians :537-581, dup_gaussians :583-592 and the Adam
+ * state surgery remove_from_optim :282-300 / dup_in_optim :308-337.
+ *  gsr_densify_stats_update : per view. xys_grad is read with a row stride of `xys_grad_stride` floats (2 for a dense
+ *      [N,2] tensor, 12 for the grad_records of the fused operator); max_dim = max(image width, height);
+ *      first != 0 when the statistics are unset (None in the reference).
+ *  gsr_densify_plan : flags [N] u8 (bit0 split, bit1 duplicate, bit2 original survives, bit3 its split samples
+ *      survive, bit4 its duplicate survives), ranks [N,4] i32 (exclusive ranks among {split, surviving originals,
+ *      surviving splits, surviving duplicates}; 16-byte aligned), counts [4] i32 on the DEVICE = the four totals.
+ *      do_densify = 0 is the cull-only branch (:462-466): the three statistics may then be NULL unless
+ *      use_cull_screen.  cull_big = (step > refine_every * reset_alpha_every) (:513).
+ *  gsr_densify_apply : counts_host = the four totals read back by the caller; N' = counts[1] + n_split_samples *
+ *      counts[2] + counts[3] rows are written to every dst tensor (row order: surviving originals, split samples
+ *      sample-major, duplicates).  samples [n_split_samples * counts[0], 3] are the standard-normal draws of
+ *      split_gaussians (:543-545), row s * counts[0] + (rank of the source among ALL split Gaussians).
+ *      kinds: COPY (new rows copy their source), MEANS (split samples get mean + R(q)(exp(s) z)), SCALES (rows whose
+ *      source was split get log(exp(s) / 1.6)), ZERO_NEW (Adam moments: zeros for new rows).  src and dst must not
+ *      alias.  map [N'] u32 is scratch (destination row -> source row).
+ * ---------------------------------------------------------------------------------------------- */
+#define GSR_DENSIFY_MAX_TENSORS 24
+typedef enum gsr_densify_kind {
+  GSR_DENSIFY_COPY = 0,
+  GSR_DENSIFY_MEANS = 1,
+  GSR_DENSIFY_SCALES = 2,
+  GSR_DENSIFY_ZERO_NEW = 3
+} gsr_densify_kind;
+GSR_API int gsr_densify_stats_update(int num_points, const float *xys_grad, int xys_grad_stride, const int32_t *radii,
+                                     float max_dim, int first, float *xys_grad_norm, float *vis_counts,
+                                     float *max_2Dsize, void *stream);
+GSR_API size_t gsr_densify_plan_workspace_bytes(int num_points);
+GSR_API int gsr_densify_plan(int num_points, const float *scales_raw, const float *opacities_raw,
+                             const float *xys_grad_norm, const float *vis_counts, const float *max_2Dsize,
+                             int do_densify, float max_dim, float densify_grad_thresh, float densify_size_thresh,
+                             int use_split_screen, float split_screen_size, float cull_alpha_thresh, int cull_big,
+                             float cull_scale_thresh, int use_cull_screen, float cull_screen_size, uint8_t *flags,
+                             int32_t *ranks, int32_t *counts, void *workspace, size_t workspace_bytes, void *stream);
+GSR_API int gsr_densify_apply(int num_points, int n_split_samples, const int32_t *counts_host, const uint8_t *flags,
+                              const int32_t *ranks, const float *samples, const float *means, const float *scales_raw,
+                              const float *quats_raw, int num_tensors, const float *const *src_host,
+                              float *const *dst_host, const int32_t *widths_host, const int32_t *kinds_host,
+                              uint32_t *map, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
