@@ -158,6 +158,7 @@ struct GatherSegment {
   int width;          // floats per row
   int kind;           // gsr_densify_kind
   int rows_per_cta;
+  unsigned magic;     // ceil(2^32 / width)
 };
 struct GatherLaunch {
   GatherSegment seg[GSR_DENSIFY_MAX_TENSORS];
@@ -170,38 +171,63 @@ struct GatherLaunch {
   const float *means, *scales_raw, *quats_raw;
 };
 
+constexpr int GATHER_MAX_ROWS = 4096;   // rows per CTA (width-1 tensors); wider rows use 4096 / width, at least 32
+
+// One CTA moves `rows_per_cta` destination rows of ONE tensor: the row map is staged in shared memory with one
+// coalesced read, then the elements are streamed with destination-contiguous (fully coalesced) writes; the loop is
+// specialised per tensor kind and unrolled so that several independent gathers are in flight per thread.
+template <int KIND>
+__device__ __forceinline__ void gather_rows(const GatherLaunch &L, const GatherSegment &S, const unsigned *s_map,
+                                            long long row0, int total) {
+  const int w = S.width;
+  const unsigned magic = S.magic;   // ceil(2^32 / w): j / w == umulhi(j, magic) for j < 2^17, w <= 4096
+  const float *__restrict__ src = S.src;
+  float *__restrict__ dst = S.dst + row0 * w;
+#pragma unroll 4
+  for (int j = threadIdx.x; j < total; j += blockDim.x) {
+    const int lr = (w == 1) ? j : (int)__umulhi((unsigned)j, magic), c = j - lr * w;
+    const unsigned code = s_map[lr];
+    const unsigned from = code & ((1u << MAP_KIND_SHIFT) - 1u), kind = code >> MAP_KIND_SHIFT;
+    float val;
+    if (KIND == GSR_DENSIFY_ZERO_NEW) {
+      val = (kind == MAP_ORIG) ? __ldg(src + (size_t)from * w + c) : 0.f;
+    } else if (KIND == GSR_DENSIFY_SCALES) {
+      val = __ldg(src + (size_t)from * w + c);
+      if (L.flags[from] & DF_SPLIT) val = logf(expf(val) / 1.6f);  // :563-569 (children, and the duplicate of a split)
+    } else if (KIND == GSR_DENSIFY_MEANS) {
+      val = __ldg(src + (size_t)from * w + c);
+      if (kind == MAP_SPLIT) {
+        // new_means = R(q/|q|) (exp(scales) * z) + mean  (:543-553); z = samples[s * n_split + split rank]
+        const int s = (int)((row0 + lr - L.n_keep_orig) / L.n_keep_split);
+        const float *z = L.samples + ((size_t)s * L.n_split + L.ranks[from].x) * 3;
+        const float *sc = L.scales_raw + (size_t)from * 3, *q = L.quats_raw + (size_t)from * 4;
+        float R[9];
+        quat_to_rotmat(q[0], q[1], q[2], q[3], R);
+        const float v0 = expf(sc[0]) * z[0], v1 = expf(sc[1]) * z[1], v2 = expf(sc[2]) * z[2];
+        val = (R[3 * c] * v0 + R[3 * c + 1] * v1 + R[3 * c + 2] * v2) + val;
+      }
+    } else {
+      val = __ldg(src + (size_t)from * w + c);
+    }
+    dst[j] = val;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 densify_gather_kernel(const __grid_constant__ GatherLaunch L) {
+  __shared__ unsigned s_map[GATHER_MAX_ROWS];
   const GatherSegment &S = L.seg[blockIdx.y];
   const long long row0 = (long long)blockIdx.x * S.rows_per_cta;
   if (row0 >= L.new_n) return;
   const int rows = (int)min((long long)S.rows_per_cta, (long long)L.new_n - row0);
-  const int w = S.width, total = rows * w;
-  float *__restrict__ dst = S.dst + row0 * w;
-  for (int j = threadIdx.x; j < total; j += blockDim.x) {
-    const int lr = j / w, c = j - lr * w;
-    const long long r = row0 + lr;
-    const unsigned code = L.map[r];
-    const unsigned src = code & ((1u << MAP_KIND_SHIFT) - 1u), kind = code >> MAP_KIND_SHIFT;
-    float val;
-    if (S.kind == GSR_DENSIFY_ZERO_NEW) {
-      val = (kind == MAP_ORIG) ? S.src[(size_t)src * w + c] : 0.f;
-    } else if (S.kind == GSR_DENSIFY_SCALES) {
-      val = S.src[(size_t)src * w + c];
-      if (L.flags[src] & DF_SPLIT) val = logf(expf(val) / 1.6f);  // :563-569 (children, and the duplicate of a split)
-    } else if (S.kind == GSR_DENSIFY_MEANS && kind == MAP_SPLIT) {
-      // new_means = R(q/|q|) (exp(scales) * z) + mean  (:543-553); z = samples[s * n_split + split rank]
-      const int s = (int)((r - L.n_keep_orig) / L.n_keep_split);
-      const float *z = L.samples + ((size_t)s * L.n_split + L.ranks[src].x) * 3;
-      const float *sc = L.scales_raw + (size_t)src * 3, *q = L.quats_raw + (size_t)src * 4;
-      float R[9];
-      quat_to_rotmat(q[0], q[1], q[2], q[3], R);
-      const float v0 = expf(sc[0]) * z[0], v1 = expf(sc[1]) * z[1], v2 = expf(sc[2]) * z[2];
-      val = (R[3 * c] * v0 + R[3 * c + 1] * v1 + R[3 * c + 2] * v2) + L.means[(size_t)src * 3 + c];
-    } else {
-      val = S.src[(size_t)src * w + c];
-    }
-    dst[j] = val;
+  for (int i = threadIdx.x; i < rows; i += blockDim.x) s_map[i] = L.map[row0 + i];
+  __syncthreads();
+  const int total = rows * S.width;
+  switch (S.kind) {
+    case GSR_DENSIFY_ZERO_NEW: gather_rows<GSR_DENSIFY_ZERO_NEW>(L, S, s_map, row0, total); break;
+    case GSR_DENSIFY_SCALES: gather_rows<GSR_DENSIFY_SCALES>(L, S, s_map, row0, total); break;
+    case GSR_DENSIFY_MEANS: gather_rows<GSR_DENSIFY_MEANS>(L, S, s_map, row0, total); break;
+    default: gather_rows<GSR_DENSIFY_COPY>(L, S, s_map, row0, total); break;
   }
 }
 
@@ -332,8 +358,9 @@ GSR_API int gsr_densify_apply(int num_points, int n_split_samples, const int32_t
     S.dst = dst_host[k];
     S.width = widths_host[k];
     S.kind = kinds_host[k];
-    const int rpc = 4096 / S.width;
+    const int rpc = GATHER_MAX_ROWS / S.width;
     S.rows_per_cta = rpc < 32 ? 32 : rpc;
+    S.magic = S.width == 1 ? 0u : (unsigned)((0x100000000ull + (unsigned)S.width - 1) / (unsigned)S.width);
     const unsigned gx = (unsigned)((new_n + S.rows_per_cta - 1) / S.rows_per_cta);
     grid_x = gx > grid_x ? gx : grid_x;
   }

@@ -106,6 +106,8 @@ class _RenderGaussians(Function):
             z = torch.zeros_like
             grads = (z(means3d), z(scales), z(quats), torch.zeros(n, 3, device=means3d.device),
                      torch.zeros(n, k_rest, 3, device=means3d.device), z(opacities))
+            if ctx.aux is not None:
+                ctx.aux.xys_grad = torch.zeros(n, 2, device=means3d.device)
         else:
             rec, radii, conics, mask, ids_sorted, tile_bins, background, final_Ts, final_idx = saved[6:]
             v_rgb = v_rgb.contiguous()

@@ -1,0 +1,236 @@
+"""On-disk formats either side of the hot path — pure host code (numpy / torch CPU):
+
+  * checkpoints  `step-%09d.ckpt` exactly as `Trainer.save_checkpoint` writes them (gs_toolkit/engine/trainer.py:443-476):
+        {"step", "pipeline": {"_model.gauss_params.<name>": tensor, ...}, "optimizers": {group: Adam.state_dict()},
+         "schedulers": {group: LambdaLR.state_dict()}, "scalers": GradScaler.state_dict()}
+    and as `Trainer._load_checkpoint` / `Pipeline.load_pipeline` / `GaussianSplattingModel.load_state_dict` read them
+    (trainer.py:404-441, pipelines/base_pipeline.py:355-367, models/vanilla_gs.py:236-258: "module." prefix stripped,
+    pre-`gauss_params` names remapped, parameters resized to the stored Gaussian count);
+  * `transforms.json`  the reference's own dataset format (data/dataparsers/gs_toolkit_dataparser.py:77-457): frames
+    sorted by file name, intrinsics global or per frame, train / eval split by fraction (dataparsers_utils.py:10-32) or
+    by explicit `<split>_filenames`, poses oriented ("up") and centred ("poses") as camera_utils.py:552-668 does by
+    default, optional auto-scale; images are NOT decoded here (no image library in this image) — file names are
+    returned;
+  * `camera_to_view_proj`  camera-to-world (OpenGL axes) -> the (viewmat, projmat, fovs) the operators take, i.e. the
+    per-view prologue of `get_outputs` (vanilla_gs.py:722-741, utils/comms.py:103-123).
+"""
+from __future__ import annotations
+
+import json
+import math
+import os
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from .synthetic import projection_matrix
+
+GROUPS = ("means", "scales", "quats", "features_dc", "features_rest", "opacities")
+_PREFIX = "_model.gauss_params."
+
+
+# ------------------------------------------------------------------------------------------------- checkpoints
+def checkpoint_path(checkpoint_dir: str, step: int) -> str:
+    return os.path.join(checkpoint_dir, f"step-{step:09d}.ckpt")
+
+
+def save_checkpoint(checkpoint_dir: str, step: int, params: Dict[str, torch.Tensor], optimizers=None,
+                    schedulers: Optional[Dict[str, dict]] = None, save_only_latest_checkpoint: bool = True,
+                    extra_pipeline_state: Optional[Dict[str, torch.Tensor]] = None) -> str:
+    """trainer.py:443-476.  `optimizers` is a rasterizer.optim.GaussianOptimizers (or anything with a
+    `state_dict()` returning {group: Adam.state_dict()}), or None."""
+    os.makedirs(checkpoint_dir, exist_ok=True)
+    path = checkpoint_path(checkpoint_dir, step)
+    pipeline = {_PREFIX + k: v.detach().cpu() for k, v in params.items()}
+    if extra_pipeline_state:
+        pipeline.update({k: v.detach().cpu() for k, v in extra_pipeline_state.items()})
+    opt_sd = {}
+    if optimizers is not None:
+        for name, sd in optimizers.state_dict().items():
+            opt_sd[name] = {"state": {i: {k: (v.detach().cpu() if torch.is_tensor(v) else v) for k, v in st.items()}
+                                      for i, st in sd["state"].items()}, "param_groups": sd["param_groups"]}
+    torch.save({"step": step, "pipeline": pipeline, "optimizers": opt_sd, "schedulers": schedulers or {},
+                "scalers": {}}, path)
+    if save_only_latest_checkpoint:
+        for f in os.listdir(checkpoint_dir):
+            if os.path.join(checkpoint_dir, f) != path:
+                os.unlink(os.path.join(checkpoint_dir, f))
+    return path
+
+
+def latest_checkpoint_step(load_dir: str) -> int:
+    """trainer.py:410-416 (specific to the `step-<n>.ckpt` name format)."""
+    return sorted(int(x[x.find("-") + 1: x.find(".")]) for x in os.listdir(load_dir))[-1]
+
+
+def load_checkpoint(load_dir_or_file: str, load_step: Optional[int] = None, device="cpu") -> Dict[str, object]:
+    """Returns {"step", "params": {name: tensor}, "optimizers": {group: Adam.state_dict()}, "schedulers", "extra"}.
+    Accepts checkpoints written by the reference trainer (incl. DDP "module." prefixes and the pre-gauss_params
+    parameter names) and by `save_checkpoint`."""
+    path = load_dir_or_file
+    if os.path.isdir(path):
+        step = latest_checkpoint_step(path) if load_step is None else load_step
+        path = checkpoint_path(path, step)
+    assert os.path.exists(path), f"Checkpoint {path} does not exist"
+    loaded = torch.load(path, map_location="cpu", weights_only=False)
+    state = {(k[len("module."):] if k.startswith("module.") else k): v for k, v in loaded["pipeline"].items()}
+    params, extra = {}, {}
+    for k, v in state.items():
+        if k.startswith(_PREFIX):
+            params[k[len(_PREFIX):]] = v
+        elif k.startswith("_model.") and k[len("_model."):] in GROUPS:   # old checkpoints (vanilla_gs.py:239-251)
+            params.setdefault(k[len("_model."):], v)
+        else:
+            extra[k] = v
+    missing = [g for g in GROUPS if g not in params]
+    if missing:
+        raise RuntimeError(f"checkpoint {path} holds no Gaussian parameters {missing}")
+    n = params["means"].shape[0]
+    for k, v in params.items():
+        if v.shape[0] != n:
+            raise RuntimeError(f"checkpoint {path}: {k} has {v.shape[0]} rows, means has {n}")
+    params = {k: v.to(device=device, dtype=torch.float32).contiguous() for k, v in params.items()}
+    return {"step": int(loaded["step"]), "params": params, "optimizers": loaded.get("optimizers", {}),
+            "schedulers": loaded.get("schedulers", {}), "extra": extra, "path": path}
+
+
+# ------------------------------------------------------------------------------------------------- cameras
+def camera_to_view_proj(camera_to_world: np.ndarray, fx: float, fy: float, width: int, height: int,
+                        znear: float = 0.001, zfar: float = 1000.0) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """vanilla_gs.py:722-741: flip y and z of the camera axes (OpenGL -> the operator's +z-forward convention),
+    invert analytically, projmat = projection_matrix(0.001, 1000, fovx, fovy) @ viewmat.
+    Returns (viewmat [4,4], projmat [4,4] full projection, camera position [3]), float32."""
+    c2w = np.asarray(camera_to_world, dtype=np.float64)
+    R = c2w[:3, :3] @ np.diag([1.0, -1.0, -1.0])
+    T = c2w[:3, 3:4]
+    V = np.eye(4)
+    V[:3, :3] = R.T
+    V[:3, 3:4] = -R.T @ T
+    fovx = 2 * math.atan(width / (2 * fx))
+    fovy = 2 * math.atan(height / (2 * fy))
+    P = projection_matrix(znear, zfar, fovx, fovy).astype(np.float64)
+    return V.astype(np.float32), (P @ V).astype(np.float32), c2w[:3, 3].astype(np.float32)
+
+
+def _rotation_matrix(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """camera_utils.py:462-493 (rotation taking a to b); float32 arithmetic like the reference."""
+    a = (a / np.linalg.norm(a)).astype(np.float32)
+    b = (b / np.linalg.norm(b)).astype(np.float32)
+    v = np.cross(a, b)
+    c = np.dot(a, b)
+    if c < -1 + 1e-8:
+        raise ValueError("average up vector is exactly opposite to +z (the reference perturbs it randomly)")
+    s = np.linalg.norm(v)
+    K = np.array([[0, -v[2], v[1]], [v[2], 0, -v[0]], [-v[1], v[0], 0]], dtype=np.float32)
+    return (np.eye(3, dtype=np.float32) + K + (K @ K) * ((1 - c) / (s ** 2 + 1e-8))).astype(np.float32)
+
+
+def auto_orient_and_center_poses(poses: np.ndarray, method: str = "up", center_method: str = "poses"):
+    """camera_utils.py:552-668 for the methods the reference's dataparser uses by default ("up" / "none" orientation,
+    "poses" / "none" centring).  poses: [n,4,4] or [n,3,4] camera-to-world.  Returns (poses [n,3,4], transform [3,4])."""
+    poses = np.asarray(poses, dtype=np.float32)
+    if poses.shape[-2] == 3:
+        poses = np.concatenate([poses, np.tile(np.array([[[0, 0, 0, 1]]], np.float32), (poses.shape[0], 1, 1))], axis=1)
+    origins = poses[:, :3, 3]
+    mean_origin = origins.mean(axis=0)
+    if center_method == "poses":
+        translation = mean_origin
+    elif center_method == "none":
+        translation = np.zeros_like(mean_origin)
+    else:
+        raise NotImplementedError(f"center_method {center_method!r} (only 'poses' and 'none')")
+    if method == "up":
+        up = poses[:, :3, 1].mean(axis=0)
+        up = up / np.linalg.norm(up)
+        rotation = _rotation_matrix(up, np.array([0, 0, 1], np.float32))
+        transform = np.concatenate([rotation, rotation @ -translation[:, None]], axis=-1)
+        oriented = transform @ poses
+    elif method == "none":
+        transform = np.eye(4, dtype=np.float32)
+        transform[:3, 3] = -translation
+        transform = transform[:3, :]
+        oriented = transform @ poses
+    else:
+        raise NotImplementedError(f"orientation method {method!r} (only 'up' and 'none')")
+    return oriented.astype(np.float32), transform.astype(np.float32)
+
+
+def train_eval_split_fraction(num_images: int, train_split_fraction: float):
+    """dataparsers_utils.py:10-32."""
+    num_train = math.ceil(num_images * train_split_fraction)
+    i_all = np.arange(num_images)
+    i_train = np.linspace(0, num_images - 1, num_train, dtype=int)
+    i_eval = np.setdiff1d(i_all, i_train)
+    assert len(i_eval) == num_images - num_train
+    return i_train, i_eval
+
+
+def load_transforms(data: str, split: str = "train", train_split_fraction: float = 0.9,
+                    orientation_method: str = "up", center_method: str = "poses", auto_scale_poses: bool = False,
+                    scale_factor: float = 1.0, downscale_factor: int = 1) -> Dict[str, object]:
+    """gs_toolkit_dataparser.py:77-457 for perspective cameras.  `data` is a directory holding transforms.json or the
+    json file itself.  Returns {"image_filenames": [...], "camera_to_worlds": [n,3,4], "fx","fy","cx","cy": [n] float32,
+    "height","width": [n] int32, "transform": [3,4], "scale_factor": float, "indices": [n]} for the requested split."""
+    assert os.path.exists(data), f"Data directory {data} does not exist."
+    if data.endswith(".json"):
+        meta_path, data_dir = data, os.path.dirname(data)
+    else:
+        meta_path, data_dir = os.path.join(data, "transforms.json"), data
+    with open(meta_path, "r", encoding="UTF-8") as f:
+        meta = json.load(f)
+    if "applied_scale" in meta:
+        scale_factor = meta["applied_scale"]
+
+    def fname(fp: str) -> str:
+        if downscale_factor > 1:
+            return os.path.join(data_dir, f"images_{downscale_factor}", os.path.basename(fp))
+        return os.path.join(data_dir, fp)
+
+    frames = meta["frames"]
+    frames = [frames[i] for i in np.argsort([fname(fr["file_path"]) for fr in frames])]
+    names: List[str] = [fname(fr["file_path"]) for fr in frames]
+    n = len(frames)
+
+    def intrinsic(key: str, cast):
+        if key in meta:
+            return np.full(n, cast(meta[key]))
+        for fr in frames:
+            assert key in fr, f"{key} not specified in frame"
+        return np.array([cast(fr[key]) for fr in frames])
+
+    fx, fy, cx, cy = (intrinsic(k, float).astype(np.float32) for k in ("fl_x", "fl_y", "cx", "cy"))
+    height, width = (intrinsic(k, int).astype(np.int32) for k in ("h", "w"))
+    poses = np.array([fr["transform_matrix"] for fr in frames], dtype=np.float32)
+
+    has_split_files_spec = any(f"{s}_filenames" in meta for s in ("train", "val", "test"))
+    if f"{split}_filenames" in meta:
+        wanted = set(fname(x) for x in meta[f"{split}_filenames"])
+        unmatched = wanted.difference(names)
+        if unmatched:
+            raise RuntimeError(f"Some filenames for split {split} were not found: {unmatched}.")
+        indices = np.array([i for i, p in enumerate(names) if p in wanted], dtype=np.int32)
+    elif has_split_files_spec:
+        raise RuntimeError(f"The dataset's list of filenames for split {split} is missing.")
+    else:
+        i_train, i_eval = train_eval_split_fraction(n, train_split_fraction)
+        if split == "train":
+            indices = i_train
+        elif split in ("val", "test"):
+            indices = i_eval
+        else:
+            raise ValueError(f"Unknown dataparser split {split}")
+
+    method = meta.get("orientation_override", orientation_method)
+    poses, transform = auto_orient_and_center_poses(poses, method=method, center_method=center_method)
+    s = 1.0
+    if auto_scale_poses:
+        s /= float(np.max(np.abs(poses[:, :3, 3])))
+    s *= scale_factor
+    poses[:, :3, 3] *= s
+    idx = np.asarray(indices, dtype=np.int64)
+    d = float(downscale_factor)
+    return {"image_filenames": [names[i] for i in idx], "camera_to_worlds": poses[idx, :3, :4],
+            "fx": fx[idx] / d, "fy": fy[idx] / d, "cx": cx[idx] / d, "cy": cy[idx] / d,
+            "height": (height[idx] // downscale_factor).astype(np.int32), "width": (width[idx] // downscale_factor).astype(np.int32),
+            "transform": transform, "scale_factor": s, "indices": idx}

@@ -160,7 +160,8 @@ def test_stats_and_refinement_vs_reference_golden(path):
     info = refinement_after(params, opt, stats, cfg, step, int(z["meta_num_train_data"]), hw, samples=_cuda(z["samples"]))
     torch.cuda.synchronize()
     assert info["n_after"] == int(z["meta_n_after"]), info
-    assert stats.xys_grad_norm is None and stats.max_2Dsize is None
+    if step > cfg.warmup_length:   # the reference returns before touching the statistics during warm-up (:383-384)
+        assert stats.xys_grad_norm is None and stats.max_2Dsize is None
     for k in GROUPS:
         got = params[k].detach().cpu().numpy()
         assert params[k].requires_grad and params[k].is_leaf

@@ -1,0 +1,196 @@
+"""cfg3 (BASELINE configs[2]): training WITH adaptive density control on a synthetic 200-view scene,
+800x800, teacher = 200 k Gaussians rendered once, student = 100 k random Gaussians that densify.  `gs-train` itself
+cannot run here (gs_toolkit's dependencies are absent), so the per-iteration maths of the reference is restated
+(engine/trainer.py:478-498 train_iteration, models/vanilla_gs.py:759-947 get_outputs / get_loss_dict, :344-497
+after_train / refinement_after, configs/method_configs.py:98-125 optimizers + means scheduler) and run twice from the
+same initial state in the same harness:
+  (ref)  the unmodified reference CUDA extension behind reference-style autograd wrappers + the model's torch glue,
+         the torch SSIM formulation, six torch.optim.Adam, the torch densification (oracle restatement on the GPU);
+  (ours) fused render operator + fused L1/SSIM loss + one-launch Adam + densification kernels of this package.
+The refinement schedule is compressed (refine_every 25, reset interval 600, 1200 iterations) so that splitting,
+duplication, culling, the opacity reset and the cull-only phase all occur.  Checks: both runs converge to the same
+PSNR (the two trajectories are chaotic, not comparable element-wise) and end with a similar Gaussian count; records
+iterations/s (gpurun_out/train_cfg3.json)."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from test_gpu_train_loop import _ssim
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+H = W = 800
+BW = 16
+N_VIEWS = 200
+LRS = {"means": 1.6e-4, "features_dc": 0.0025, "features_rest": 0.0025 / 20, "opacities": 0.05, "scales": 0.005, "quats": 0.001}
+GROUPS = ("means", "scales", "quats", "features_dc", "features_rest", "opacities")
+CENTRE = (0.0, 0.0, 4.0)
+
+
+def _gaussians(n, seed, scale_lo, scale_hi, spread):
+    g = torch.Generator().manual_seed(seed)
+    U = lambda *s: torch.rand(*s, generator=g)
+    Nr = lambda *s: torch.randn(*s, generator=g)
+    means = Nr(n, 3) * spread + torch.tensor(CENTRE)
+    scales = torch.log(torch.exp(math.log(scale_lo) + (math.log(scale_hi) - math.log(scale_lo)) * U(n, 3)))
+    return {"means": means, "scales": scales, "quats": Nr(n, 4), "features_dc": (U(n, 3) - 0.5) / 0.28209479177387814,
+            "features_rest": Nr(n, 15, 3) * 0.03, "opacities": Nr(n, 1) * 1.5 + 0.5}
+
+
+def _cameras():
+    from rasterizer.synthetic import look_at_viewmat, projection_matrix
+
+    fov = math.radians(50.0)
+    fx = fy = 0.5 * W / math.tan(0.5 * fov)
+    P = projection_matrix(0.001, 1000.0, fov, fov).astype(np.float64)
+    cams = []
+    for ring in range(8):               # 8 rings x 25 cameras (the reference's synthetic recipe uses 8 x 20)
+        for k in range(N_VIEWS // 8):
+            V = look_at_viewmat(yaw_deg=360.0 * k / (N_VIEWS // 8) + 7.0 * ring, pitch_deg=-35.0 + 10.0 * ring, centre=CENTRE)
+            PM = (P @ V.astype(np.float64)).astype(np.float32)
+            cam_pos = (-V[:3, :3].T.astype(np.float64) @ V[:3, 3].astype(np.float64)).astype(np.float32)
+            cams.append(tuple(torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in (V, PM, cam_pos)))
+    return cams, fx, fy
+
+
+def test_cfg3_training_with_densification():
+    from oracle import densify_ref as dr
+    from oracle.build_ref import load_ref
+    from rasterizer.densify import DensifyConfig, DensifyStats, refinement_after
+    from rasterizer.fused import RenderAux, render_gaussians
+    from rasterizer.losses import l1_ssim_loss
+    from rasterizer.optim import GaussianOptimizers, default_means_scheduler
+    from ref_autograd import make_ops
+
+    cams, fx, fy = _cameras()
+    cx, cy = W / 2.0, H / 2.0
+    bg = torch.zeros(3, device="cuda")
+    cfg = DensifyConfig(warmup_length=100, refine_every=25, reset_alpha_every=24, stop_screen_size_at=800, stop_split_at=1000)
+    cfgd = dict(cfg.__dict__)
+    iters, sh_interval = 1200, 100
+    teacher = {k: v.cuda() for k, v in _gaussians(200_000, 100, 0.004, 0.03, 0.55).items()}
+    student0 = _gaussians(100_000, 101, 0.01, 0.03, 0.6)
+    student0["opacities"] = torch.full((100_000, 1), float(torch.logit(torch.tensor(0.1))))   # vanilla_gs.py:181
+    student0["features_rest"] = torch.zeros(100_000, 15, 3)
+
+    def render_fused(p, cam, deg, aux=None):
+        V, PM, _ = cam
+        rgb, _, _ = render_gaussians(p["means"], p["scales"], p["quats"], p["features_dc"], p["features_rest"], p["opacities"], V, PM,
+                                     fx, fy, cx, cy, H, W, deg, background=bg, render_depth=False, aux=aux)
+        return rgb
+
+    with torch.no_grad():
+        gts = [torch.clamp(render_fused(teacher, cam, 3), max=1.0) for cam in cams]
+    order = torch.randperm(iters, generator=torch.Generator().manual_seed(5)).tolist()
+    sched = default_means_scheduler()
+
+    def psnr_of(p):
+        with torch.no_grad():
+            mse = torch.stack([((torch.clamp(render_fused(p, cam, 3), max=1.0) - gt) ** 2).mean() for cam, gt in zip(cams[::4], gts[::4])])
+        return float((-10 * torch.log10(mse)).mean())
+
+    # ------------------------------------------------------------------ ours
+    def run_ours():
+        p = {k: v.clone().cuda().requires_grad_(True) for k, v in student0.items()}
+        opt = GaussianOptimizers(p, LRS, schedulers={"means": sched})
+        stats, aux = DensifyStats(), RenderAux()
+        torch.manual_seed(9)
+        counts = []
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for step in range(iters):
+            v = order[step] % N_VIEWS
+            opt.zero_grad_all()
+            pred = torch.clamp(render_fused(p, cams[v], min(step // sh_interval, 3), aux), max=1.0)
+            loss = l1_ssim_loss(pred, gts[v], 0.2)
+            loss.backward()
+            opt.optimizer_step_all()
+            opt.scheduler_step_all(step)
+            if step < cfg.stop_split_at:                         # after_train (:347-348)
+                stats.update(aux.xys_grad, aux.radii, (H, W))
+            if step % cfg.refine_every == 0:                     # refinement_after (callback every refine_every)
+                info = refinement_after(p, opt, stats, cfg, step, N_VIEWS, (H, W))
+                counts.append(info["n_after"])
+        e1.record()
+        torch.cuda.synchronize()
+        return p, e0.elapsed_time(e1) * 1e-3, counts
+
+    # ------------------------------------------------------------------ reference formulation
+    def run_ref(ops):
+        sh_fn, proj_fn, rast_fn = ops
+        p = {k: v.clone().cuda().requires_grad_(True) for k, v in student0.items()}
+        opts = {k: torch.optim.Adam([p[k]], lr=LRS[k], eps=1e-15) for k in GROUPS}
+        lam = torch.optim.lr_scheduler.LambdaLR(opts["means"], lr_lambda=lambda s: sched(s) / LRS["means"])
+        stats = {"xys_grad_norm": None, "vis_counts": None, "max_2Dsize": None}
+        torch.manual_seed(9)
+        counts = []
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for step in range(iters):
+            v = order[step] % N_VIEWS
+            V, PM, cam_pos = cams[v]
+            for o in opts.values():
+                o.zero_grad(set_to_none=True)
+            deg = min(step // sh_interval, 3)
+            scales, quats = torch.exp(p["scales"]), p["quats"] / p["quats"].norm(dim=-1, keepdim=True)
+            coeffs = torch.cat((p["features_dc"][:, None, :], p["features_rest"]), dim=1)
+            xys, depths, radii, conics, comp, nth, cov3d = proj_fn(p["means"], scales, 1.0, quats, V, PM, fx, fy, cx, cy, H, W, BW, 0.01)
+            xys.retain_grad()
+            rgbs = torch.clamp(sh_fn(deg, (p["means"].detach() - cam_pos[None]).contiguous(), coeffs) + 0.5, min=0.0)
+            rgb, _ = rast_fn(xys, depths, radii, conics, nth, rgbs, torch.sigmoid(p["opacities"]), H, W, BW, bg)
+            pred = torch.clamp(rgb, max=1.0)
+            gt = gts[v]
+            loss = 0.8 * (gt - pred).abs().mean() + 0.2 * (1 - _ssim(gt.permute(2, 0, 1)[None], pred.permute(2, 0, 1)[None]))
+            loss.backward()
+            for o in opts.values():
+                o.step()
+            lam.step()
+            with torch.no_grad():
+                if step < cfg.stop_split_at:
+                    dr.after_train(stats, xys.grad.detach(), radii, (H, W))
+                if step % cfg.refine_every == 0 and step > cfg.warmup_length:
+                    cur = {k: p[k].detach() for k in GROUPS}
+                    mom = {k: (opts[k].state[p[k]]["exp_avg"], opts[k].state[p[k]]["exp_avg_sq"]) for k in GROUPS}
+                    do_dens = step < cfg.stop_split_at and step % (cfg.reset_alpha_every * cfg.refine_every) > N_VIEWS + cfg.refine_every
+                    samples = None
+                    if do_dens:   # the draws of split_gaussians (:543-545)
+                        avg = (stats["xys_grad_norm"] / stats["vis_counts"]) * 0.5 * max(H, W)
+                        sp = cur["scales"].exp().max(dim=-1).values > cfg.densify_size_thresh
+                        if step < cfg.stop_screen_size_at:
+                            sp = sp | (stats["max_2Dsize"] > cfg.split_screen_size)
+                        samples = torch.randn((cfg.n_split_samples * int((sp & (avg > cfg.densify_grad_thresh)).sum()), 3), device="cuda")
+                    newp, newmom, info = dr.refinement_after(cur, mom, stats, cfgd, step, N_VIEWS, (H, W), samples)
+                    for k in GROUPS:   # remove_from_optim / dup_in_optim: new Parameter, state moved over
+                        st = opts[k].state.pop(p[k])
+                        p[k] = newp[k].contiguous().requires_grad_(True)
+                        st["exp_avg"], st["exp_avg_sq"] = newmom[k][0].contiguous(), newmom[k][1].contiguous()
+                        opts[k].param_groups[0]["params"] = [p[k]]
+                        opts[k].state[p[k]] = st
+                    stats = {"xys_grad_norm": None, "vis_counts": None, "max_2Dsize": None}
+                    counts.append(p["means"].shape[0])
+        e1.record()
+        torch.cuda.synchronize()
+        return p, e0.elapsed_time(e1) * 1e-3, counts
+
+    report = {"workload": f"cfg3: {N_VIEWS} views {W}x{H}, teacher 200k, student 100k -> densified, {iters} iterations, "
+                          f"L1 + 0.2 (1 - SSIM), 6 Adam groups, refinement every {cfg.refine_every}"}
+    p, t, counts = run_ours()
+    report["ours"] = {"iters_per_s": iters / t, "psnr": psnr_of(p), "n_final": int(p["means"].shape[0]), "n_max": max(counts)}
+    print("[cfg3] ours", report["ours"])
+    ref_ext = load_ref()
+    if ref_ext is not None:
+        p, t, counts = run_ref(make_ops(ref_ext))
+        report["ref"] = {"iters_per_s": iters / t, "psnr": psnr_of(p), "n_final": int(p["means"].shape[0]), "n_max": max(counts)}
+        print("[cfg3] ref ", report["ref"])
+        report["speedup"] = report["ours"]["iters_per_s"] / report["ref"]["iters_per_s"]
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(report, open(os.path.join(ROOT, "gpurun_out", "train_cfg3.json"), "w"), indent=1)
+    assert report["ours"]["n_max"] > 100_000, "densification never grew the set"
+    assert report["ours"]["psnr"] > 12.0
+    if "ref" in report:
+        assert abs(report["ours"]["psnr"] - report["ref"]["psnr"]) < 0.7, report
+        assert abs(report["ours"]["n_final"] - report["ref"]["n_final"]) < 0.2 * report["ref"]["n_final"], report
