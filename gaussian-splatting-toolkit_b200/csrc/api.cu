@@ -14,7 +14,7 @@ void set_error(const char *fmt, ...) {
 }  // namespace gsr
 
 extern "C" {
-GSR_API const char *gsr_version(void) { return "0.1.2+b200.1"; }
+GSR_API const char *gsr_version(void) { return "0.1.2+b200.2"; }
 GSR_API const char *gsr_last_error(void) { return gsr::g_err; }
 GSR_API int gsr_built_for_sm(void) { return 100; }
 }

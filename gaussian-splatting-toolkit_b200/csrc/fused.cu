@@ -94,7 +94,7 @@ fused_preprocess_forward_kernel(int n, int K, int deg_use, const float *__restri
                                 float clip_thresh, float4 *__restrict__ rec0, float4 *__restrict__ rec1,
                                 float4 *__restrict__ rec2, float *__restrict__ xys, float *__restrict__ depths,
                                 int *__restrict__ radii, float *__restrict__ conics, float *__restrict__ opac_act,
-                                int *__restrict__ clamp_mask, int vec_ok) {
+                                int *__restrict__ clamp_mask, float *__restrict__ compensation, int vec_ok) {
   extern __shared__ float smem[];
   __shared__ FusedCam cam;
   load_cam(cam, viewmat, projmat);
@@ -113,10 +113,15 @@ fused_preprocess_forward_kernel(int n, int K, int deg_use, const float *__restri
   const float s0 = glob_scale * __expf(scales_raw[3 * G]), s1 = glob_scale * __expf(scales_raw[3 * G + 1]),
               s2 = glob_scale * __expf(scales_raw[3 * G + 2]);
   const float4 q = reinterpret_cast<const float4 *>(quats_raw)[g];
-  const float opac = 1.f / (1.f + __expf(-opacities_raw[g]));
+  float opac = 1.f / (1.f + __expf(-opacities_raw[g]));
 
   const ProjFwd p = project_one(px, py, pz, s0, s1, s2, q.x, q.y, q.z, q.w, cam.V, cam.PM, fx, fy, cx, cy, img_w,
                                 img_h, tiles_x, tiles_y, block_width, clip_thresh);
+  // rasterize_mode == "antialiased": opacities = sigmoid(raw) * compensation (vanilla_gs.py:813-816)
+  if (compensation != nullptr) {
+    compensation[g] = p.comp;
+    opac *= p.comp;
+  }
 
   // SH colour (sh.cuh:33-98) + clamp(rgb + 0.5, min=0) (vanilla_gs.py:806-807)
   float Y[25];
@@ -160,7 +165,8 @@ fused_preprocess_backward_kernel(int n, int K, int deg_use, const float *__restr
                                  const float *__restrict__ opacities_raw, const float *__restrict__ viewmat,
                                  const float *__restrict__ projmat, float glob_scale, float fx, float fy, int img_w,
                                  int img_h, const int *__restrict__ radii, const float *__restrict__ conics,
-                                 const int *__restrict__ clamp_mask, const float4 *__restrict__ grad_rec,
+                                 const int *__restrict__ clamp_mask, const float *__restrict__ compensation,
+                                 const float4 *__restrict__ grad_rec,
                                  const float *__restrict__ v_xys_extra, float *__restrict__ v_means3d,
                                  float *__restrict__ v_scales_raw, float *__restrict__ v_quats_raw,
                                  float *__restrict__ v_opacities_raw, float *__restrict__ v_features_dc,
@@ -200,9 +206,13 @@ fused_preprocess_backward_kernel(int n, int K, int deg_use, const float *__restr
       vx += v_xys_extra[2 * G];
       vy += v_xys_extra[2 * G + 1];
     }
+    // antialiased: opacity = sigmoid(raw) * comp  =>  v_sigmoid = v_opacity * comp, v_comp = v_opacity * sigmoid(raw)
+    const float sig = 1.f / (1.f + __expf(-opacities_raw[g]));
+    const float comp = compensation != nullptr ? compensation[g] : 1.f;
+    const float v_comp = compensation != nullptr ? ga.z * sig : 0.f;
     const ProjBwd pg = project_one_vjp(visible, px, py, pz, e0, e1, e2, glob_scale, q.x, q.y, q.z, q.w, cam.V, cam.PM, fx,
-                                       fy, img_w, img_h, c3, conics[3 * G], conics[3 * G + 1], conics[3 * G + 2], 1.f,
-                                       vx, vy, ga.w, gb.x, gb.y, gb.z, 0.f);
+                                       fy, img_w, img_h, c3, conics[3 * G], conics[3 * G + 1], conics[3 * G + 2], comp,
+                                       vx, vy, ga.w, gb.x, gb.y, gb.z, v_comp);
     v_means3d[3 * G] = pg.mean[0];
     v_means3d[3 * G + 1] = pg.mean[1];
     v_means3d[3 * G + 2] = pg.mean[2];
@@ -219,10 +229,7 @@ fused_preprocess_backward_kernel(int n, int K, int deg_use, const float *__restr
                                                                (pg.quat[2] - h2 * d) * inv, (pg.quat[3] - h3 * d) * inv);
     }
     // opacity = sigmoid(raw)  =>  v_raw = v_opacity * o (1 - o)
-    {
-      const float o = 1.f / (1.f + __expf(-opacities_raw[g]));
-      v_opacities_raw[g] = ga.z * o * (1.f - o);
-    }
+    v_opacities_raw[g] = (ga.z * comp) * sig * (1.f - sig);
     // SH adjoint (sh.cuh:100-186) with the clamp mask; basis 0 -> features_dc, the others -> features_rest
     float Y[25];
     sh_basis_all(deg_use, px - cam.cam[0], py - cam.cam[1], pz - cam.cam[2], Y);
@@ -257,7 +264,8 @@ GSR_API int gsr_fused_preprocess_forward(int num_points, int sh_degree, int degr
                                          const float *projmat, float glob_scale, float fx, float fy, float cx, float cy,
                                          unsigned img_height, unsigned img_width, unsigned block_width,
                                          float clip_thresh, float *records, float *xys, float *depths, int32_t *radii,
-                                         float *conics, float *opacities, int32_t *clamp_mask, void *stream) {
+                                         float *conics, float *opacities, int32_t *clamp_mask,
+                                         float *compensation /*nullable*/, void *stream) {
   using namespace gsr;
   GSR_REQUIRE(num_points >= 0, GSR_ERR_INVALID_ARGUMENT, "fused_preprocess_forward: num_points < 0");
   GSR_REQUIRE(sh_degree >= 0 && sh_degree <= 4, GSR_ERR_UNSUPPORTED, "fused_preprocess_forward: sh_degree %d not in [0,4]", sh_degree);
@@ -280,7 +288,7 @@ GSR_API int gsr_fused_preprocess_forward(int num_points, int sh_degree, int degr
       num_points, K, degrees_to_use, means3d, scales_raw, quats_raw, opacities_raw, features_dc, features_rest, viewmat,
       projmat, glob_scale, fx, fy, cx, cy, (int)img_width, (int)img_height, (int)cdiv(img_width, block_width),
       (int)cdiv(img_height, block_width), (int)block_width, clip_thresh, rec, rec + num_points, rec + 2 * (size_t)num_points,
-      xys, depths, radii, conics, opacities, clamp_mask, vec_ok);
+      xys, depths, radii, conics, opacities, clamp_mask, compensation, vec_ok);
   GSR_CHECK_LAUNCH("fused_preprocess_forward_kernel");
   return GSR_OK;
 }
@@ -289,7 +297,8 @@ GSR_API int gsr_fused_preprocess_backward(int num_points, int sh_degree, int deg
                                           const float *scales_raw, const float *quats_raw, const float *opacities_raw,
                                           const float *viewmat, const float *projmat, float glob_scale, float fx,
                                           float fy, unsigned img_height, unsigned img_width, const int32_t *radii,
-                                          const float *conics, const int32_t *clamp_mask, const float *grad_records,
+                                          const float *conics, const int32_t *clamp_mask,
+                                          const float *compensation /*nullable*/, const float *grad_records,
                                           const float *v_xys_extra, float *v_means3d, float *v_scales_raw,
                                           float *v_quats_raw, float *v_opacities_raw, float *v_features_dc,
                                           float *v_features_rest, void *stream) {
@@ -311,7 +320,8 @@ GSR_API int gsr_fused_preprocess_backward(int num_points, int sh_degree, int deg
   const int vec_ok = ((uintptr_t)v_features_rest % 16 == 0) ? 1 : 0;
   fused_preprocess_backward_kernel<<<cdiv(num_points, FU_THREADS), FU_THREADS, smem, (cudaStream_t)stream>>>(
       num_points, K, degrees_to_use, means3d, scales_raw, quats_raw, opacities_raw, viewmat, projmat, glob_scale, fx, fy,
-      (int)img_width, (int)img_height, radii, conics, clamp_mask, reinterpret_cast<const float4 *>(grad_records),
+      (int)img_width, (int)img_height, radii, conics, clamp_mask, compensation,
+      reinterpret_cast<const float4 *>(grad_records),
       v_xys_extra, v_means3d, v_scales_raw, v_quats_raw, v_opacities_raw, v_features_dc, v_features_rest, vec_ok);
   GSR_CHECK_LAUNCH("fused_preprocess_backward_kernel");
   return GSR_OK;

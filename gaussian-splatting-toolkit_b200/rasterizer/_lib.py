@@ -54,8 +54,8 @@ SIGNATURES = {
     "gsr_nd_rasterize_backward": (_i, [_u, _u, _u, _u, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p,
                                        _p, _p, _p, _p]),
     "gsr_fused_preprocess_forward": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _f, _f, _f, _f, _f, _u, _u, _u, _f,
-                                          _p, _p, _p, _p, _p, _p, _p, _p]),
-    "gsr_fused_preprocess_backward": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _p, _f, _f, _f, _u, _u, _p, _p, _p, _p, _p,
+                                          _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "gsr_fused_preprocess_backward": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _p, _f, _f, _f, _u, _u, _p, _p, _p, _p, _p, _p,
                                            _p, _p, _p, _p, _p, _p, _p]),
     "gsr_blend_packed_forward": (_i, [_u, _u, _u, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "gsr_blend_packed_backward": (_i, [_u, _u, _u, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),

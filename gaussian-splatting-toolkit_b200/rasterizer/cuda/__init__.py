@@ -454,8 +454,10 @@ def nd_rasterize_backward(img_height, img_width, block_width, gaussians_ids_sort
 def fused_preprocess_forward(means3d: Tensor, scales_raw: Tensor, quats_raw: Tensor, opacities_raw: Tensor,
                              features_dc: Tensor, features_rest: Tensor, viewmat: Tensor, projmat: Tensor,
                              glob_scale: float, fx: float, fy: float, cx: float, cy: float, img_height: int,
-                             img_width: int, block_width: int, degrees_to_use: int, clip_thresh: float = 0.01):
-    """-> (records [3,N,4], xys [N,2], depths [N], radii [N] i32, conics [N,3], opacities [N], clamp_mask [N] i32)"""
+                             img_width: int, block_width: int, degrees_to_use: int, clip_thresh: float = 0.01,
+                             antialiased: bool = False):
+    """-> (records [3,N,4], xys [N,2], depths [N], radii [N] i32, conics [N,3], opacities [N], clamp_mask [N] i32,
+    compensation [N] | None).  `antialiased`: opacities = sigmoid(raw) * compensation (vanilla_gs.py:813-816)."""
     for t, nm in ((means3d, "means3d"), (scales_raw, "scales"), (quats_raw, "quats"), (opacities_raw, "opacities"),
                   (features_dc, "features_dc"), (features_rest, "features_rest"), (viewmat, "viewmat"),
                   (projmat, "projmat")):
@@ -471,18 +473,20 @@ def fused_preprocess_forward(means3d: Tensor, scales_raw: Tensor, quats_raw: Ten
     xys, depths = torch.empty((n, 2), **f32), torch.empty((n,), **f32)
     radii, conics = torch.empty((n,), **i32), torch.empty((n, 3), **f32)
     opac, mask = torch.empty((n,), **f32), torch.empty((n,), **i32)
+    comp = torch.empty((n,), **f32) if antialiased else None
     with _Guard(means3d) as st:
         _lib.check(_lib.load().gsr_fused_preprocess_forward(
             n, sh_degree, int(degrees_to_use), _ptr(means3d), _ptr(scales_raw), _ptr(quats_raw), _ptr(opacities_raw),
             _ptr(features_dc), _ptr(features_rest), _ptr(viewmat), _ptr(projmat), float(glob_scale), float(fx), float(fy),
             float(cx), float(cy), int(img_height), int(img_width), int(block_width), float(clip_thresh), _ptr(rec),
-            _ptr(xys), _ptr(depths), _ptr(radii), _ptr(conics), _ptr(opac), _ptr(mask), st), "fused_preprocess_forward")
-    return rec, xys, depths, radii, conics, opac, mask
+            _ptr(xys), _ptr(depths), _ptr(radii), _ptr(conics), _ptr(opac), _ptr(mask),
+            _ptr(comp) if comp is not None else None, st), "fused_preprocess_forward")
+    return rec, xys, depths, radii, conics, opac, mask, comp
 
 
 def fused_preprocess_backward(means3d, scales_raw, quats_raw, opacities_raw, k_rest: int, degrees_to_use: int, viewmat,
                               projmat, glob_scale, fx, fy, img_height, img_width, radii, conics, clamp_mask, grad_rec,
-                              v_xys_extra=None, out=None):
+                              v_xys_extra=None, out=None, compensation=None):
     """-> (v_means3d, v_scales_raw, v_quats_raw, v_opacities_raw [N,1], v_features_dc [N,3], v_features_rest [N,k_rest,3]).
     `out`: optional dict of preallocated outputs with those names (e.g. views of a GradientBucket)."""
     _check_input(grad_rec, "grad_rec", torch.float32)
@@ -499,8 +503,8 @@ def fused_preprocess_backward(means3d, scales_raw, quats_raw, opacities_raw, k_r
         _lib.check(_lib.load().gsr_fused_preprocess_backward(
             n, sh_degree, int(degrees_to_use), _ptr(means3d), _ptr(scales_raw), _ptr(quats_raw), _ptr(opacities_raw),
             _ptr(viewmat), _ptr(projmat), float(glob_scale), float(fx), float(fy), int(img_height), int(img_width),
-            _ptr(radii), _ptr(conics), _ptr(clamp_mask), _ptr(grad_rec),
-            _ptr(v_xys_extra) if v_xys_extra is not None else None, _ptr(v_means), _ptr(v_scales), _ptr(v_quats),
+            _ptr(radii), _ptr(conics), _ptr(clamp_mask), _ptr(compensation) if compensation is not None else None,
+            _ptr(grad_rec), _ptr(v_xys_extra) if v_xys_extra is not None else None, _ptr(v_means), _ptr(v_scales), _ptr(v_quats),
             _ptr(v_opac), _ptr(v_dc), _ptr(v_rest), st), "fused_preprocess_backward")
     return v_means, v_scales, v_quats, v_opac, v_dc, v_rest
 

@@ -80,20 +80,14 @@ class DensifyStats:
                 "densify_stats_update")
 
     def all_reduce(self, group=None) -> None:
-        """View-parallel training: make the statistics identical on every rank (sum, sum, max) so that
-        all replicas take the same split / cull decisions.  vis_counts starts at 1 on every rank: the surplus
-        (world - 1) is removed."""
-        import torch.distributed as dist
+        """View-parallel training: make the statistics identical on every rank — sum, sum, max
+        (view_parallel.all_reduce_densification_stats) — so that all replicas take the same split / cull decisions.
+        Call it right before `refinement_after`; the ratio xys_grad_norm / vis_counts is then the mean gradient norm
+        over all ranks' views."""
+        from .view_parallel import all_reduce_densification_stats
 
-        if self.xys_grad_norm is None or not (dist.is_available() and dist.is_initialized()):
-            return
-        world = dist.get_world_size(group)
-        if world == 1:
-            return
-        dist.all_reduce(self.xys_grad_norm, group=group)
-        dist.all_reduce(self.vis_counts, group=group)
-        self.vis_counts -= float(world - 1)
-        dist.all_reduce(self.max_2Dsize, op=dist.ReduceOp.MAX, group=group)
+        if self.xys_grad_norm is not None:
+            all_reduce_densification_stats(self.xys_grad_norm, self.vis_counts, self.max_2Dsize, group)
 
 
 def plan(params: Dict[str, Tensor], stats: DensifyStats, config: DensifyConfig, step: int, do_densify: bool,

@@ -8,8 +8,8 @@ separate torch ops and 5 operator calls per view (gs_toolkit/models/vanilla_gs.p
     sigmoid(opacities), project_gaussians, rasterize_gaussians (colour + alpha), rasterize_gaussians (depth)
 
 Not part of the reference package's surface: a model has to opt in.  The numerics per pixel /
-per Gaussian are those of the separate operators (same device functions); `rasterize_mode="antialiased"` is not
-covered by the fused path.
+per Gaussian are those of the separate operators (same device functions); both `rasterize_mode`s of the model are
+covered ("antialiased": opacity x EWA compensation, vanilla_gs.py:813-816).
 """
 from __future__ import annotations
 
@@ -38,7 +38,7 @@ def render_gaussians(means3d: Tensor, scales: Tensor, quats: Tensor, features_dc
                      opacities: Tensor, viewmat: Tensor, projmat: Tensor, fx: float, fy: float, cx: float, cy: float,
                      img_height: int, img_width: int, degrees_to_use: int, background: Optional[Tensor] = None,
                      block_width: int = 16, render_depth: bool = True, glob_scale: float = 1.0,
-                     clip_thresh: float = 0.01, aux: Optional[RenderAux] = None
+                     clip_thresh: float = 0.01, aux: Optional[RenderAux] = None, rasterize_mode: str = "classic"
                      ) -> Tuple[Tensor, Optional[Tensor], Tensor]:
     """Render one view from RAW parameters: `scales` are log-scales, `quats` unnormalised (w,x,y,z), `opacities`
     logits [N,1], `features_dc` [N,3], `features_rest` [N,K-1,3].
@@ -48,6 +48,8 @@ def render_gaussians(means3d: Tensor, scales: Tensor, quats: Tensor, features_dc
     calls of the reference model return before its own epilogue (vanilla_gs.py:835-855).
     Differentiable w.r.t. means3d, scales, quats, features_dc, features_rest, opacities."""
     assert block_width > 1 and block_width <= 16, "block_width must be between 2 and 16"
+    if rasterize_mode not in ("classic", "antialiased"):
+        raise ValueError("Unknown rasterize_mode: %s" % rasterize_mode)   # vanilla_gs.py:817-818
     if background is None:
         background = torch.ones(3, dtype=torch.float32, device=means3d.device)
     assert background.shape[0] == 3, "incorrect shape of background color tensor, expected shape 3"
@@ -55,7 +57,7 @@ def render_gaussians(means3d: Tensor, scales: Tensor, quats: Tensor, features_dc
         means3d.contiguous(), scales.contiguous(), quats.contiguous(), features_dc.contiguous(),
         features_rest.contiguous(), opacities.contiguous(), viewmat.contiguous(), projmat.contiguous(), fx, fy, cx, cy,
         img_height, img_width, degrees_to_use, background.contiguous(), block_width, render_depth, glob_scale,
-        clip_thresh, aux)
+        clip_thresh, aux, rasterize_mode == "antialiased")
     return rgb, (depth[..., None] if render_depth else None), alpha[..., None]
 
 
@@ -63,14 +65,14 @@ class _RenderGaussians(Function):
     @staticmethod
     def forward(ctx, means3d, scales, quats, features_dc, features_rest, opacities, viewmat, projmat, fx, fy, cx, cy,
                 img_height, img_width, degrees_to_use, background, block_width, render_depth, glob_scale, clip_thresh,
-                aux):
+                aux, antialiased=False):
         n = means3d.shape[0]
         if n < 1 or means3d.shape[-1] != 3:
             raise ValueError(f"Invalid shape for means3d: {means3d.shape}")
         opac_raw = opacities.reshape(-1)
-        rec, xys, depths, radii, conics, opac, mask = _C.fused_preprocess_forward(
+        rec, xys, depths, radii, conics, opac, mask, comp = _C.fused_preprocess_forward(
             means3d, scales, quats, opac_raw, features_dc.reshape(n, 3), features_rest, viewmat, projmat, glob_scale, fx, fy,
-            cx, cy, img_height, img_width, block_width, degrees_to_use, clip_thresh)
+            cx, cy, img_height, img_width, block_width, degrees_to_use, clip_thresh, antialiased)
         m, ids_sorted, tile_bins = _C.bin_gaussians_fast(xys, depths, radii, conics, opac, img_height, img_width,
                                                          block_width)
         dev = means3d.device
@@ -93,7 +95,8 @@ class _RenderGaussians(Function):
             ctx.save_for_backward(means3d, scales, quats, opacities, viewmat, projmat)
         else:
             ctx.save_for_backward(means3d, scales, quats, opacities, viewmat, projmat, rec, radii, conics, mask,
-                                  ids_sorted, tile_bins, background, final_Ts, final_idx)
+                                  ids_sorted, tile_bins, background, final_Ts, final_idx,
+                                  comp if comp is not None else torch.empty(0, device=dev))
         return rgb, depth, 1 - final_Ts
 
     @staticmethod
@@ -109,7 +112,7 @@ class _RenderGaussians(Function):
             if ctx.aux is not None:
                 ctx.aux.xys_grad = torch.zeros(n, 2, device=means3d.device)
         else:
-            rec, radii, conics, mask, ids_sorted, tile_bins, background, final_Ts, final_idx = saved[6:]
+            rec, radii, conics, mask, ids_sorted, tile_bins, background, final_Ts, final_idx, comp = saved[6:]
             v_rgb = v_rgb.contiguous()
             v_alpha = torch.zeros(H, W, device=v_rgb.device) if v_alpha is None else v_alpha.contiguous()
             v_d = v_depth.contiguous() if (render_depth and v_depth is not None) else None
@@ -119,7 +122,7 @@ class _RenderGaussians(Function):
                 ctx.aux.xys_grad = grad_rec[:, 0:2]
             v_means, v_scales, v_quats, v_opac, v_dc, v_rest = _C.fused_preprocess_backward(
                 means3d, scales, quats, opacities.reshape(-1), k_rest, degrees_to_use, viewmat, projmat, glob_scale, fx, fy,
-                H, W, radii, conics, mask, grad_rec)
+                H, W, radii, conics, mask, grad_rec, compensation=comp if comp.numel() else None)
             grads = (v_means, v_scales, v_quats, v_dc, v_rest, v_opac.view_as(opacities))
         v_means, v_scales, v_quats, v_dc, v_rest, v_opac = grads
-        return (v_means, v_scales, v_quats, v_dc.reshape(dc_shape), v_rest, v_opac) + (None,) * 15
+        return (v_means, v_scales, v_quats, v_dc.reshape(dc_shape), v_rest, v_opac) + (None,) * 16

@@ -247,6 +247,9 @@ GSR_API int gsr_nd_rasterize_backward(unsigned img_height, unsigned img_width, u
  *   {v_x, v_y, v_opacity, v_depth | v_a, v_b, v_c, - | v_r, v_g, v_b, -} (zero-filled by the call).
  * gsr_fused_preprocess_backward: grad_records (+ optional v_xys_extra [N,2]) -> gradients of the six raw parameter
  *   tensors (chain rules of exp / normalise / sigmoid / clamp included).
+ * compensation [N] (nullable): non-NULL selects rasterize_mode = "antialiased" (vanilla_gs.py:813-816): the forward
+ *   stores the EWA compensation factor there and uses opacity = sigmoid(raw) * compensation; the backward (same
+ *   array) routes d/d compensation through the projection adjoint.  NULL = "classic".
  * ---------------------------------------------------------------------------------------------- */
 GSR_API int gsr_fused_preprocess_forward(int num_points, int sh_degree, int degrees_to_use, const float *means3d,
                                          const float *scales_raw, const float *quats_raw, const float *opacities_raw,
@@ -254,12 +257,14 @@ GSR_API int gsr_fused_preprocess_forward(int num_points, int sh_degree, int degr
                                          const float *projmat, float glob_scale, float fx, float fy, float cx, float cy,
                                          unsigned img_height, unsigned img_width, unsigned block_width,
                                          float clip_thresh, float *records, float *xys, float *depths, int32_t *radii,
-                                         float *conics, float *opacities, int32_t *clamp_mask, void *stream);
+                                         float *conics, float *opacities, int32_t *clamp_mask,
+                                         float *compensation /*nullable*/, void *stream);
 GSR_API int gsr_fused_preprocess_backward(int num_points, int sh_degree, int degrees_to_use, const float *means3d,
                                           const float *scales_raw, const float *quats_raw, const float *opacities_raw,
                                           const float *viewmat, const float *projmat, float glob_scale, float fx,
                                           float fy, unsigned img_height, unsigned img_width, const int32_t *radii,
-                                          const float *conics, const int32_t *clamp_mask, const float *grad_records,
+                                          const float *conics, const int32_t *clamp_mask,
+                                          const float *compensation /*nullable*/, const float *grad_records,
                                           const float *v_xys_extra /*nullable*/, float *v_means3d, float *v_scales_raw,
                                           float *v_quats_raw, float *v_opacities_raw, float *v_features_dc,
                                           float *v_features_rest, void *stream);

@@ -64,9 +64,11 @@ def test_fused_render_vs_oracle(oracle, name):
         assert_float_parity(to_np(v).reshape(ref[k].shape), ref[k], k, max_norm_rel=3e-4, max_frac_bad=3e-3)
 
 
-def test_fused_render_equals_separate_operators():
+@pytest.mark.parametrize("mode", ["classic", "antialiased"])
+def test_fused_render_equals_separate_operators(mode):
     """Same image / depth / alpha and the same raw-parameter gradients as the three operators + torch glue the way
-    gs_toolkit/models/vanilla_gs.py:759-855 chains them."""
+    gs_toolkit/models/vanilla_gs.py:759-855 chains them, in both rasterize modes (antialiased: opacities multiplied by
+    the EWA compensation factor, :813-816, whose gradient flows back through project_gaussians)."""
     import rasterizer
     from oracle import oracle as orc
     from rasterizer.fused import render_gaussians
@@ -90,7 +92,7 @@ def test_fused_render_equals_separate_operators():
         means, scales, 1.0, quats, s["viewmat"], s["projmat"], s["fx"], s["fy"], s["cx"], s["cy"], H, W, bw)
     viewdirs = means.detach() - s["cam_pos"][None]
     rgbs = torch.clamp(spherical_harmonics(3, viewdirs, colors_all) + 0.5, min=0.0)
-    opac = torch.sigmoid(op)
+    opac = torch.sigmoid(op) * comp[:, None] if mode == "antialiased" else torch.sigmoid(op)
     rgb_a, alpha_a = rasterizer.rasterize_gaussians(xys, depths, radii, conics, nth, rgbs, opac, H, W, bw,
                                                     background=s["background"], return_alpha=True)
     depth_a = rasterizer.rasterize_gaussians(xys, depths, radii, conics, nth, depths[:, None].repeat(1, 3), opac, H, W, bw,
@@ -99,7 +101,7 @@ def test_fused_render_equals_separate_operators():
     b_leaves = leaves()
     rgb_b, depth_b, alpha_b = render_gaussians(b_leaves[0], b_leaves[1], b_leaves[2], b_leaves[3], b_leaves[4], b_leaves[5],
                                                s["viewmat"], s["projmat"], s["fx"], s["fy"], s["cx"], s["cy"], H, W, 3,
-                                               background=s["background"])
+                                               background=s["background"], rasterize_mode=mode)
     assert_float_parity(rgb_b, rgb_a, "rgb", max_frac_bad=2e-5)
     assert_float_parity(depth_b, depth_a, "depth", max_frac_bad=2e-5)
     assert_float_parity(alpha_b[..., 0], alpha_a, "alpha", max_frac_bad=2e-5, atol=1e-6)
@@ -127,6 +129,8 @@ def test_fused_render_empty_and_no_depth():
     assert depth is None and rgb.shape == (32, 48, 3)
     rgb2, depth2, alpha2 = render_gaussians(s["means3d"], *args, background=s["background"], render_depth=True)
     assert torch.equal(rgb, rgb2) and torch.equal(alpha, alpha2)
+    with pytest.raises(ValueError, match="Unknown rasterize_mode"):
+        render_gaussians(s["means3d"], *args, rasterize_mode="fancy")
     behind = s["means3d"].clone()
     behind[:, 2] *= -1
     behind.requires_grad_(True)

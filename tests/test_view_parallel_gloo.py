@@ -50,6 +50,14 @@ def _worker(rank, world, port, results):
     a, b, c = torch.full((N,), float(rank)), torch.ones(N), torch.full((N,), float(10 * rank))
     all_reduce_densification_stats(a, b, c)
     ok = ok and float(a[0]) == 1.0 and float(b[0]) == 2.0 and float(c[0]) == 10.0
+    # the same through the densification-statistics holder of rasterizer.densify (f2)
+    from rasterizer.densify import DensifyStats
+
+    st = DensifyStats()
+    st.all_reduce()   # unset statistics: no-op
+    st.xys_grad_norm, st.vis_counts, st.max_2Dsize = torch.full((N,), 0.5 + rank), torch.full((N,), 2.0), torch.full((N,), 0.1 * rank)
+    st.all_reduce()
+    ok = ok and float(st.xys_grad_norm[3]) == 2.0 and float(st.vis_counts[3]) == 4.0 and abs(float(st.max_2Dsize[3]) - 0.1) < 1e-7
     views = [view_for_rank(step, rank, world, 7) for step in range(7)]
     gathered = [None] * world
     dist.all_gather_object(gathered, views)
