@@ -159,6 +159,7 @@ struct GatherSegment {
   int kind;           // gsr_densify_kind
   int rows_per_cta;
   unsigned magic;     // ceil(2^32 / width)
+  int vec_ok;         // dst 16-byte aligned => 128-bit stores
 };
 struct GatherLaunch {
   GatherSegment seg[GSR_DENSIFY_MAX_TENSORS];
@@ -177,39 +178,55 @@ constexpr int GATHER_MAX_ROWS = 4096;   // rows per CTA (width-1 tensors); wider
 // coalesced read, then the elements are streamed with destination-contiguous (fully coalesced) writes; the loop is
 // specialised per tensor kind and unrolled so that several independent gathers are in flight per thread.
 template <int KIND>
+__device__ __forceinline__ float gather_value(const GatherLaunch &L, const GatherSegment &S, const unsigned *s_map,
+                                              long long row0, int lr, int c) {
+  const int w = S.width;
+  const unsigned code = s_map[lr];
+  const unsigned from = code & ((1u << MAP_KIND_SHIFT) - 1u), kind = code >> MAP_KIND_SHIFT;
+  if (KIND == GSR_DENSIFY_ZERO_NEW) return (kind == MAP_ORIG) ? __ldg(S.src + (size_t)from * w + c) : 0.f;
+  float val = __ldg(S.src + (size_t)from * w + c);
+  if (KIND == GSR_DENSIFY_SCALES) {
+    if (L.flags[from] & DF_SPLIT) val = logf(expf(val) / 1.6f);  // :563-569 (children, and the duplicate of a split)
+  } else if (KIND == GSR_DENSIFY_MEANS) {
+    if (kind == MAP_SPLIT) {
+      // new_means = R(q/|q|) (exp(scales) * z) + mean  (:543-553); z = samples[s * n_split + split rank]
+      const int s = (int)((row0 + lr - L.n_keep_orig) / L.n_keep_split);
+      const float *z = L.samples + ((size_t)s * L.n_split + L.ranks[from].x) * 3;
+      const float *sc = L.scales_raw + (size_t)from * 3, *q = L.quats_raw + (size_t)from * 4;
+      float R[9];
+      quat_to_rotmat(q[0], q[1], q[2], q[3], R);
+      const float v0 = expf(sc[0]) * z[0], v1 = expf(sc[1]) * z[1], v2 = expf(sc[2]) * z[2];
+      val = (R[3 * c] * v0 + R[3 * c + 1] * v1 + R[3 * c + 2] * v2) + val;
+    }
+  }
+  return val;
+}
+
+// The CTA's destination range is contiguous (rows_per_cta rows of width w starting at a 16-byte boundary when the
+// tensor is 16-byte aligned: rows_per_cta is a multiple of 4): every thread gathers 4 consecutive destination
+// elements (possibly from two source rows) and writes them with one 128-bit store.
+template <int KIND>
 __device__ __forceinline__ void gather_rows(const GatherLaunch &L, const GatherSegment &S, const unsigned *s_map,
                                             long long row0, int total) {
   const int w = S.width;
   const unsigned magic = S.magic;   // ceil(2^32 / w): j / w == umulhi(j, magic) for j < 2^17, w <= 4096
-  const float *__restrict__ src = S.src;
   float *__restrict__ dst = S.dst + row0 * w;
-#pragma unroll 4
-  for (int j = threadIdx.x; j < total; j += blockDim.x) {
-    const int lr = (w == 1) ? j : (int)__umulhi((unsigned)j, magic), c = j - lr * w;
-    const unsigned code = s_map[lr];
-    const unsigned from = code & ((1u << MAP_KIND_SHIFT) - 1u), kind = code >> MAP_KIND_SHIFT;
-    float val;
-    if (KIND == GSR_DENSIFY_ZERO_NEW) {
-      val = (kind == MAP_ORIG) ? __ldg(src + (size_t)from * w + c) : 0.f;
-    } else if (KIND == GSR_DENSIFY_SCALES) {
-      val = __ldg(src + (size_t)from * w + c);
-      if (L.flags[from] & DF_SPLIT) val = logf(expf(val) / 1.6f);  // :563-569 (children, and the duplicate of a split)
-    } else if (KIND == GSR_DENSIFY_MEANS) {
-      val = __ldg(src + (size_t)from * w + c);
-      if (kind == MAP_SPLIT) {
-        // new_means = R(q/|q|) (exp(scales) * z) + mean  (:543-553); z = samples[s * n_split + split rank]
-        const int s = (int)((row0 + lr - L.n_keep_orig) / L.n_keep_split);
-        const float *z = L.samples + ((size_t)s * L.n_split + L.ranks[from].x) * 3;
-        const float *sc = L.scales_raw + (size_t)from * 3, *q = L.quats_raw + (size_t)from * 4;
-        float R[9];
-        quat_to_rotmat(q[0], q[1], q[2], q[3], R);
-        const float v0 = expf(sc[0]) * z[0], v1 = expf(sc[1]) * z[1], v2 = expf(sc[2]) * z[2];
-        val = (R[3 * c] * v0 + R[3 * c + 1] * v1 + R[3 * c + 2] * v2) + val;
-      }
-    } else {
-      val = __ldg(src + (size_t)from * w + c);
+  const int nvec = S.vec_ok ? (total >> 2) : 0;
+#pragma unroll 2
+  for (int q = threadIdx.x; q < nvec; q += blockDim.x) {
+    const int j = q << 2;
+    int lr = (w == 1) ? j : (int)__umulhi((unsigned)j, magic), c = j - lr * w;
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      v[e] = gather_value<KIND>(L, S, s_map, row0, lr, c);
+      if (++c == w) { c = 0; ++lr; }
     }
-    dst[j] = val;
+    reinterpret_cast<float4 *>(dst)[q] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+  for (int j = (nvec << 2) + threadIdx.x; j < total; j += blockDim.x) {
+    const int lr = (w == 1) ? j : (int)__umulhi((unsigned)j, magic), c = j - lr * w;
+    dst[j] = gather_value<KIND>(L, S, s_map, row0, lr, c);
   }
 }
 
@@ -358,8 +375,9 @@ GSR_API int gsr_densify_apply(int num_points, int n_split_samples, const int32_t
     S.dst = dst_host[k];
     S.width = widths_host[k];
     S.kind = kinds_host[k];
-    const int rpc = GATHER_MAX_ROWS / S.width;
+    const int rpc = (GATHER_MAX_ROWS / S.width) & ~3;   // multiple of 4 rows => 16-byte aligned CTA ranges
     S.rows_per_cta = rpc < 32 ? 32 : rpc;
+    S.vec_ok = ((uintptr_t)S.dst & 15u) == 0;
     S.magic = S.width == 1 ? 0u : (unsigned)((0x100000000ull + (unsigned)S.width - 1) / (unsigned)S.width);
     const unsigned gx = (unsigned)((new_n + S.rows_per_cta - 1) / S.rows_per_cta);
     grid_x = gx > grid_x ? gx : grid_x;

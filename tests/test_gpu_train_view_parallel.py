@@ -122,6 +122,11 @@ def test_view_parallel_training_with_densification_2gpu():
     # split decisions are not comparable one to one): same parameters up to the order of the FP32 gradient sums
     _, cr, ref = _train(0, 1, 2, 11)
     print("[view-parallel f2] Gaussian counts after refinements (2 ranks):", c0)
+    # (Adam turns the sign of a rounding-noise gradient into a full +-lr step, so a few elements legitimately differ:
+    # the bound is on the fraction of such elements and on the norm)
     for k in GROUPS:
-        err = float(np.linalg.norm(s0[k] - ref[k].numpy()) / np.linalg.norm(ref[k].numpy()))
-        assert err < 1e-4, (k, err)
+        a, b = s0[k], ref[k].numpy()
+        err = float(np.linalg.norm(a - b) / np.linalg.norm(b))
+        frac = float((np.abs(a - b) > 1e-3 * np.abs(b) + 1e-4).mean())
+        print(f"[view-parallel f2] {k}: normwise {err:.2e}, fraction of differing elements {frac:.2e}")
+        assert err < 1e-4 and frac < 1e-3, (k, err, frac)   # observed: <= 2e-6, <= 5e-5
