@@ -220,6 +220,11 @@ class ResidentView:
         return {k: v / n for k, v in out.items()}
 
 
+# diagnostic only (never a reported number): skip the large host copies of the e2e leg to separate PCIe time from
+# exchange time when looking at multi-GPU runs; the JSON line is tagged "diagnostic"
+DIAG_NOCOPY = os.environ.get("GSR_E2E_NOCOPY") == "1"
+
+
 class PublicApiView:
     """One view through the public autograd API with HOST buffers for the per-view inputs/outputs (`e2e`).
 
@@ -228,10 +233,10 @@ class PublicApiView:
     streams so that PCIe traffic overlaps the kernels (H2D of the upstream gradients under the forward pass, D2H of
     the image under the backward pass); device-side input buffers are double-buffered across steps."""
 
-    def __init__(self, s, scene_np, bucket=None):
+    def __init__(self, s, scene_np, bucket=None, peer=None):
         import torch
 
-        self.torch, self.s, self.bucket = torch, s, bucket
+        self.torch, self.s, self.bucket, self.peer = torch, s, bucket, peer
         dev = s["means3d"].device
         self.means = s["means3d"].clone().requires_grad_(True)
         self.scales = s["scales"].clone().requires_grad_(True)
@@ -269,8 +274,9 @@ class PublicApiView:
         self.d_projmat.copy_(self.h_projmat, non_blocking=True)
         self.h2d_stream.wait_event(self.buf_free[i])
         with torch.cuda.stream(self.h2d_stream):
-            self.d_vimg[i].copy_(self.h_vimg, non_blocking=True)
-            self.d_valpha[i].copy_(self.h_valpha, non_blocking=True)
+            if not DIAG_NOCOPY:
+                self.d_vimg[i].copy_(self.h_vimg, non_blocking=True)
+                self.d_valpha[i].copy_(self.h_valpha, non_blocking=True)
             in_ready = torch.cuda.Event()
             in_ready.record()
         for p in (self.means, self.scales, self.quats, self.coeffs, self.opac):
@@ -284,7 +290,7 @@ class PublicApiView:
         else:  # view-parallel: coeffs.grad comes out already summed over the ranks
             from rasterizer.view_parallel import spherical_harmonics_view_parallel
 
-            sh = spherical_harmonics_view_parallel(s["degrees_to_use"], self.means, s["cam_pos"], self.coeffs)
+            sh = spherical_harmonics_view_parallel(s["degrees_to_use"], self.means, s["cam_pos"], self.coeffs, peer=self.peer)
         rgbs = torch.clamp(sh + 0.5, min=0.0)
         img, alpha = rasterizer.rasterize_gaussians(xys, depths, radii, conics, nth, rgbs, self.opac, H, W, bw,
                                                     background=s["background"], return_alpha=True)
@@ -294,8 +300,9 @@ class PublicApiView:
         self.d2h_stream.wait_event(fwd_done)
         with torch.cuda.stream(self.d2h_stream):
             img_d, alpha_d = img.detach(), alpha.detach()
-            self.h_img.copy_(img_d, non_blocking=True)
-            self.h_alpha.copy_(alpha_d, non_blocking=True)
+            if not DIAG_NOCOPY:
+                self.h_img.copy_(img_d, non_blocking=True)
+                self.h_alpha.copy_(alpha_d, non_blocking=True)
             img_d.record_stream(self.d2h_stream)
             alpha_d.record_stream(self.d2h_stream)
         main.wait_event(in_ready)
@@ -447,6 +454,12 @@ def main():
     import torch.distributed as dist
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    numa_cpus = None
+    if world > 1 and os.environ.get("GSR_NUMA_BIND", "1") != "0":
+        # before any pinned allocation: keep this rank's host buffers and PCIe traffic on its GPU's socket
+        from rasterizer.view_parallel import bind_process_to_gpu_numa
+
+        numa_cpus = bind_process_to_gpu_numa(local_rank)
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -510,7 +523,7 @@ def main():
         M_ref = int(_nth.sum().item())
 
     # e2e through the public API with host buffers
-    pv = PublicApiView(s, scene_np, bucket)
+    pv = PublicApiView(s, scene_np, bucket, peer)
 
     def e2e_step():
         pv.step()
@@ -555,6 +568,12 @@ def main():
                                  "resident leg only",
             "clocks": clocks, "roofline": roofline,
         }
+        if world > 1:
+            line["config"]["host_numa_binding"] = (f"rank pinned to the {len(numa_cpus)} CPUs local to its GPU (NVML)"
+                                                   if numa_cpus else "none")
+            line["config"]["sh_gradient_exchange"] = "NVLink peer loads (symmetric memory)" if peer is not None else "NCCL all-gather"
+        if DIAG_NOCOPY:
+            line["diagnostic"] = "GSR_E2E_NOCOPY=1: e2e WITHOUT its host copies - not a reportable number"
         if world == 1:
             line["fused_operator"] = fused_leg(torch, s, scene_np, args.steps, args.warmup)
         if world == 1 and not args.no_cpu_baseline:

@@ -161,11 +161,12 @@ class _SphericalHarmonicsViewParallel(torch.autograd.Function):
     `group` (all-gather of the 3-float colour gradients + multi-view adjoint kernel), see exchange_gradients."""
 
     @staticmethod
-    def forward(ctx, degrees_to_use, means3d, cam_pos, coeffs, group, average):
+    def forward(ctx, degrees_to_use, means3d, cam_pos, coeffs, group, average, peer=None):
         from . import cuda as _C
         from .sh import deg_from_sh
 
         ctx.degrees_to_use, ctx.degree, ctx.group, ctx.average = degrees_to_use, deg_from_sh(coeffs.shape[-2]), group, average
+        ctx.peer = peer
         viewdirs = (means3d - cam_pos.reshape(1, 3)).contiguous()
         ctx.save_for_backward(means3d, cam_pos)
         return _C.compute_sh_forward(coeffs.shape[0], ctx.degree, degrees_to_use, viewdirs, coeffs)
@@ -177,6 +178,17 @@ class _SphericalHarmonicsViewParallel(torch.autograd.Function):
         means3d, cam_pos = ctx.saved_tensors
         v_colors = v_colors.contiguous()
         world = dist.get_world_size(ctx.group) if (dist.is_available() and dist.is_initialized()) else 1
+        peer = ctx.peer
+        if world > 1 and peer is not None:
+            # NVLink peer-memory path (PeerColorGrads): publish, barrier, the kernel loads the peers' colour gradients
+            peer.local_rgb.copy_(v_colors)
+            peer.local_cam.copy_(cam_pos.reshape(3))
+            peer.hdl.barrier(channel=0)
+            v_coeffs = _C.compute_sh_backward_multiview(ctx.degree, ctx.degrees_to_use, means3d, peer.peer_cam, peer.peer_rgb)
+            peer.hdl.barrier(channel=1)
+            if ctx.average:
+                v_coeffs.div_(world)
+            return None, None, None, v_coeffs, None, None, None
         if world == 1:
             v_all, cams = [v_colors], cam_pos.reshape(1, 3).contiguous()
         else:
@@ -187,16 +199,18 @@ class _SphericalHarmonicsViewParallel(torch.autograd.Function):
         v_coeffs = _C.compute_sh_backward_multiview(ctx.degree, ctx.degrees_to_use, means3d, cams, v_all)
         if ctx.average and world > 1:
             v_coeffs.div_(world)
-        return None, None, None, v_coeffs, None, None
+        return None, None, None, v_coeffs, None, None, None
 
 
 def spherical_harmonics_view_parallel(degrees_to_use: int, means3d: torch.Tensor, cam_pos: torch.Tensor,
-                                      coeffs: torch.Tensor, group=None, average: bool = False) -> torch.Tensor:
+                                      coeffs: torch.Tensor, group=None, average: bool = False,
+                                      peer: "PeerColorGrads" = None) -> torch.Tensor:
     """Drop-in for `spherical_harmonics(degrees_to_use, means3d - cam_pos, coeffs)` in a view-parallel job:
     same colours; `coeffs.grad` comes out already reduced over `group`, so the SH coefficients must be left out
-    of the gradient all-reduce (only 11 of the 59 floats per Gaussian remain to be reduced)."""
+    of the gradient all-reduce (only 11 of the 59 floats per Gaussian remain to be reduced).  With `peer` (a
+    PeerColorGrads mailbox) the backward loads the peers' colour gradients over NVLink instead of all-gathering them."""
     return _SphericalHarmonicsViewParallel.apply(degrees_to_use, means3d.detach().contiguous(), cam_pos.contiguous(),
-                                                 coeffs.contiguous(), group, average)
+                                                 coeffs.contiguous(), group, average, peer)
 
 
 class GradientExchange:
@@ -247,6 +261,30 @@ class GradientExchange:
         self.peer.hdl.barrier(channel=1)
         if average:
             bucket.flat.div_(dist.get_world_size(self.group))
+
+
+def bind_process_to_gpu_numa(device_index: int) -> Optional[list]:
+    """Pin the calling process to the CPUs NVML reports as local to GPU `device_index` (its NUMA node), so that the
+    pinned host buffers it allocates afterwards (first touch) and its H2D / D2H traffic stay on the GPU's own socket —
+    with 8 ranks streaming images over PCIe, cross-socket traffic is the first thing to saturate.  Returns the CPU
+    list, or None when NVML / the affinity call is unavailable (nothing is changed then)."""
+    try:
+        import os
+
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [64 * i + b for i, w in enumerate(mask) for b in range(64) if (int(w) >> b) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:  # pragma: no cover - depends on the platform
+        return None
 
 
 def view_for_rank(step: int, rank: int, world_size: int, num_views: int) -> int:

@@ -438,6 +438,11 @@ def _exchange_worker(rank, world, port, results):
     dist.all_reduce(summed)
     torch.cuda.synchronize()
     err_ag = float((c1.grad - summed).norm() / summed.norm()) + float((col1 - col2).abs().max())
+    if peer is not None:   # the same autograd form with the peers' colour gradients loaded over NVLink
+        c3 = coeffs.clone().requires_grad_(True)
+        spherical_harmonics_view_parallel(3, means, cam, c3, peer=peer).backward(v_rgb)
+        torch.cuda.synchronize()
+        err_ag += float((c3.grad - summed).norm() / summed.norm())
     results[rank] = (err, err_p2p, err_ag)
     dist.destroy_process_group()
 
