@@ -96,5 +96,28 @@ def main():
     print("train files", out["train_files"], "val files", out["val_files"])
 
 
+def gen_scheduler():
+    """io_scheduler_ref.npz: learning rates of the reference's ExponentialDecayScheduler (engine/schedulers.py:94-135)
+    driving a real torch.optim.Adam through LambdaLR, for the `means` configuration of configs/method_configs.py:98-105 and
+    for a warm-up variant."""
+    from gs_toolkit.engine.schedulers import ExponentialDecaySchedulerConfig
+
+    out = {}
+    for tag, lr_init, kw in (("means", 1.6e-4, dict(lr_final=1.6e-6, max_steps=30000)),
+                             ("warm_cos", 1e-3, dict(lr_final=1e-4, max_steps=500, warmup_steps=100)),
+                             ("warm_lin", 1e-3, dict(lr_final=None, max_steps=400, warmup_steps=50, ramp="linear"))):
+        p = torch.nn.Parameter(torch.zeros(1))
+        opt = torch.optim.Adam([p], lr=lr_init, eps=1e-15)
+        sched = ExponentialDecaySchedulerConfig(**kw).setup().get_scheduler(optimizer=opt, lr_init=lr_init)
+        lrs = []
+        for _ in range(600):
+            opt.step()
+            sched.step()
+            lrs.append(sched.get_last_lr()[0])
+        out[tag] = np.array(lrs, dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, "io_scheduler_ref.npz"), **out)
+
+
 if __name__ == "__main__":
     main()
+    gen_scheduler()

@@ -132,3 +132,17 @@ def test_checkpoint_round_trip_and_reference_loads_it(tmp_path):
         adam.load_state_dict(raw["optimizers"][k])      # engine/optimizers.py:197-204
         assert torch.equal(adam.state[model.gauss_params[k]]["exp_avg_sq"], opt.sd[k]["state"][0]["exp_avg_sq"])
         assert adam.param_groups[0]["lr"] == 1e-3
+
+
+def test_exponential_decay_lr_vs_reference_scheduler():
+    """rasterizer.optim.exponential_decay_lr against the learning rates the reference's ExponentialDecayScheduler +
+    LambdaLR produced (tests/golden/io_scheduler_ref.npz, gen_golden_io.py): after the k-th scheduler step lr = f(k)."""
+    from rasterizer.optim import default_means_scheduler, exponential_decay_lr
+
+    z = np.load(os.path.join(GOLD, "io_scheduler_ref.npz"))
+    fns = {"means": default_means_scheduler(),
+           "warm_cos": exponential_decay_lr(1e-3, 1e-4, 500, warmup_steps=100),
+           "warm_lin": exponential_decay_lr(1e-3, None, 400, warmup_steps=50, ramp="linear")}
+    for tag, fn in fns.items():
+        got = np.array([fn(k) for k in range(1, len(z[tag]) + 1)])
+        np.testing.assert_allclose(got, z[tag], rtol=1e-12, atol=0, err_msg=tag)
