@@ -148,7 +148,9 @@ def apply(params: Dict[str, Tensor], optimizers: Optional[GaussianOptimizers], f
         w = src.numel() // n if n else 1
         dst = torch.empty((new_n,) + tuple(src.shape[1:]), dtype=torch.float32, device=dev)
         new_params[name] = dst
-        srcs.append(src); dsts.append(dst); widths.append(w)
+        srcs.append(src)
+        dsts.append(dst)
+        widths.append(w)
         kinds.append(KIND_MEANS if name == "means" else KIND_SCALES if name == "scales" else KIND_COPY)
         if optimizers is not None and name in optimizers.state:
             m, v = optimizers.moments(name)
@@ -156,7 +158,10 @@ def apply(params: Dict[str, Tensor], optimizers: Optional[GaussianOptimizers], f
                 nm, nv = torch.empty_like(dst), torch.empty_like(dst)
                 new_moments[name] = (nm, nv)
                 for s_, d_ in ((m, nm), (v, nv)):
-                    srcs.append(s_); dsts.append(d_); widths.append(w); kinds.append(KIND_ZERO_NEW)
+                    srcs.append(s_)
+                    dsts.append(d_)
+                    widths.append(w)
+                    kinds.append(KIND_ZERO_NEW)
     k = len(srcs)
     ptr_t, i32_t = C.c_void_p * k, C.c_int32 * k
     src_a, dst_a = ptr_t(*[t.data_ptr() for t in srcs]), ptr_t(*[t.data_ptr() for t in dsts])
@@ -197,13 +202,12 @@ def refinement_after(params: Dict[str, Tensor], optimizers: Optional[GaussianOpt
                         and step % reset_interval > num_train_data + config.refine_every)
     cull_only = (not do_densification) and step >= config.stop_split_at and config.continue_cull_post_densification
     if do_densification or cull_only:
-        n = info["n_before"]
         flags, ranks, counts = plan(params, stats, config, step, do_densification, last_size)
         n_split, n_keep_orig, n_keep_split, n_keep_dup = counts
         if do_densification and n_split > 0 and samples is None:
             samples = torch.randn((config.n_split_samples * n_split, 3), device=params["means"].device,
                                   generator=generator)
-        if not (n_keep_orig == n and n_keep_split == 0 and n_keep_dup == 0):
+        if not (n_keep_orig == n0 and n_keep_split == 0 and n_keep_dup == 0):
             info["n_after"] = apply(params, optimizers, flags, ranks, counts, config.n_split_samples, samples)
         info.update(n_split=n_split, n_kept=n_keep_orig, n_new_split=config.n_split_samples * n_keep_split,
                     n_new_dup=n_keep_dup)
