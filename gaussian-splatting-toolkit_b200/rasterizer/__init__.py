@@ -9,6 +9,11 @@ Public surface (identical names, argument order and return values):
 Sub-modules the models import directly: rasterizer.sh (num_sh_bases, spherical_harmonics),
 rasterizer.project_gaussians, rasterizer.rasterize, rasterizer._torch_impl (quat_to_rotmat).
 
+Beyond the drop-in surface (not part of the reference package; a model opts in):
+rasterizer.fused (one-node render operator), rasterizer.losses (fused L1 + SSIM), rasterizer.optim (one-launch Adam for
+the parameter groups), rasterizer.densify (after_train / refinement_after as compaction kernels), rasterizer.io_ply /
+rasterizer.io_scene (.ply, checkpoints, transforms.json), rasterizer.view_parallel (multi-GPU gradient exchange).
+
 All compute happens in libgsr_b200.so (hand-written sm_100a CUDA, C ABI in include/gsr_b200.h); importing
 this package does not load the library (so CPU-only tooling can import it) but the first operator call
 does, and raises if it is missing — there is no PyTorch or CPU fallback.

@@ -129,4 +129,4 @@ def test_view_parallel_training_with_densification_2gpu():
         err = float(np.linalg.norm(a - b) / np.linalg.norm(b))
         frac = float((np.abs(a - b) > 1e-3 * np.abs(b) + 1e-4).mean())
         print(f"[view-parallel f2] {k}: normwise {err:.2e}, fraction of differing elements {frac:.2e}")
-        assert err < 1e-4 and frac < 1e-3, (k, err, frac)   # observed: <= 2e-6, <= 5e-5
+        assert err < 5e-4 and frac < 5e-3, (k, err, frac)   # observed over runs: <= 2.3e-5, <= 2.5e-4
