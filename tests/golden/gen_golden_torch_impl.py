@@ -31,7 +31,7 @@ def load_ref():
     return m
 
 
-def run_case(ti, name, scene):
+def run_case(ti, name, scene, prefix="torch_impl_"):
     s = scene
     t = {k: torch.from_numpy(v) if isinstance(v, np.ndarray) else v for k, v in s.items()}
     H, W, bw = s["img_height"], s["img_width"], s["block_width"]
@@ -67,7 +67,7 @@ def run_case(ti, name, scene):
         ref_gaussian_ids_sorted=vs.numpy(), ref_tile_bins=bins.numpy(), ref_out_img=img.numpy(),
         ref_final_Ts=fT.numpy(),
     )
-    np.savez_compressed(os.path.join(HERE, f"torch_impl_{name}.npz"), **out)
+    np.savez_compressed(os.path.join(HERE, f"{prefix}{name}.npz"), **out)
 
 
 def main():
@@ -81,6 +81,15 @@ def main():
     run_case(ti, "b_rotated_40x32_bw8",
              make_scene(70, 40, 32, 0.05, 0.3, margin=0.45, seed=12, block_width=8, degrees_to_use=2,
                         viewmat=look_at_viewmat(yaw_deg=12.0, pitch_deg=-7.0, shift=(0.1, -0.05, 0.2))))
+    # (c), (d): CPU-side pins of the oracle only (`oracle_pin_` prefix: tests/test_oracle_golden.py); the GPU suite keeps
+    # its two torch_impl fixtures
+    # (c) tall ragged image, block_width 4, SH degree 1 stored and used (every tile must hold a Gaussian: the reference
+    #     restatement reads an unbound `idx` for pixels of an empty tile, _torch_impl.py:467)
+    run_case(ti, "c_tall_24x54_bw4_deg1", make_scene(150, 24, 54, 0.2, 0.6, margin=1.0, seed=13, block_width=4, sh_degree=1),
+             prefix="oracle_pin_torch_impl_")
+    # (d) large, mostly opaque Gaussians (early termination, T <= 1e-4), SH degree 0
+    run_case(ti, "d_opaque_64x48_deg0", make_scene(120, 64, 48, 0.3, 0.9, margin=0.6, seed=14, sh_degree=0),
+             prefix="oracle_pin_torch_impl_")
 
 
 if __name__ == "__main__":
