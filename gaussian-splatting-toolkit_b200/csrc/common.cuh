@@ -14,6 +14,8 @@ namespace gsr {
 
 // thread-local error message (api.cu)
 void set_error(const char *fmt, ...);
+// process-wide count of own kernel launches (api.cu; read with gsr_launch_count())
+void count_launch();
 
 #define GSR_REQUIRE(cond, code, ...)  \
   do {                                \
@@ -39,6 +41,7 @@ void set_error(const char *fmt, ...);
       gsr::set_error("launch of %s failed: %s", name, cudaGetErrorString(_e));          \
       return GSR_ERR_CUDA;                                                              \
     }                                                                                   \
+    gsr::count_launch();                                                                \
   } while (0)
 
 static inline unsigned cdiv(unsigned a, unsigned b) { return (a + b - 1) / b; }

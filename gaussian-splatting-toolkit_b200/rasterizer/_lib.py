@@ -26,6 +26,7 @@ SIGNATURES = {
     "gsr_version": (C.c_char_p, []),
     "gsr_last_error": (C.c_char_p, []),
     "gsr_built_for_sm": (_i, []),
+    "gsr_launch_count": (C.c_ulonglong, []),
     "gsr_compute_sh_forward": (_i, [_i, _i, _i, _p, _p, _p, _p]),
     "gsr_compute_sh_backward": (_i, [_i, _i, _i, _p, _p, _p, _p]),
     "gsr_compute_sh_backward_multiview": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p]),

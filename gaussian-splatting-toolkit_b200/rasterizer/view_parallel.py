@@ -37,19 +37,24 @@ class GradientBucket:
 
     def __init__(self, num_points: int, sh_bases: int = 16, device="cuda"):
         self.num_points, self.sh_bases = num_points, sh_bases
-        self.flat = torch.zeros(floats_per_gaussian(sh_bases) * num_points, dtype=torch.float32, device=device)
-        self.views: Dict[str, torch.Tensor] = {}
-        self.offsets: Dict[str, Tuple[int, int]] = {}
-        off = 0
-        for name, shape in segment_shapes(num_points, sh_bases).items():
+        shapes = segment_shapes(num_points, sh_bases)
+        # every segment starts on a 16-byte boundary for ANY N (the projection adjoint requires a 16-byte aligned
+        # v_quat, project.cu): offsets are rounded up to a multiple of 4 floats, the <= 3 pad floats stay zero and
+        # simply ride along in the all-reduce
+        sizes, starts, off = {}, {}, 0
+        for name, shape in shapes.items():
             n = 1
             for d in shape:
                 n *= d
-            # every segment starts on a 16-byte boundary (n is a multiple of 4 floats whenever N is)
-            self.views[name] = self.flat[off:off + n].view(shape)
-            self.offsets[name] = (off, off + n)
-            off += n
-        assert off == self.flat.numel()
+            starts[name], sizes[name] = off, n
+            off = (off + n + 3) // 4 * 4
+        self.flat = torch.zeros(off, dtype=torch.float32, device=device)
+        self.views: Dict[str, torch.Tensor] = {}
+        self.offsets: Dict[str, Tuple[int, int]] = {}
+        for name, shape in shapes.items():
+            lo, n = starts[name], sizes[name]
+            self.views[name] = self.flat[lo:lo + n].view(shape)
+            self.offsets[name] = (lo, lo + n)
 
     def __getitem__(self, name: str) -> torch.Tensor:
         return self.views[name]

@@ -56,6 +56,9 @@ typedef enum gsr_status {
 GSR_API const char *gsr_version(void);      /* "0.1.2+b200.<n>": tracks rasterizer/version.py:1 */
 GSR_API const char *gsr_last_error(void);   /* thread-local message of the last non-zero return */
 GSR_API int gsr_built_for_sm(void);         /* 100 : the only arch in the fatbin is sm_100a */
+/* number of kernels of THIS library launched by the process so far (every launch site is counted after its
+ * cudaGetLastError check; library kernels such as CUB's and memsets are not) — bench.py's `gpu_launches` */
+GSR_API unsigned long long gsr_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Spherical harmonics  — replaces compute_sh_forward / compute_sh_backward

@@ -84,3 +84,39 @@ def load_ref():
 if __name__ == "__main__":
     p = build_ref(verbose=True)
     print("reference extension:", p)
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# The reference's PYTHON side under baseline/_ref/ (git-ignored, travels to the GPU box) — used by bench.py's literal
+# `_torch_impl` timing and by tests/test_gpu_dropin_reference_callers.py (the reference's unmodified wrappers / model
+# class driven over libgsr_b200).  Two steps, both only where /root/reference exists:
+#   1. `pip install --no-index --no-build-isolation --no-deps --target baseline/_ref <copy of gs_toolkit/gs_components>`
+#      — the reference's own setup.py (package `rasterizer` + its CUDA extension `rasterizer/csrc.so`, sm_100);
+#   2. the pure-Python `gs_toolkit` package: its build backend (poetry-core) is absent from this image, so
+#      `pip install /root/reference` cannot run; the package directory is copied as pip would have copied it
+#      (minus gs_components — step 1 — and the legacy viewer's static assets).
+BASELINE_REF = os.path.join(os.path.dirname(HERE), "baseline", "_ref")
+REF_ROOT = "/root/reference"
+
+
+def install_ref_python(verbose: bool = False) -> str | None:
+    import shutil
+    import subprocess
+    import tempfile
+
+    if not os.path.isdir(os.path.join(REF_ROOT, "gs_toolkit")):
+        return BASELINE_REF if os.path.isdir(os.path.join(BASELINE_REF, "rasterizer")) else None
+    os.makedirs(BASELINE_REF, exist_ok=True)
+    if not os.path.exists(os.path.join(BASELINE_REF, "rasterizer", "csrc.so")):
+        with tempfile.TemporaryDirectory() as tmp:
+            src = os.path.join(tmp, "gs_components")
+            shutil.copytree(os.path.join(REF_ROOT, "gs_toolkit", "gs_components"), src)
+            env = dict(os.environ, TORCH_CUDA_ARCH_LIST="10.0", MAX_JOBS="8")
+            subprocess.run([sys.executable, "-m", "pip", "install", "--no-index", "--no-build-isolation", "--no-deps",
+                            "--find-links", "/opt/wheelhouse", "--target", BASELINE_REF, src], check=True, env=env,
+                           stdout=None if verbose else subprocess.DEVNULL, stderr=None if verbose else subprocess.DEVNULL)
+    dst = os.path.join(BASELINE_REF, "gs_toolkit")
+    if not os.path.isdir(dst):
+        shutil.copytree(os.path.join(REF_ROOT, "gs_toolkit"), dst,
+                        ignore=shutil.ignore_patterns("gs_components", "viewer_legacy", "__pycache__", "*.so"))
+    return BASELINE_REF

@@ -1,0 +1,56 @@
+"""Unchanged-caller proof of the drop-in boundary.
+
+The reference's OWN Python — its `rasterizer` wrappers (rasterizer/{project_gaussians,rasterize,sh,utils}.py) and its
+model class (`GaussianSplattingModel.get_outputs`, gs_toolkit/models/vanilla_gs.py:672-855), installed unmodified under
+baseline/_ref/ by oracle/build_ref.install_ref_python() — runs twice in fresh interpreters on the same scene: once over
+the reference's own CUDA extension, once over this repository's `rasterizer/csrc.so` (the eleven names of
+csrc/ext.cpp:6-17 as shims over the C ABI of libgsr_b200.so).  Same image, same depth, same `xys.grad`, same parameter
+gradients."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from parity import assert_float_parity
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "baseline", "_ref")
+OURS_SO = os.path.join(ROOT, "gaussian-splatting-toolkit_b200", "rasterizer", "csrc.so")
+
+
+def _run(mode, scene_path, tmp_path):
+    out = str(tmp_path / f"{mode}.npz")
+    env = {k: v for k, v in os.environ.items() if k != "PYTHONPATH"}
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "dropin_child.py"), mode, scene_path, out],
+                         env=env, capture_output=True, text=True)
+    print(res.stdout[-2000:])
+    assert res.returncode == 0, res.stderr[-4000:]
+    return np.load(out)
+
+
+def test_reference_wrappers_and_model_run_unchanged_over_libgsr(tmp_path):
+    if not (os.path.exists(os.path.join(REF, "rasterizer", "csrc.so")) and os.path.isdir(os.path.join(REF, "gs_toolkit"))):
+        pytest.skip("baseline/_ref (reference install) not present")
+    assert os.path.exists(OURS_SO), "rasterizer/csrc.so missing: run __graft_entry__.build()"
+    from rasterizer.synthetic import look_at_viewmat, make_scene
+
+    scene = make_scene(50_000, 640, 400, 0.008, 0.08, margin=1.1, seed=77,
+                       viewmat=look_at_viewmat(yaw_deg=12.0, pitch_deg=-7.0, shift=(0.1, -0.2, 0.3)))
+    scene_path = str(tmp_path / "scene.npz")
+    np.savez(scene_path, **{k: v for k, v in scene.items()})
+    ref = _run("ref", scene_path, tmp_path)
+    ours = _run("ours", scene_path, tmp_path)
+    assert "baseline/_ref" in str(ref["native"]) and str(ours["native"]).endswith("rasterizer/csrc.so")
+    for k in ("A_radii", "A_num_tiles_hit"):
+        assert np.array_equal(ours[k], ref[k]), k
+    for k, frac in (("A_img", 1e-4), ("A_alpha", 1e-4), ("B_rgb", 1e-4), ("B_depth", 1e-3)):
+        assert_float_parity(ours[k], ref[k], k, max_frac_bad=frac)
+    grads = [k for k in ref.files if k.startswith("A_v_") or k.startswith("B_grad_") or k == "B_v_xy"]
+    assert len(grads) == 6 + 1 + 6
+    for k in grads:
+        assert_float_parity(ours[k], ref[k], k, max_norm_rel=5e-5, max_frac_bad=5e-4)
+    print(f"[drop-in] reference wrappers, one view fwd+bwd (50k Gaussians, 640x400), wall: reference ext "
+          f"{float(ref['A_wall_ms_per_view']):.3f} ms, libgsr_b200 behind the same wrappers {float(ours['A_wall_ms_per_view']):.3f} ms")
