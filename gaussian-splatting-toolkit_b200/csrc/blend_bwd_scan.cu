@@ -1,0 +1,248 @@
+// blend_bwd_scan.cu — GAUSSIAN-PARALLEL adjoint of the per-tile alpha compositing (3 channels, FP32, 16x16 tiles).
+//
+// Same function as blend_backward_kernel (blend_bwd.cu; reference rasterize_backward_kernel, csrc/backward.cu:133-303)
+// with the two parallel axes swapped inside a warp:
+//
+//   blend_backward_kernel      lane = PIXEL of the warp's 8x4 block, loop over the surviving Gaussians.  The per-pixel
+//                              state (T, running colour sum) is private; the nine per-Gaussian gradient sums need a
+//                              32-lane reduction PER VISIT (14 SHFL + 28 ALU + a RED, ~45 % of the loop).
+//   blend_backward_scan_kernel lane = GAUSSIAN (32 consecutive survivors of the warp's compacted list), loop over the 32
+//                              pixels of the block.  The nine gradient sums are private registers (no reduction, one set
+//                              of REDs per 32 visits); what crosses lanes is the per-pixel state, and that is a PREFIX
+//                              SCAN over the lanes: the transmittance behind Gaussian j is T_in * prod_{i<=j} 1/(1-alpha_i)
+//                              (back to front), the colour sum behind it a prefix sum — two warp-shuffle scans
+//                              (10 SHFL + 10 ALU) per pixel step, with the per-pixel carry (T, s) kept in shared memory
+//                              between groups of 32 survivors.
+//
+// The per-pixel colour bookkeeping of the reference (three running sums S_c and three v_out terms,
+// backward.cu:243-262) collapses to ONE scalar because the upstream gradient is constant per pixel:
+//   s = sum_c S_c v_out_c - T_final (v_out_alpha - sum_c bg_c v_out_c),   d_j = sum_c rgb_{j,c} v_out_c
+//   v_alpha_j = T_j d_j - ra_j s ,   s <- s + alpha_j T_j d_j             (T_j = transmittance in front of j)
+// Staging (double-buffered packed records), exact warp compaction and the early cut at max(final_idx) are those of
+// blend_bwd.cu; survivors left over at the end of a staged batch stay in registers and are completed from the next
+// batch, so only the last group of a tile can be partially filled.
+#include <stdlib.h>
+
+#include "blend_common.cuh"
+
+namespace gsr {
+
+namespace {
+
+struct LaneGaussian {  // the Gaussian a lane owns for one group
+  float x, y, A, B, C, o, r, g, b;
+  int id;    // Gaussian index, -1 = empty lane
+  int sidx;  // its position in the tile-sorted list (compared with the pixel's final_idx)
+};
+
+__device__ __forceinline__ void load_lane_gaussian(LaneGaussian &G, const float4 (*rec)[BLEND_THREADS], int slot,
+                                                   int batch_end) {
+  const float4 q0 = rec[0][slot], q1 = rec[1][slot], q2 = rec[2][slot];
+  G.x = q0.x; G.y = q0.y;
+  G.A = q1.x; G.B = q1.y; G.C = q1.z; G.o = q1.w;
+  G.r = q2.x; G.g = q2.y; G.b = q2.z;
+  G.id = __float_as_int(q2.w);
+  G.sidx = batch_end - slot;
+}
+
+__device__ __forceinline__ void clear_lane_gaussian(LaneGaussian &G) {
+  G.x = G.y = G.A = G.B = G.C = G.o = G.r = G.g = G.b = 0.f;
+  G.id = -1;
+  G.sidx = 0x7fffffff;
+}
+
+// One group: 32 lanes x 32 pixels.  pixc[p] = {v_out_r, v_out_g, v_out_b, bits(final_idx)}, pixs[p] = {px, py, T, s}.
+__device__ __forceinline__ void process_group(const LaneGaussian &G, const float4 *__restrict__ pixc,
+                                              float4 *__restrict__ pixs, int lane, float *__restrict__ v_xy,
+                                              float *__restrict__ v_conic, float *__restrict__ v_colors,
+                                              float *__restrict__ v_opacity) {
+  const unsigned full = 0xffffffffu;
+  float a_r = 0.f, a_g = 0.f, a_b = 0.f, a_xx = 0.f, a_xy = 0.f, a_yy = 0.f, a_x = 0.f, a_y = 0.f, a_w = 0.f;
+#pragma unroll 2
+  for (int p = 0; p < 32; ++p) {
+    const float4 c = pixc[p];
+    const float4 st = pixs[p];
+    const float dx = G.x - st.x, dy = G.y - st.y;
+    const float gx = G.A * dx, gy = G.C * dy;
+    const float power = dx * (gx + G.B * dy) + gy * dy;  // = -sigma log2(e)
+    const float vis = exp2f(power);
+    const float alpha = fminf(0.99f, G.o * vis);
+    const bool valid = (G.sidx <= __float_as_int(c.w)) && !(power > 0.f || alpha < 1.f / 255.f);
+    const float alpha_e = valid ? alpha : 0.f;
+    const float vis_e = valid ? vis : 0.f;
+    const float ra = 1.f / (1.f - alpha_e);
+    // inclusive product scan over the lanes (lane order = back to front): R_j = prod_{i<=j} ra_i
+    float R = ra;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const float up = __shfl_up_sync(full, R, d);
+      if (lane >= d) R *= up;
+    }
+    const float T = st.z * R;  // transmittance in front of this Gaussian
+    const float fac = alpha_e * T;
+    const float dj = G.r * c.x + G.g * c.y + G.b * c.z;
+    const float cj = fac * dj;
+    float S = cj;  // inclusive sum scan: S_j = sum_{i<=j} alpha_i T_i d_i
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const float up = __shfl_up_sync(full, S, d);
+      if (lane >= d) S += up;
+    }
+    const float s_behind = st.w + (S - cj);
+    const float v_alpha = T * dj - ra * s_behind;
+    const float w = vis_e * v_alpha;
+    a_r += fac * c.x;
+    a_g += fac * c.y;
+    a_b += fac * c.z;
+    const float wdx = w * dx, wdy = w * dy;
+    a_xx += wdx * dx;
+    a_xy += wdx * dy;
+    a_yy += wdy * dy;
+    a_x += wdx;
+    a_y += wdy;
+    a_w += w;
+    if (lane == 31) *reinterpret_cast<float2 *>(&pixs[p].z) = make_float2(T, st.w + S);  // carry to the next group
+  }
+  __syncwarp();
+  if (G.id >= 0) {
+    // v_sigma = -o vis v_alpha = -o w;  conic = -(2A, B, 2C) ln2
+    const unsigned g = (unsigned)G.id;
+    const float no = -G.o;
+    const float ca = -2.f * kLn2 * G.A, cb = -kLn2 * G.B, cc = -2.f * kLn2 * G.C;
+    atomicAdd(v_colors + 3u * g, a_r);
+    atomicAdd(v_colors + 3u * g + 1u, a_g);
+    atomicAdd(v_colors + 3u * g + 2u, a_b);
+    atomicAdd(v_conic + 3u * g, 0.5f * no * a_xx);
+    atomicAdd(v_conic + 3u * g + 1u, no * a_xy);
+    atomicAdd(v_conic + 3u * g + 2u, 0.5f * no * a_yy);
+    atomicAdd(v_xy + 2u * g, no * (ca * a_x + cb * a_y));
+    atomicAdd(v_xy + 2u * g + 1u, no * (cb * a_x + cc * a_y));
+    atomicAdd(v_opacity + g, a_w);
+  }
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(BLEND_THREADS, 3)
+blend_backward_scan_kernel(int tiles_x, int img_w, int img_h, const int *__restrict__ gaussian_ids_sorted,
+                           const int2 *__restrict__ tile_bins, const float2 *__restrict__ xys,
+                           const float *__restrict__ conics, const float *__restrict__ colors,
+                           const float *__restrict__ opacities, const float *__restrict__ background,
+                           const float *__restrict__ final_Ts, const int *__restrict__ final_idx,
+                           const float *__restrict__ v_output, const float *__restrict__ v_output_alpha,
+                           float *__restrict__ v_xy, float *__restrict__ v_conic, float *__restrict__ v_colors,
+                           float *__restrict__ v_opacity) {
+  __shared__ float4 s_rec[2][3][BLEND_THREADS];
+  __shared__ unsigned char s_list[BLEND_THREADS / 32][BLEND_THREADS];
+  __shared__ float4 s_pixc[BLEND_THREADS / 32][32];
+  __shared__ float4 s_pixs[BLEND_THREADS / 32][32];
+  __shared__ int s_warp_max[BLEND_THREADS / 32];
+
+  const unsigned full = 0xffffffffu;
+  const int tile_x = blockIdx.x, tile_y = blockIdx.y;
+  const int tile_id = tile_y * tiles_x + tile_x;
+  const int tr = threadIdx.x, nthreads = BLEND_THREADS, lane = tr & 31, warp = tr >> 5;
+  int lx, ly;
+  map_pixel(16, lx, ly);
+  const int ipx = tile_x * 16 + lx, ipy = tile_y * 16 + ly;
+  const bool inside = (ipx < img_w) && (ipy < img_h);
+  const int pix = inside ? (ipy * img_w + ipx) : 0;
+
+  const float fx0 = (float)__reduce_min_sync(full, inside ? ipx : 0x7fffffff);
+  const float fx1 = (float)__reduce_max_sync(full, inside ? ipx : -0x7fffffff);
+  const float fy0 = (float)__reduce_min_sync(full, inside ? ipy : 0x7fffffff);
+  const float fy1 = (float)__reduce_max_sync(full, inside ? ipy : -0x7fffffff);
+
+  const int2 range = tile_bins[tile_id];
+  const int bin_final = inside ? final_idx[pix] : -1;
+  {
+    const float T_final = inside ? final_Ts[pix] : 1.f;
+    float vo_r = 0.f, vo_g = 0.f, vo_b = 0.f, vo_a = 0.f;
+    if (inside) {
+      vo_r = v_output[3 * (size_t)pix];
+      vo_g = v_output[3 * (size_t)pix + 1];
+      vo_b = v_output[3 * (size_t)pix + 2];
+      vo_a = v_output_alpha[pix];
+    }
+    // T_final ra v_out_alpha - T_final ra sum_c bg_c v_out_c = ra c_final (backward.cu:252-256); s starts at -c_final
+    const float c_final = T_final * (vo_a - (background[0] * vo_r + background[1] * vo_g + background[2] * vo_b));
+    s_pixc[warp][lane] = make_float4(vo_r, vo_g, vo_b, __int_as_float(bin_final));
+    s_pixs[warp][lane] = make_float4((float)ipx, (float)ipy, T_final, -c_final);
+  }
+  const int warp_bin_final = __reduce_max_sync(full, bin_final);
+  if (lane == 0) s_warp_max[warp] = warp_bin_final;
+  __syncthreads();
+  int cta_bin_final = -1;
+  for (int w = 0; w < (nthreads >> 5); ++w) cta_bin_final = max(cta_bin_final, s_warp_max[w]);
+
+  const int end = min(range.y, cta_bin_final + 1);
+  const int count = end - range.x;
+  if (count <= 0) return;  // uniform across the CTA
+  const int num_batches = (count + nthreads - 1) / nthreads;
+
+  BlendRecord rec;
+  if (end - 1 - tr >= range.x)
+    rec = gather_record(gaussian_ids_sorted[end - 1 - tr], xys, conics, colors, opacities);
+
+  LaneGaussian G;
+  clear_lane_gaussian(G);
+  int n_pending = 0;  // lanes [0, n_pending) hold survivors of earlier batches that wait for a full group
+
+  for (int b = 0; b < num_batches; ++b) {
+    const int buf = b & 1;
+    const int batch_end = end - 1 - nthreads * b;  // sorted index held by slot 0; slot t holds batch_end - t
+    if (batch_end - tr >= range.x) {
+      s_rec[buf][0][tr] = rec.r0;
+      s_rec[buf][1][tr] = rec.r1;
+      s_rec[buf][2][tr] = rec.r2;
+    }
+    __syncthreads();
+    {
+      const int nxt = batch_end - nthreads - tr;
+      if (nxt >= range.x) rec = gather_record(gaussian_ids_sorted[nxt], xys, conics, colors, opacities);
+    }
+    const int batch_size = min(nthreads, batch_end + 1 - range.x);
+    const int t_begin = max(0, batch_end - warp_bin_final);  // slots before it are behind every pixel's last contributor
+    if (t_begin >= batch_size) continue;
+    const int n_list = compact_survivors(s_rec[buf][0], s_rec[buf][1], t_begin, batch_size, fx0, fx1, fy0, fy1,
+                                         s_list[warp], lane);
+    int li = 0;  // next unread entry of the list
+    while (n_pending + (n_list - li) >= 32) {
+      if (lane >= n_pending) load_lane_gaussian(G, s_rec[buf], s_list[warp][li + lane - n_pending], batch_end);
+      li += 32 - n_pending;
+      n_pending = 0;
+      process_group(G, s_pixc[warp], s_pixs[warp], lane, v_xy, v_conic, v_colors, v_opacity);
+    }
+    const int rest = n_list - li;  // < 32 - n_pending
+    if (lane >= n_pending && lane < n_pending + rest)
+      load_lane_gaussian(G, s_rec[buf], s_list[warp][li + lane - n_pending], batch_end);
+    n_pending += rest;
+  }
+  if (n_pending > 0) {
+    if (lane >= n_pending) clear_lane_gaussian(G);
+    process_group(G, s_pixc[warp], s_pixs[warp], lane, v_xy, v_conic, v_colors, v_opacity);
+  }
+}
+
+// GSR_BWD_KERNEL = pixel (default) | scan — read once; A/B switch between the two adjoint kernels
+int blend_bwd_use_scan() {
+  static const int v = [] {
+    const char *e = getenv("GSR_BWD_KERNEL");
+    return (e && e[0] == 's') ? 1 : 0;
+  }();
+  return v;
+}
+
+int launch_blend_backward_scan(dim3 grid, cudaStream_t st, int img_w, int img_h, const int *gaussian_ids_sorted,
+                               const int2 *tile_bins, const float2 *xys, const float *conics, const float *colors,
+                               const float *opacities, const float *background, const float *final_Ts,
+                               const int *final_idx, const float *v_output, const float *v_output_alpha, float *v_xy,
+                               float *v_conic, float *v_colors, float *v_opacity) {
+  blend_backward_scan_kernel<<<grid, BLEND_THREADS, 0, st>>>((int)grid.x, img_w, img_h, gaussian_ids_sorted, tile_bins, xys,
+                                                             conics, colors, opacities, background, final_Ts, final_idx,
+                                                             v_output, v_output_alpha, v_xy, v_conic, v_colors, v_opacity);
+  GSR_CHECK_LAUNCH("blend_backward_scan_kernel");
+  return GSR_OK;
+}
+
+}  // namespace gsr

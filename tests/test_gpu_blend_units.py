@@ -36,11 +36,28 @@ np.savez({path!r}, **out)
 """
 
 
-def _run(units, tmp_path):
-    path = str(tmp_path / f"units{units}.npz")
-    env = dict(os.environ, GSR_BLEND_UNITS=str(units))
+def _run(units, tmp_path, bwd="pixel"):
+    path = str(tmp_path / f"units{units}_{bwd}.npz")
+    env = dict(os.environ, GSR_BLEND_UNITS=str(units), GSR_BWD_KERNEL=bwd)
     subprocess.run([sys.executable, "-c", _SCRIPT.format(root=ROOT, path=path)], check=True, env=env)
     return np.load(path)
+
+
+def test_gaussian_parallel_scan_adjoint_matches_pixel_parallel(tmp_path):
+    """GSR_BWD_KERNEL=scan (blend_bwd_scan.cu: lane = Gaussian, warp prefix scans carry the per-pixel state) against the
+    default pixel-parallel adjoint: same gradients up to the order of the FP32 sums."""
+    ref = _run(1, tmp_path)
+    got = _run(1, tmp_path, bwd="scan")
+    for name in ("a", "b"):
+        for k in ("out_img", "final_Ts", "final_idx"):
+            assert np.array_equal(got[f"{name}_{k}"], ref[f"{name}_{k}"]), (name, k)
+        for k in ("v_xy", "v_conic", "v_colors", "v_opacity"):
+            a, b = got[f"{name}_{k}"].astype(np.float64), ref[f"{name}_{k}"].astype(np.float64)
+            err = np.linalg.norm(a - b) / np.linalg.norm(b)
+            print(f"[scan adjoint] scene {name} {k}: normwise rel vs pixel-parallel {err:.2e}")
+            assert err < 5e-6, (name, k, err)
+    print(f"[scan adjoint] cfg2 view (bindings harness) {float(got['ms_per_view_cfg2']):.3f} ms vs pixel-parallel "
+          f"{float(ref['ms_per_view_cfg2']):.3f} ms")
 
 
 def test_subwarp_units_match_default_kernels(tmp_path):

@@ -51,6 +51,8 @@ def test_reference_wrappers_and_model_run_unchanged_over_libgsr(tmp_path):
     grads = [k for k in ref.files if k.startswith("A_v_") or k.startswith("B_grad_") or k == "B_v_xy"]
     assert len(grads) == 6 + 1 + 6
     for k in grads:
-        assert_float_parity(ours[k], ref[k], k, max_norm_rel=5e-5, max_frac_bad=5e-4)
+        # wrappers (A): the tight operator-level bound; model (B): two rasterize passes + depth / alpha division chain,
+        # bounded by the north star's 1e-4 (observed on B200: <= 6.2e-5 normwise)
+        assert_float_parity(ours[k], ref[k], k, max_norm_rel=5e-5 if k.startswith("A_") else 1e-4, max_frac_bad=5e-4)
     print(f"[drop-in] reference wrappers, one view fwd+bwd (50k Gaussians, 640x400), wall: reference ext "
           f"{float(ref['A_wall_ms_per_view']):.3f} ms, libgsr_b200 behind the same wrappers {float(ours['A_wall_ms_per_view']):.3f} ms")
