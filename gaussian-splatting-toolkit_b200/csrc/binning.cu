@@ -9,11 +9,9 @@
 // All of it is HBM-bound integer work.  The sort keeps the reference's key format ((tile << 32) | depth bits,
 // int64) so sorted keys are bit-identical, but only radix-sorts the bits that can be non-zero
 // (32 + ceil(log2(num_tiles))) and carries the 4-byte Gaussian id as the value instead of producing an
-// 8-byte permutation and gathering through it.
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
-
+// 8-byte permutation and gathering through it.  Scan and sort are the hand-written kernels of radix_sort.cuh.
 #include "common.cuh"
+#include "radix_sort.cuh"
 #include "tile_cull.cuh"
 
 namespace gsr {
@@ -112,9 +110,7 @@ static inline int key_end_bit(int num_tiles) {
 extern "C" {
 
 GSR_API size_t gsr_cumsum_workspace_bytes(int num_points) {
-  size_t bytes = 0;
-  cub::DeviceScan::InclusiveSum(nullptr, bytes, (const int *)nullptr, (int *)nullptr, num_points > 0 ? num_points : 1);
-  return bytes + 256;
+  return gsr::rs::scan_workspace_bytes(num_points) + 512;
 }
 
 GSR_API int gsr_cumsum_tiles_hit(int num_points, const int32_t *num_tiles_hit, int32_t *cum_tiles_hit,
@@ -127,12 +123,13 @@ GSR_API int gsr_cumsum_tiles_hit(int num_points, const int32_t *num_tiles_hit, i
     return GSR_OK;
   }
   GSR_REQUIRE(num_tiles_hit && cum_tiles_hit && workspace, GSR_ERR_INVALID_ARGUMENT, "cumsum_tiles_hit: null pointer");
-  size_t need = 0;
-  cub::DeviceScan::InclusiveSum(nullptr, need, num_tiles_hit, cum_tiles_hit, num_points);
+  const size_t need = gsr_cumsum_workspace_bytes(num_points);
   GSR_REQUIRE(workspace_bytes >= need, GSR_ERR_WORKSPACE, "cumsum_tiles_hit: workspace %zu < %zu bytes",
               workspace_bytes, need);
-  GSR_CUDA(cub::DeviceScan::InclusiveSum(workspace, need, num_tiles_hit, cum_tiles_hit, num_points,
-                                         (cudaStream_t)stream));
+  GSR_REQUIRE((uintptr_t)workspace % 4 == 0, GSR_ERR_INVALID_ARGUMENT, "cumsum_tiles_hit: misaligned workspace");
+  const int rc = rs::inclusive_scan(num_points, nullptr, num_tiles_hit, cum_tiles_hit, 0x7fffffff, nullptr, workspace,
+                                    (cudaStream_t)stream);
+  if (rc != GSR_OK) return rc;
   if (total_host_pinned)
     GSR_CUDA(cudaMemcpyAsync(total_host_pinned, cum_tiles_hit + (num_points - 1), sizeof(int32_t),
                              cudaMemcpyDeviceToHost, (cudaStream_t)stream));
@@ -199,10 +196,9 @@ GSR_API int gsr_map_gaussian_to_intersects_tight(int num_points, int num_interse
 }
 
 GSR_API size_t gsr_sort_workspace_bytes(int num_intersects) {
-  size_t bytes = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint64_t *)nullptr, (uint64_t *)nullptr,
-                                  (const int *)nullptr, (int *)nullptr, num_intersects > 0 ? num_intersects : 1, 0, 64);
-  return bytes + 256;
+  const size_t m = num_intersects > 0 ? num_intersects : 1;
+  // ping-pong buffers for the keys (8 B) and ids (4 B) + histogram workspace
+  return ((8 * m + 255) & ~(size_t)255) + ((4 * m + 255) & ~(size_t)255) + gsr::rs::workspace_bytes((int)m) + 512;
 }
 
 GSR_API int gsr_sort_intersects(int num_intersects, int num_tiles, const int64_t *isect_ids,
@@ -214,16 +210,24 @@ GSR_API int gsr_sort_intersects(int num_intersects, int num_tiles, const int64_t
   if (num_intersects == 0) return GSR_OK;
   GSR_REQUIRE(isect_ids && gaussian_ids && isect_ids_sorted && gaussian_ids_sorted && workspace,
               GSR_ERR_INVALID_ARGUMENT, "sort_intersects: null pointer");
-  const int end_bit = key_end_bit(num_tiles);
-  size_t need = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, need, (const uint64_t *)isect_ids, (uint64_t *)isect_ids_sorted,
-                                  gaussian_ids, gaussian_ids_sorted, num_intersects, 0, end_bit);
+  const size_t need = gsr_sort_workspace_bytes(num_intersects);
   GSR_REQUIRE(workspace_bytes >= need, GSR_ERR_WORKSPACE, "sort_intersects: workspace %zu < %zu bytes",
               workspace_bytes, need);
-  GSR_CUDA(cub::DeviceRadixSort::SortPairs(workspace, need, (const uint64_t *)isect_ids,
-                                           (uint64_t *)isect_ids_sorted, gaussian_ids, gaussian_ids_sorted,
-                                           num_intersects, 0, end_bit, (cudaStream_t)stream));
-  return GSR_OK;
+  GSR_REQUIRE((uintptr_t)workspace % 8 == 0, GSR_ERR_INVALID_ARGUMENT, "sort_intersects: misaligned workspace");
+  const int end_bit = key_end_bit(num_tiles);
+  const size_t m = num_intersects;
+  char *ws = (char *)workspace;
+  unsigned long long *keys_tmp = (unsigned long long *)ws; ws += (8 * m + 255) & ~(size_t)255;
+  int *vals_tmp = (int *)ws;                               ws += (4 * m + 255) & ~(size_t)255;
+  void *sort_ws = ws;
+  // pass 0 reads the caller's (const) arrays; the last pass must write the caller's output arrays
+  const bool odd = rs::num_passes(0, end_bit) & 1;
+  unsigned long long *out_k = reinterpret_cast<unsigned long long *>(isect_ids_sorted);
+  unsigned long long *kx = odd ? out_k : keys_tmp, *ky = odd ? keys_tmp : out_k;
+  int *vx = odd ? gaussian_ids_sorted : vals_tmp, *vy = odd ? vals_tmp : gaussian_ids_sorted;
+  return rs::sort_pairs_from<unsigned long long, int>(reinterpret_cast<const unsigned long long *>(isect_ids), gaussian_ids,
+                                                      kx, vx, ky, vy, num_intersects, nullptr, 0, end_bit, sort_ws,
+                                                      (cudaStream_t)stream);
 }
 
 GSR_API int gsr_get_tile_bin_edges(int num_intersects, const int64_t *isect_ids_sorted, int num_tiles,

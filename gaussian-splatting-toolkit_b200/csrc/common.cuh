@@ -76,7 +76,9 @@ __device__ __forceinline__ bool cov2d_to_conic_radius(float cxx, float cxy, floa
 
 // (w,x,y,z) quaternion -> row-major rotation matrix (normalises inside): reference helpers.cuh:144-159
 __device__ __forceinline__ void quat_to_rotmat(float qw, float qx, float qy, float qz, float R[9]) {
-  float s = rsqrtf(qw * qw + qx * qx + qy * qy + qz * qz);
+  // summation order of the reference: its float4 holds (w,x,y,z) in the fields (x,y,z,w) and it adds w*w + x*x + y*y + z*z
+  // over the FIELDS, i.e. z^2 first (helpers.cuh:146-147)
+  float s = rsqrtf(qz * qz + qw * qw + qx * qx + qy * qy);
   float w = qw * s, x = qx * s, y = qy * s, z = qz * s;
   R[0] = 1.f - 2.f * (y * y + z * z);
   R[1] = 2.f * (x * y - w * z);

@@ -43,7 +43,8 @@ __device__ __forceinline__ ProjFwd project_one(float px, float py, float pz, flo
     o_cov3d[5] = M[6] * M[6] + M[7] * M[7] + M[8] * M[8];
 
     // project_cov3d_ewa (forward.cu:398-442)
-    const float tan_fovx = 0.5f * (float)img_w / fx, tan_fovy = 0.5f * (float)img_h / fy;
+    // the reference evaluates `0.5 * img_size.x / fx` in DOUBLE (forward.cu:71-72) and rounds once
+    const float tan_fovx = (float)(0.5 * (double)img_w / (double)fx), tan_fovy = (float)(0.5 * (double)img_h / (double)fy);
     const float lim_x = 1.3f * tan_fovx, lim_y = 1.3f * tan_fovy;
     const float tz = vz;
     const float tx = tz * fminf(lim_x, fmaxf(-lim_x, vx / tz));
@@ -62,7 +63,7 @@ __device__ __forceinline__ ProjFwd project_one(float px, float py, float pz, flo
     const float b1 = T1[0] * c3[1] + T1[1] * c3[3] + T1[2] * c3[4];
     const float b2 = T1[0] * c3[2] + T1[1] * c3[4] + T1[2] * c3[5];
     const float c00 = a0 * T0[0] + a1 * T0[1] + a2 * T0[2];
-    const float c01 = a0 * T1[0] + a1 * T1[1] + a2 * T1[2];
+    const float c01 = b0 * T0[0] + b1 * T0[1] + b2 * T0[2];  // the reference reads cov[0][1] = column 0, row 1 of glm's (T V) T^T
     const float c11 = b0 * T1[0] + b1 * T1[1] + b2 * T1[2];
     const float det_orig = c00 * c11 - c01 * c01;
     const float cxx = c00 + 0.3f, cxy = c01, cyy = c11 + 0.3f;

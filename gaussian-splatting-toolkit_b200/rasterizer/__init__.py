@@ -12,7 +12,8 @@ rasterizer.project_gaussians, rasterizer.rasterize, rasterizer._torch_impl (quat
 Beyond the drop-in surface (not part of the reference package; a model opts in):
 rasterizer.fused (one-node render operator), rasterizer.losses (fused L1 + SSIM), rasterizer.optim (one-launch Adam for
 the parameter groups), rasterizer.densify (after_train / refinement_after as compaction kernels), rasterizer.io_ply /
-rasterizer.io_scene (.ply, checkpoints, transforms.json), rasterizer.view_parallel (multi-GPU gradient exchange).
+rasterizer.io_scene (.ply, checkpoints, transforms.json), rasterizer.view_parallel (multi-GPU gradient exchange),
+rasterizer.binning (`set_binning_mode("async")`: rasterize without the host read of the pair count).
 
 All compute happens in libgsr_b200.so (hand-written sm_100a CUDA, C ABI in include/gsr_b200.h); importing
 this package does not load the library (so CPU-only tooling can import it) but the first operator call
@@ -25,6 +26,7 @@ from typing import Any
 
 import torch
 
+from .binning import BinningOverflow, get_binning_mode, set_binning_mode
 from .gaussian_rasterizer import GaussianRasterizationSettings, GaussianRasterizer
 from .project_gaussians import project_gaussians
 from .rasterize import rasterize_gaussians
@@ -60,6 +62,10 @@ __all__ = [
     # Inria-style façade (not part of the reference package; see gaussian_rasterizer.py)
     "GaussianRasterizer",
     "GaussianRasterizationSettings",
+    # asynchronous tile binning (no host read of the pair count; see binning.py)
+    "set_binning_mode",
+    "get_binning_mode",
+    "BinningOverflow",
 ]
 
 

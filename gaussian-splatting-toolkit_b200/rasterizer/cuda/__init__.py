@@ -11,7 +11,7 @@ AT_ERROR shape checks of bindings.cu:65-68,86-93,420-426,490-496.
 """
 from __future__ import annotations
 
-from typing import Tuple
+from typing import Optional, Tuple
 
 import torch
 from torch import Tensor
@@ -321,6 +321,36 @@ def bin_gaussians_fast(xys: Tensor, depths: Tensor, radii: Tensor, conics: Tenso
                                          int(img_height), int(img_width), int(block_width), _ptr(ids_sorted),
                                          _ptr(tile_bins), _ptr(ws2), ws2_bytes, st), "bin_emit_sort")
     return m, ids_sorted, tile_bins
+
+
+def bin_gaussians_device(xys: Tensor, depths: Tensor, radii: Tensor, conics: Tensor, opacities: Tensor,
+                         img_height: int, img_width: int, block_width: int, capacity: int,
+                         meta_pinned: Optional[Tensor] = None):
+    """Asynchronous internal binning (include/gsr_b200.h, gsr_bin_gaussians_device): the pair count M stays on the
+    device, nothing synchronises.  Returns (gaussian_ids_sorted [capacity] i32, tile_bins [T,2] i32, meta int32[4] on
+    the device = {M, overflow, min(M, capacity), 0}).  `meta_pinned` (pinned host int32[4]) receives a copy on the
+    current stream; the caller inspects it later (rasterizer.binning)."""
+    _check_input(xys, "xys", torch.float32)
+    _check_input(depths, "depths", torch.float32)
+    _check_input(radii, "radii", torch.int32)
+    _check_input(conics, "conics", torch.float32)
+    _check_input(opacities, "opacities", torch.float32)
+    lib = _lib.load()
+    n, dev = xys.size(0), xys.device
+    capacity = int(capacity)
+    tiles_x = (img_width + block_width - 1) // block_width
+    tiles_y = (img_height + block_width - 1) // block_width
+    ids_sorted = torch.empty((max(capacity, 1),), dtype=torch.int32, device=dev)
+    tile_bins = torch.empty((tiles_x * tiles_y, 2), dtype=torch.int32, device=dev)
+    meta = torch.empty((4,), dtype=torch.int32, device=dev)
+    ws_bytes = lib.gsr_bin_device_workspace_bytes(n, capacity)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    with _Guard(xys) as st:
+        _lib.check(lib.gsr_bin_gaussians_device(
+            n, _ptr(xys), _ptr(depths), _ptr(radii), _ptr(conics), _ptr(opacities), int(img_height), int(img_width),
+            int(block_width), capacity, _ptr(ids_sorted), _ptr(tile_bins), _ptr(meta),
+            _P(meta_pinned.data_ptr()) if meta_pinned is not None else None, _ptr(ws), ws_bytes, st), "bin_gaussians_device")
+    return ids_sorted, tile_bins, meta
 
 
 def sort_intersects(isect_ids: Tensor, gaussian_ids: Tensor, num_tiles: int) -> Tuple[Tensor, Tensor]:

@@ -19,6 +19,7 @@ import torch
 from torch import Tensor
 from torch.autograd import Function
 
+from . import binning as _binning
 from . import cuda as _C
 
 
@@ -73,10 +74,13 @@ class _RenderGaussians(Function):
         rec, xys, depths, radii, conics, opac, mask, comp = _C.fused_preprocess_forward(
             means3d, scales, quats, opac_raw, features_dc.reshape(n, 3), features_rest, viewmat, projmat, glob_scale, fx, fy,
             cx, cy, img_height, img_width, block_width, degrees_to_use, clip_thresh, antialiased)
-        m, ids_sorted, tile_bins = _C.bin_gaussians_fast(xys, depths, radii, conics, opac, img_height, img_width,
-                                                         block_width)
+        # sync mode: one host read of M; async mode (rasterizer.binning): m is None, nothing synchronises
+        m, ids_sorted, tile_bins = _binning.bin_gaussians(xys, depths, radii, conics, opac, img_height, img_width,
+                                                          block_width)
         dev = means3d.device
-        if m < 1:
+        if m is None:
+            m = -1  # unknown on the host (asynchronous binning): treated as non-empty, empty tiles blend to background
+        if m == 0:
             rgb = torch.ones(img_height, img_width, 3, device=dev) * background
             depth = torch.zeros(img_height, img_width, device=dev)
             final_Ts = torch.ones(img_height, img_width, device=dev)
@@ -91,7 +95,7 @@ class _RenderGaussians(Function):
         ctx.meta = (fx, fy, img_height, img_width, block_width, degrees_to_use, render_depth, glob_scale, m,
                     features_rest.shape[1] if features_rest.dim() == 3 else 0, tuple(features_dc.shape))
         ctx.aux = aux
-        if m < 1:
+        if m == 0:
             ctx.save_for_backward(means3d, scales, quats, opacities, viewmat, projmat)
         else:
             ctx.save_for_backward(means3d, scales, quats, opacities, viewmat, projmat, rec, radii, conics, mask,
@@ -105,7 +109,9 @@ class _RenderGaussians(Function):
         saved = ctx.saved_tensors
         means3d, scales, quats, opacities, viewmat, projmat = saved[:6]
         n = means3d.shape[0]
-        if m < 1:
+        if m < 0:
+            _binning.poll()  # non-blocking: raises if an earlier asynchronous call overflowed its pair buffers
+        if m == 0:
             z = torch.zeros_like
             grads = (z(means3d), z(scales), z(quats), torch.zeros(n, 3, device=means3d.device),
                      torch.zeros(n, k_rest, 3, device=means3d.device), z(opacities))

@@ -10,6 +10,7 @@ from torch.autograd import Function
 
 import os
 
+from . import binning as _binning
 from . import cuda as _C
 from .utils import bin_and_sort_gaussians, compute_cumulative_intersects, get_tile_bin_edges
 
@@ -53,7 +54,8 @@ def _bin_tight(xys, depths, radii, conics, opacity, img_height, img_width, block
     hit = _BinCache.lookup(tensors, meta)
     if hit is not None:
         return hit
-    result = _C.bin_gaussians_fast(xys, depths, radii, conics, opacity.reshape(-1), img_height, img_width, block_width)
+    # sync mode: one host read of M (as the reference); async mode (rasterizer.binning): none
+    result = _binning.bin_gaussians(xys, depths, radii, conics, opacity, img_height, img_width, block_width)
     _BinCache.store(tensors, meta, result)
     return result
 
@@ -101,7 +103,7 @@ class _RasterizeGaussians(Function):
             cum_tiles_hit = None
         else:
             num_intersects, cum_tiles_hit = compute_cumulative_intersects(num_tiles_hit)
-        if num_intersects < 1:
+        if num_intersects is not None and num_intersects < 1:
             # empty scene: background image, zero-size bookkeeping (rasterizer/rasterize.py:119-127)
             out_img = torch.ones(img_height, img_width, channels, device=xys.device) * background
             gaussian_ids_sorted = torch.zeros(0, 1, device=xys.device)
@@ -130,7 +132,9 @@ class _RasterizeGaussians(Function):
             v_out_alpha = torch.zeros_like(v_out_img[..., 0])
         (gaussian_ids_sorted, tile_bins, xys, conics, colors, opacity, background, final_Ts,
          final_idx) = ctx.saved_tensors
-        if num_intersects < 1:
+        if _binning.get_binning_mode() == "async":
+            _binning.poll()  # non-blocking: raises if an earlier asynchronous call overflowed its pair buffers
+        if num_intersects is not None and num_intersects < 1:
             v_xy, v_conic = torch.zeros_like(xys), torch.zeros_like(conics)
             v_colors, v_opacity = torch.zeros_like(colors), torch.zeros_like(opacity)
         else:

@@ -38,7 +38,7 @@ _pinned_total = {}
 def compute_cumulative_intersects(num_tiles_hit: Tensor) -> Tuple[int, Tensor]:
     """(M, cum_tiles_hit) — int32 inclusive scan + host read of the total (rasterizer/utils.py:106-125).
 
-    The scan is CUB's (inside libgsr_b200); the total travels through a pinned host word filled by an async
+    The scan is libgsr_b200's own (csrc/radix_sort.cuh); the total travels through a pinned host word filled by an async
     copy on the same stream, followed by a stream (not device) synchronisation."""
     nth = num_tiles_hit.contiguous()
     if nth.numel() == 0:

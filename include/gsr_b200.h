@@ -187,6 +187,21 @@ GSR_API int gsr_bin_emit_sort(int num_points, int num_intersects, const float *x
                               unsigned img_height, unsigned img_width, unsigned block_width,
                               int32_t *gaussian_ids_sorted, int32_t *tile_bins, void *workspace,
                               size_t workspace_bytes, void *stream);
+/* Asynchronous form of the fast binning: the pair count M stays on the DEVICE.  Every kernel after the scan reads it from
+ * `meta` and runs on a grid sized for `capacity`; the call neither synchronises nor allocates, so a whole view can be
+ * captured in a CUDA graph (the reference's `.item()`, rasterizer/utils.py:124, is the one host read this removes).
+ *   gaussian_ids_sorted [capacity] i32 (entries >= min(M, capacity) are unspecified), tile_bins [T,2] i32,
+ *   meta  DEVICE int32[4] = {M, overflow (M > capacity), min(M, capacity), 0}; if meta_host_pinned != NULL the four words
+ *   are also copied there on `stream` (read them after an event / at the next call: `overflow` means the farthest
+ *   pairs were dropped and the caller must repeat the view with a larger capacity).
+ * Sorting and scanning are the library's own kernels (csrc/radix_sort.cuh); per-tile order as above. */
+GSR_API size_t gsr_bin_device_workspace_bytes(int num_points, int capacity);
+GSR_API int gsr_bin_gaussians_device(int num_points, const float *xys, const float *depths, const int32_t *radii,
+                                     const float *conics, const float *opacities, unsigned img_height,
+                                     unsigned img_width, unsigned block_width, int capacity,
+                                     int32_t *gaussian_ids_sorted, int32_t *tile_bins, int32_t *meta,
+                                     int32_t *meta_host_pinned /*nullable*/, void *workspace, size_t workspace_bytes,
+                                     void *stream);
 GSR_API size_t gsr_sort_workspace_bytes(int num_intersects);
 GSR_API int gsr_sort_intersects(int num_intersects, int num_tiles, const int64_t *isect_ids,
                                 const int32_t *gaussian_ids, int64_t *isect_ids_sorted,

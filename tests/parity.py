@@ -33,9 +33,12 @@ def rel_report(a, b, name="", atol=None):
                 frac_bad=float(bad.mean()), scale=scale)
 
 
-def assert_float_parity(a, b, name, mask=None, max_norm_rel=RTOL, max_frac_bad=0.0, atol=None, verbose=True):
+def assert_float_parity(a, b, name, mask=None, max_norm_rel=RTOL, max_frac_bad=0.0, atol=None, verbose=True,
+                        min_bad_count=0):
     """Elementwise |a-b| <= 1e-4*|b| + atol (atol defaults to 1e-4 * rms(b)) on all but `max_frac_bad` of the
-    elements, AND normwise relative error <= max_norm_rel.  `mask` (bool, True = compare) restricts the check."""
+    elements (or `min_bad_count` elements, whichever is larger: on a 3 000-Gaussian scene ONE flipped threshold
+    decision already moves ~4 gradient entries = 7e-4 of a 6 000-element tensor), AND normwise relative error
+    <= max_norm_rel.  `mask` (bool, True = compare) restricts the check."""
     a, b = to_np(a), to_np(b)
     if mask is not None:
         mask = to_np(mask).astype(bool)
@@ -46,7 +49,8 @@ def assert_float_parity(a, b, name, mask=None, max_norm_rel=RTOL, max_frac_bad=0
         print(f"[parity] {name:28s} max_abs={r['max_abs']:.3e} norm_rel={r['norm_rel']:.3e} "
               f"frac_bad={r['frac_bad']:.2e} rms_ref={r['scale']:.3e}")
     assert r["norm_rel"] <= max_norm_rel, f"{name}: normwise relative error {r['norm_rel']:.3e} > {max_norm_rel:.1e}"
-    assert r["frac_bad"] <= max_frac_bad, f"{name}: {r['frac_bad']:.3e} of elements outside 1e-4 (allowed {max_frac_bad:.1e})"
+    allowed = max(max_frac_bad, (min_bad_count + 0.5) / max(1, a.size))
+    assert r["frac_bad"] <= allowed, f"{name}: {r['frac_bad']:.3e} of elements outside 1e-4 (allowed {allowed:.1e})"
     return r
 
 

@@ -1,0 +1,117 @@
+"""The hand-written sort / scan and the asynchronous (device-side M) binning against the synchronous path and torch."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _projected(scene):
+    from rasterizer import cuda as C
+    from rasterizer.synthetic import scene_to_torch
+
+    s = scene_to_torch(scene, "cuda")
+    N = s["means3d"].shape[0]
+    out = C.project_gaussians_forward(N, s["means3d"], s["scales"], 1.0, s["quats"], s["viewmat"], s["projmat"], s["fx"],
+                                      s["fy"], s["cx"], s["cy"], s["img_height"], s["img_width"], s["block_width"], 0.01)
+    return s, out
+
+
+@pytest.mark.parametrize("case", ["60k_500x300", "tiny_300_40x24_bw4", "cfg2", "onepass_2k_64x64"])
+def test_device_binning_matches_synchronous_binning(case):
+    from rasterizer import cuda as C
+    from rasterizer.synthetic import make_config_scene, make_scene
+
+    scene = {"60k_500x300": lambda: make_scene(60_000, 500, 300, 0.004, 0.05, margin=1.1, seed=31),
+             "tiny_300_40x24_bw4": lambda: make_scene(300, 40, 24, 0.05, 0.2, seed=1, block_width=4),
+             "cfg2": lambda: make_config_scene("cfg2"),
+             "onepass_2k_64x64": lambda: make_scene(2000, 64, 64, 0.02, 0.2, seed=5)}[case]()  # 16 tiles: one radix pass
+    s, (cov3d, xys, depths, radii, conics, comp, nth) = _projected(scene)
+    H, W, bw = s["img_height"], s["img_width"], s["block_width"]
+    op = s["opacities"].contiguous()
+    m, ids, bins = C.bin_gaussians_fast(xys, depths, radii, conics, op, H, W, bw)
+    pin = torch.zeros(4, dtype=torch.int32).pin_memory()
+    ids_d, bins_d, meta = C.bin_gaussians_device(xys, depths, radii, conics, op, H, W, bw, int(1.3 * m) + 7, meta_pinned=pin)
+    torch.cuda.synchronize()
+    assert pin.tolist() == [m, 0, m, 0] and meta.tolist() == [m, 0, m, 0]
+    assert torch.equal(ids_d[:m], ids) and torch.equal(bins_d, bins)
+    # exactly full buffers are not an overflow
+    ids_e, bins_e, meta_e = C.bin_gaussians_device(xys, depths, radii, conics, op, H, W, bw, m)
+    assert meta_e.tolist() == [m, 0, m, 0] and torch.equal(ids_e[:m], ids) and torch.equal(bins_e, bins)
+    # overflow: flagged, and the kept pairs are the first `cap` of the depth-ordered emission (the nearest Gaussians)
+    cap = max(1, m // 2)
+    ids_o, bins_o, meta_o = C.bin_gaussians_device(xys, depths, radii, conics, op, H, W, bw, cap)
+    assert meta_o.tolist() == [m, 1, cap, 0]
+    b = bins_o.long()
+    assert int((b[:, 1] - b[:, 0]).sum()) == cap
+    full, part = bins.long(), bins_o.long()
+    for t in torch.randint(0, bins.shape[0], (64,)).tolist():  # every truncated tile list is a PREFIX of the full one
+        n_part = int(part[t, 1] - part[t, 0])
+        assert n_part <= int(full[t, 1] - full[t, 0])
+        assert torch.equal(ids_o[part[t, 0]:part[t, 1]], ids[full[t, 0]:full[t, 0] + n_part])
+
+
+def test_own_radix_sort_64bit_keys_random_and_ties():
+    """gsr_sort_intersects (hand-written LSD radix sort, 6 passes over 45 key bits) == torch.sort(stable)."""
+    from rasterizer import cuda as C
+
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for m, tiles in ((1, 3), (31, 2), (4096, 100), (4097, 8160), (1_000_003, 32400)):
+        tile = torch.randint(0, tiles, (m,), generator=g, device="cuda", dtype=torch.int64)
+        depth = torch.randint(0, 2**31 - 1, (m,), generator=g, device="cuda", dtype=torch.int64)
+        depth[::3] = depth[0]  # many exact ties
+        keys = (tile << 32) | depth
+        vals = torch.arange(m, device="cuda", dtype=torch.int32)
+        ks, vs = C.sort_intersects(keys, vals, tiles)
+        ks_t, order = torch.sort(keys, stable=True)
+        assert torch.equal(ks, ks_t) and torch.equal(vs.long(), order), (m, tiles)
+
+
+def test_own_scan_matches_torch_cumsum():
+    import rasterizer
+
+    g = torch.Generator(device="cuda").manual_seed(2)
+    for n in (1, 255, 4096, 4097, 1_000_001):
+        x = torch.randint(0, 50, (n,), generator=g, device="cuda", dtype=torch.int32)
+        total, cum = rasterizer.compute_cumulative_intersects(x)
+        ref = torch.cumsum(x, 0, dtype=torch.int32)
+        assert torch.equal(cum, ref) and total == int(ref[-1])
+
+
+def test_async_binning_mode_matches_sync_and_reports_overflow():
+    import rasterizer
+    from rasterizer import binning
+    from rasterizer.synthetic import make_scene
+
+    scene = make_scene(30_000, 320, 200, 0.01, 0.08, margin=1.1, seed=11)
+    s, (cov3d, xys, depths, radii, conics, comp, nth) = _projected(scene)
+    H, W, bw = s["img_height"], s["img_width"], s["block_width"]
+    colors = torch.rand(xys.shape[0], 3, device="cuda")
+    opac = s["opacities"].reshape(-1, 1).contiguous()
+
+    def render(o):
+        return rasterizer.rasterize_gaussians(xys.clone(), depths, radii, conics, nth, colors, o, H, W, bw,
+                                              background=s["background"], return_alpha=True)
+
+    binning.reset()
+    rasterizer.set_binning_mode("sync")
+    img_s, a_s = render(opac)
+    rasterizer.set_binning_mode("async")
+    try:
+        img_1, _ = render(opac)  # first call of the signature: synchronous, learns the capacity
+        img_2, a_2 = render(opac)  # asynchronous
+        binning.check()
+        assert torch.equal(img_1, img_s) and torch.equal(img_2, img_s) and torch.equal(a_2, a_s)
+        # a scene with far more pairs than the learned capacity (all opacities -> 1: nothing is culled): overflow
+        sig = next(iter(binning._signatures.values()))
+        sig.capacity = max(1, sig.max_seen // 4)
+        render(opac)
+        with pytest.raises(rasterizer.BinningOverflow):
+            binning.check()
+        assert sig.capacity > sig.max_seen  # raised: the repeated call fits
+        img_3, _ = render(opac)
+        binning.check()
+        assert torch.equal(img_3, img_s)
+    finally:
+        rasterizer.set_binning_mode("sync")
+        binning.reset()
