@@ -59,7 +59,7 @@ tight_tiles_kernel(int n, const float2 *__restrict__ xys, const float *__restric
     int x0, y0, x1, y1;
     tile_bbox(ctr.x, ctr.y, (float)r, tiles_x, tiles_y, block_width, x0, y0, x1, y1);
     const CullEllipse e = make_cull_ellipse(conics[3 * (size_t)idx], conics[3 * (size_t)idx + 1],
-                                            conics[3 * (size_t)idx + 2], opacities[idx]);
+                                            conics[3 * (size_t)idx + 2], opacities[idx], (float)(r + block_width));
     if (!e.empty) {
       int cur = 0;
       int64_t depth_id = 0;

@@ -1,24 +1,28 @@
-// binning_device.cu — the tile binning of rasterize_gaussians as ONE asynchronous call with a DEVICE-side pair count.
+// binning_device.cu — the internal tile binning of rasterize_gaussians: per-tile depth-ordered Gaussian lists with
+// exact tile culling, WITHOUT a global sort and without the host ever needing the number of pairs.
 //
-// Same result as gsr_bin_prepare + gsr_bin_emit_sort (binning_fast.cu) — and therefore the same per-tile order as the
-// reference's cumsum -> .item() -> map_gaussian_to_intersects -> torch.sort(int64) -> torch.gather ->
-// get_tile_bin_edges (rasterizer/rasterize.py:106-138, utils.py:106-182), with exact tile culling — but
-//   * the number of (Gaussian, tile) pairs M never travels to the host: every kernel after the scan reads it from device
-//     memory and runs on a grid sized for the caller's CAPACITY; the call neither synchronises nor allocates, so a view
-//     (and a whole training iteration) can be captured in a CUDA graph.  If M exceeds the capacity the pair list is
-//     truncated (the farthest Gaussians are dropped), meta[1] is set and the caller learns it asynchronously;
-//   * both sorts are the hand-written radix sort of radix_sort.cuh (no library sort), the scan is hand-written too;
-//   * the depth keys are produced by the kernel that counts the tiles (one pass over the projected Gaussians).
+// The reference builds the lists by sorting M 64-bit keys (tile << 32 | depth bits) globally: cumsum -> .item() ->
+// map_gaussian_to_intersects -> torch.sort(int64) -> torch.gather -> get_tile_bin_edges (rasterizer/rasterize.py:106-138,
+// utils.py:106-182).  The order that defines is: per tile, depth ascending (IEEE bits of the positive depth), ties in
+// Gaussian-index order.  The tile part of the key only PARTITIONS the pairs; only the order INSIDE a tile needs a
+// comparison sort, and a tile holds a few hundred pairs.  So (a counting sort by tile + small independent sorts):
 //
-//   prep_kernel        per Gaussian: depth key (IEEE bits of the positive depth; culled -> 0xffffffff), id,
-//                      number of reachable tiles + 64-bit mask of them (tile_cull.cuh)
-//   rs::sort_pairs     Gaussians by depth, 32 bits = 4 passes (stable: ties stay in index order, like the reference's
-//                      stable 64-bit sort)
-//   perm scan          cum[j] = sum_{i<=j} counts[perm[i]]: tile sums -> one-block scan of the sums (+ M, overflow flag)
-//                      -> in-tile scans
-//   emit_kernel        (tile id, Gaussian id) pairs in depth order, clipped to the capacity
-//   rs::sort_pairs     pairs by tile id, ceil(log2 T) bits = 2 passes for T <= 65536, count read from the device
-//   bin_edges_kernel   tile_bins from the sorted tile ids, count read from the device
+//   bin_count_kernel   per Gaussian: the tiles of its bounding box that can be reached with alpha >= 1/255 (exact tile
+//                      culling, tile_cull.cuh) as a count and a 64-bit mask; one RED.ADD per kept (Gaussian, tile) pair
+//                      into tile_count[tile]
+//   tile_scan_kernel   one block: exclusive scan over the T tiles -> tile_bins [T,2] (clipped to the pair capacity),
+//                      per-tile fill cursors, meta = {M, overflow, min(M, capacity)}
+//   bin_fill_kernel    per Gaussian: slot = atomicAdd(cursor[tile]) for each kept tile; writes the 64-bit key
+//                      (depth bits << 32 | Gaussian id) — unordered inside the tile's segment
+//   tile_sort_kernel   one CTA per tile: bitonic sort of the segment's keys in shared memory (<= 4096 pairs), the low
+//                      words (Gaussian ids) go to gaussian_ids_sorted; longer tiles: stable LSD radix sort of the
+//                      segment in global memory by one warp (slow path, keeps the call correct for any scene)
+//
+// Keys are unique (the id is part of the key), so the result is deterministic and identical to the reference's order
+// although the fill order is not.  No kernel's grid depends on M: the call neither synchronises nor allocates and can
+// be captured in a CUDA graph; if M exceeds the caller's capacity, meta[1] is set (the lists are truncated).
+// Compared with round 1 (depth sort of N + emit + stable sort of M pairs by tile with cub::DeviceRadixSort + bin edges)
+// this moves 12 M bytes once instead of ~50 M and drops both library sorts.
 #include "common.cuh"
 #include "radix_sort.cuh"
 #include "tile_cull.cuh"
@@ -27,117 +31,276 @@ namespace gsr {
 namespace {
 
 constexpr int BD_THREADS = 256;
+constexpr int SORT_SMEM_MAX = 4096;  // pairs a CTA sorts in shared memory (32 KB of 64-bit keys)
+typedef unsigned long long u64;
+
+// tiles kept for Gaussian g: calls f(tile_id) for each; returns the count.  `mask` caches the decision for boxes of
+// at most 64 tiles (bit k = k-th tile of the bounding box, row-major).
+template <typename F>
+__device__ __forceinline__ int for_each_kept_tile(float2 ctr, int r, float ca, float cb, float cc, float opac, int tiles_x,
+                                                  int tiles_y, int block_width, u64 &mask, bool have_mask, F f) {
+  int x0, y0, x1, y1;
+  tile_bbox(ctr.x, ctr.y, (float)r, tiles_x, tiles_y, block_width, x0, y0, x1, y1);
+  const int bw_tiles = x1 - x0, area = bw_tiles * (y1 - y0);
+  if (area <= 0) return 0;
+  int count = 0;
+  if (have_mask && area <= 64) {
+    u64 m = mask;
+    while (m) {
+      const int k = __ffsll((long long)m) - 1;
+      m &= m - 1;
+      f((y0 + k / bw_tiles) * tiles_x + x0 + k % bw_tiles);
+      ++count;
+    }
+    return count;
+  }
+  const CullEllipse e = make_cull_ellipse(ca, cb, cc, opac, (float)(r + block_width));
+  if (e.empty) return 0;
+  u64 mk = 0ull;
+  for (int i = y0; i < y1; ++i) {
+    int j0, j1;
+    cull_row_range(e, ctr.x, ctr.y, i, x0, x1, block_width, j0, j1);
+    for (int j = j0; j < j1; ++j) f(i * tiles_x + j);
+    const int cnt = j1 - j0;
+    if (cnt > 0 && area <= 64) mk |= ((cnt >= 64) ? ~0ull : ((1ull << cnt) - 1ull)) << ((i - y0) * bw_tiles + (j0 - x0));
+    count += cnt;
+  }
+  mask = mk;
+  return count;
+}
 
 __global__ void __launch_bounds__(BD_THREADS)
-prep_kernel(int n, const float2 *__restrict__ xys, const float *__restrict__ depths, const int *__restrict__ radii,
-            const float *__restrict__ conics, const float *__restrict__ opacities, int tiles_x, int tiles_y,
-            int block_width, unsigned *__restrict__ keys, int *__restrict__ ids, int *__restrict__ counts,
-            unsigned long long *__restrict__ masks) {
+bin_count_kernel(int n, const float2 *__restrict__ xys, const int *__restrict__ radii, const float *__restrict__ conics,
+                 const float *__restrict__ opacities, int tiles_x, int tiles_y, int block_width,
+                 u64 *__restrict__ masks, unsigned *__restrict__ tile_count) {
   const int g = blockIdx.x * BD_THREADS + threadIdx.x;
   if (g >= n) return;
   const int r = radii[g];
-  int count = 0;
-  unsigned long long mask = 0ull;
-  unsigned key = 0xffffffffu;
-  if (r > 0) {
-    key = (unsigned)__float_as_int(depths[g]);  // the low 32 bits of the reference key (forward.cu:116)
-    const float2 ctr = xys[g];
-    int x0, y0, x1, y1;
-    tile_bbox(ctr.x, ctr.y, (float)r, tiles_x, tiles_y, block_width, x0, y0, x1, y1);
-    const int bw_tiles = x1 - x0, area = bw_tiles * (y1 - y0);
-    const CullEllipse e = make_cull_ellipse(conics[3 * (size_t)g], conics[3 * (size_t)g + 1], conics[3 * (size_t)g + 2],
-                                            opacities[g]);
-    if (e.never_cull) {
-      count = area;
-      mask = ~0ull;
-    } else if (!e.empty) {
-      for (int i = y0; i < y1; ++i) {
-        int j0, j1;
-        cull_row_range(e, ctr.x, ctr.y, i, x0, x1, block_width, j0, j1);
-        const int cnt = j1 - j0;
-        if (cnt > 0 && area <= 64) {  // larger boxes are re-derived row by row when emitting
-          const int k0 = (i - y0) * bw_tiles + (j0 - x0);
-          mask |= ((cnt >= 64) ? ~0ull : ((1ull << cnt) - 1ull)) << k0;
-        }
-        count += cnt;
-      }
-    }
-  }
-  keys[g] = key;
-  ids[g] = g;
-  counts[g] = count;
+  u64 mask = 0ull;
+  if (r > 0)
+    for_each_kept_tile(xys[g], r, conics[3 * (size_t)g], conics[3 * (size_t)g + 1], conics[3 * (size_t)g + 2], opacities[g],
+                       tiles_x, tiles_y, block_width, mask, false, [&](int tile) { atomicAdd(tile_count + tile, 1u); });
   masks[g] = mask;
 }
 
-__global__ void __launch_bounds__(BD_THREADS)
-emit_capped_kernel(int n, const int *__restrict__ perm, const float2 *__restrict__ xys, const int *__restrict__ radii,
-                   const float *__restrict__ conics, const float *__restrict__ opacities, const int *__restrict__ cum,
-                   const unsigned long long *__restrict__ masks, int tiles_x, int tiles_y, int block_width, int capacity,
-                   unsigned *__restrict__ tile_keys, int *__restrict__ gaussian_ids) {
-  const int j = blockIdx.x * BD_THREADS + threadIdx.x;
-  if (j >= n) return;
-  const int end = min(cum[j], capacity);
-  int cur = (j == 0) ? 0 : cum[j - 1];
-  if (cur >= end) return;
-  const int g = perm[j];
-  const float2 ctr = xys[g];
-  int x0, y0, x1, y1;
-  tile_bbox(ctr.x, ctr.y, (float)radii[g], tiles_x, tiles_y, block_width, x0, y0, x1, y1);
-  const int bw_tiles = x1 - x0, area = bw_tiles * (y1 - y0);
-  if (cum[j] - cur == area) {  // every tile of the box is kept
-    for (int i = y0; i < y1; ++i)
-      for (int jx = x0; jx < x1 && cur < end; ++jx) {
-        tile_keys[cur] = (unsigned)(i * tiles_x + jx);
-        gaussian_ids[cur] = g;
-        ++cur;
-      }
-  } else if (area > 64) {  // big box, partially culled: repeat the count kernel's row ranges
-    const CullEllipse e = make_cull_ellipse(conics[3 * (size_t)g], conics[3 * (size_t)g + 1], conics[3 * (size_t)g + 2],
-                                            opacities[g]);
-    for (int i = y0; i < y1; ++i) {
-      int j0, j1;
-      cull_row_range(e, ctr.x, ctr.y, i, x0, x1, block_width, j0, j1);
-      for (int jx = j0; jx < j1 && cur < end; ++jx) {
-        tile_keys[cur] = (unsigned)(i * tiles_x + jx);
-        gaussian_ids[cur] = g;
-        ++cur;
-      }
-    }
-  } else {
-    unsigned long long m = masks[g];
-    while (m && cur < end) {
-      const int k = __ffsll((long long)m) - 1;
-      m &= m - 1;
-      const int i = y0 + k / bw_tiles, jx = x0 + k % bw_tiles;
-      tile_keys[cur] = (unsigned)(i * tiles_x + jx);
-      gaussian_ids[cur] = g;
-      ++cur;
-    }
+// one block of 1024 threads: exclusive scan of tile_count; tile_bins (clipped to capacity), cursors = segment starts
+__global__ void __launch_bounds__(1024)
+tile_scan_kernel(int num_tiles, const unsigned *__restrict__ tile_count, int capacity, int2 *__restrict__ tile_bins,
+                 unsigned *__restrict__ cursors, int *__restrict__ meta) {
+  __shared__ unsigned long long s_warp[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int per = (num_tiles + 1023) / 1024;
+  const int lo = min(num_tiles, tid * per), hi = min(num_tiles, lo + per);
+  unsigned long long sum = 0;
+  for (int i = lo; i < hi; ++i) sum += tile_count[i];
+  unsigned long long inc = sum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned long long up = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += up;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  unsigned long long base = 0, total = 0;
+  for (int w = 0; w < 32; ++w) {
+    const unsigned long long t = s_warp[w];
+    if (w < warp) base += t;
+    total += t;
+  }
+  unsigned long long run = base + inc - sum;
+  const unsigned long long cap = (unsigned long long)capacity;
+  for (int i = lo; i < hi; ++i) {
+    const unsigned long long nxt = run + tile_count[i];
+    const int s = (int)min(run, cap), e = (int)min(nxt, cap);
+    tile_bins[i] = (e > s) ? make_int2(s, e) : make_int2(0, 0);  // empty tiles are (0, 0), like the reference's zeros
+    cursors[i] = (unsigned)min(run, 0xffffffffull);
+    run = nxt;
+  }
+  if (tid == 0) {
+    // the reference keeps M in an int32 too (torch.cumsum(dtype=int32), rasterizer/utils.py:123)
+    meta[0] = (int)min(total, 0x7fffffffull);
+    meta[1] = total > cap ? 1 : 0;
+    meta[2] = (int)min(total, cap);
+    meta[3] = 0;
   }
 }
 
 __global__ void __launch_bounds__(BD_THREADS)
-bin_edges_dev_kernel(int capacity, const int *__restrict__ m_dev, const unsigned *__restrict__ keys,
-                     int2 *__restrict__ tile_bins) {
-  const int m = m_dev ? min(capacity, *m_dev) : capacity;
-  const int idx = blockIdx.x * BD_THREADS + threadIdx.x;
-  if (idx >= m) return;
-  const int cur = (int)keys[idx];
-  if (idx == 0) tile_bins[cur].x = 0;
-  if (idx == m - 1) tile_bins[cur].y = m;
-  if (idx == 0) return;
-  const int prev = (int)keys[idx - 1];
-  if (prev != cur) {
-    tile_bins[prev].y = idx;
-    tile_bins[cur].x = idx;
+bin_fill_kernel(int n, const float2 *__restrict__ xys, const float *__restrict__ depths, const int *__restrict__ radii,
+                const float *__restrict__ conics, const float *__restrict__ opacities, const u64 *__restrict__ masks,
+                int tiles_x, int tiles_y, int block_width, int capacity, unsigned *__restrict__ cursors,
+                u64 *__restrict__ keys) {
+  const int g = blockIdx.x * BD_THREADS + threadIdx.x;
+  if (g >= n) return;
+  const int r = radii[g];
+  if (r <= 0) return;
+  u64 mask = masks[g];
+  // the low 32 bits of the reference key are the IEEE bits of the depth (forward.cu:116); the id breaks ties in index order
+  const u64 key = ((u64)(unsigned)__float_as_int(depths[g]) << 32) | (u64)(unsigned)g;
+  for_each_kept_tile(xys[g], r, conics[3 * (size_t)g], conics[3 * (size_t)g + 1], conics[3 * (size_t)g + 2], opacities[g],
+                     tiles_x, tiles_y, block_width, mask, true, [&](int tile) {
+                       const unsigned pos = atomicAdd(cursors + tile, 1u);
+                       if (pos < (unsigned)capacity) keys[pos] = key;
+                     });
+}
+
+// ---- per-tile sort ---------------------------------------------------------------------------------------------------
+// slow path for tiles with more than SORT_SMEM_MAX pairs: stable LSD radix sort (8-bit digits) of n keys between two
+// global buffers, ONE warp scattering in order (the other warps only help with the histogram).  Only the bits that can
+// differ are sorted: the id bits [0, id_bits) and the depth bits [32, 64).
+__device__ void long_tile_radix_pass(const u64 *src, u64 *dst, int n, int shift, unsigned *s_hist /*[256]*/) {
+  const unsigned full = 0xffffffffu;
+  const int tid = threadIdx.x, lane = tid & 31;
+  for (int i = tid; i < 256; i += BD_THREADS) s_hist[i] = 0u;
+  __syncthreads();
+  for (int i = tid; i < n; i += BD_THREADS) atomicAdd(&s_hist[(unsigned)(src[i] >> shift) & 255u], 1u);
+  __syncthreads();
+  if (tid < 32) {
+    unsigned carry = 0;  // exclusive scan of the 256 counters
+    for (int c = 0; c < 256; c += 32) {
+      const unsigned v = s_hist[c + lane];
+      unsigned inc = v;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const unsigned up = __shfl_up_sync(full, inc, d);
+        if (lane >= d) inc += up;
+      }
+      s_hist[c + lane] = carry + inc - v;
+      carry += __shfl_sync(full, inc, 31);
+    }
+    __syncwarp();
+    const unsigned lt = (1u << lane) - 1u;
+    for (int base = 0; base < n; base += 32) {  // in order => stable
+      const int i = base + lane;
+      const bool valid = i < n;
+      u64 k = 0;
+      unsigned d = 0xffffffffu;
+      if (valid) {
+        k = src[i];
+        d = (unsigned)(k >> shift) & 255u;
+      }
+      const unsigned peers = __match_any_sync(full, d);
+      const unsigned rnk = __popc(peers & lt);
+      unsigned start = 0;
+      if (valid) start = s_hist[d];
+      __syncwarp();
+      if (valid) {
+        dst[start + rnk] = k;
+        if (rnk == 0) s_hist[d] = start + __popc(peers);
+      }
+      __syncwarp();
+    }
   }
+  __threadfence_block();
+  __syncthreads();
+}
+
+__device__ void long_tile_radix_sort(u64 *a, u64 *b, int n, int id_bits, unsigned *s_hist, int *ids_out) {
+  u64 *src = a, *dst = b;
+  for (int shift = 0; shift < id_bits; shift += 8) {
+    long_tile_radix_pass(src, dst, n, shift, s_hist);
+    u64 *t = src; src = dst; dst = t;
+  }
+  for (int shift = 32; shift < 64; shift += 8) {
+    long_tile_radix_pass(src, dst, n, shift, s_hist);
+    u64 *t = src; src = dst; dst = t;
+  }
+  for (int i = threadIdx.x; i < n; i += BD_THREADS) ids_out[i] = (int)(unsigned)src[i];
+}
+
+__global__ void __launch_bounds__(BD_THREADS)
+tile_sort_kernel(const int2 *__restrict__ tile_bins, u64 *__restrict__ keys, u64 *__restrict__ keys_tmp, int id_bits,
+                 int *__restrict__ ids_out) {
+  __shared__ u64 s_keys[SORT_SMEM_MAX];
+  __shared__ unsigned s_hist[256];
+  const int2 range = tile_bins[blockIdx.x];
+  const int n = range.y - range.x, tid = threadIdx.x;
+  if (n <= 0) return;
+  u64 *seg = keys + range.x;
+  if (n > SORT_SMEM_MAX) {
+    long_tile_radix_sort(seg, keys_tmp + range.x, n, id_bits, s_hist, ids_out + range.x);
+    return;
+  }
+  int P = 32;
+  while (P < n) P <<= 1;
+  for (int i = tid; i < P; i += BD_THREADS) s_keys[i] = i < n ? seg[i] : ~0ull;
+  __syncthreads();
+  for (int k = 2; k <= P; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = tid; t < (P >> 1); t += BD_THREADS) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int p = i | j;
+        const u64 x = s_keys[i], y = s_keys[p];
+        const bool up = (i & k) == 0;
+        if ((x > y) == up) {
+          s_keys[i] = y;
+          s_keys[p] = x;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = tid; i < n; i += BD_THREADS) ids_out[range.x + i] = (int)(unsigned)s_keys[i];
 }
 
 inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
-inline int bits_for_tiles(int n) {
+inline int bits_for(long long n) {
   int bits = 1;
-  while ((1ll << bits) < (long long)n) ++bits;
+  while ((1ll << bits) < n) ++bits;
   return bits;
+}
+
+struct BinLayout {  // carved from the caller's workspace
+  u64 *masks, *keys, *keys_tmp;
+  unsigned *tile_count, *cursors;
+};
+
+inline size_t layout_bytes(int num_points, int capacity, int num_tiles) {
+  const size_t n = num_points > 0 ? num_points : 1, c = capacity > 0 ? capacity : 1, t = num_tiles > 0 ? num_tiles : 1;
+  return al256(8 * n) + 2 * al256(8 * c) + 2 * al256(4 * t) + 256;
+}
+
+inline BinLayout carve(void *workspace, int num_points, int capacity, int num_tiles) {
+  const size_t n = num_points > 0 ? num_points : 1, c = capacity > 0 ? capacity : 1, t = num_tiles > 0 ? num_tiles : 1;
+  char *ws = (char *)workspace;
+  BinLayout L;
+  L.masks = (u64 *)ws;           ws += al256(8 * n);
+  L.keys = (u64 *)ws;            ws += al256(8 * c);
+  L.keys_tmp = (u64 *)ws;        ws += al256(8 * c);
+  L.tile_count = (unsigned *)ws; ws += al256(4 * t);
+  L.cursors = (unsigned *)ws;
+  return L;
+}
+
+// count + scan: tile_bins / cursors / meta for `capacity`
+int run_count(int num_points, const float *xys, const int32_t *radii, const float *conics, const float *opacities,
+              int tiles_x, int tiles_y, unsigned block_width, int capacity, const BinLayout &L, int32_t *tile_bins,
+              int32_t *meta, cudaStream_t st) {
+  const int num_tiles = tiles_x * tiles_y;
+  GSR_CUDA(cudaMemsetAsync(L.tile_count, 0, sizeof(unsigned) * (size_t)num_tiles, st));
+  if (num_points > 0) {
+    bin_count_kernel<<<cdiv(num_points, BD_THREADS), BD_THREADS, 0, st>>>(
+        num_points, reinterpret_cast<const float2 *>(xys), radii, conics, opacities, tiles_x, tiles_y, (int)block_width,
+        L.masks, L.tile_count);
+    GSR_CHECK_LAUNCH("bin_count_kernel");
+  }
+  tile_scan_kernel<<<1, 1024, 0, st>>>(num_tiles, L.tile_count, capacity, reinterpret_cast<int2 *>(tile_bins), L.cursors, meta);
+  GSR_CHECK_LAUNCH("tile_scan_kernel");
+  return GSR_OK;
+}
+
+int run_fill_sort(int num_points, const float *xys, const float *depths, const int32_t *radii, const float *conics,
+                  const float *opacities, int tiles_x, int tiles_y, unsigned block_width, int capacity, const BinLayout &L,
+                  const int32_t *tile_bins, int32_t *gaussian_ids_sorted, cudaStream_t st) {
+  if (num_points <= 0 || capacity <= 0) return GSR_OK;
+  bin_fill_kernel<<<cdiv(num_points, BD_THREADS), BD_THREADS, 0, st>>>(
+      num_points, reinterpret_cast<const float2 *>(xys), depths, radii, conics, opacities, L.masks, tiles_x, tiles_y,
+      (int)block_width, capacity, L.cursors, L.keys);
+  GSR_CHECK_LAUNCH("bin_fill_kernel");
+  tile_sort_kernel<<<tiles_x * tiles_y, BD_THREADS, 0, st>>>(reinterpret_cast<const int2 *>(tile_bins), L.keys, L.keys_tmp,
+                                                             bits_for(num_points), gaussian_ids_sorted);
+  GSR_CHECK_LAUNCH("tile_sort_kernel");
+  return GSR_OK;
 }
 
 }  // namespace
@@ -145,15 +308,14 @@ inline int bits_for_tiles(int n) {
 
 extern "C" {
 
-// ---- asynchronous form: device-side M, capacity-bounded pair buffers ------------------------------------------------
-GSR_API size_t gsr_bin_device_workspace_bytes(int num_points, int capacity) {
+GSR_API size_t gsr_bin_device_workspace_bytes(int num_points, int capacity, unsigned img_height, unsigned img_width,
+                                              unsigned block_width) {
   using namespace gsr;
-  const size_t n = num_points > 0 ? num_points : 1, c = capacity > 0 ? capacity : 1;
-  // per Gaussian: depth keys a/b, ids a/b, counts, cum (4 B each) + masks (8 B); per pair: tile keys a/b, ids tmp (4 B each)
-  return 6 * al256(4 * n) + al256(8 * n) + al256(rs::scan_workspace_bytes((int)n)) + 3 * al256(4 * c) +
-         al256(rs::workspace_bytes((int)(n > c ? n : c))) + 256;
+  if (block_width < 2) block_width = 2;
+  return layout_bytes(num_points, capacity, (int)(cdiv(img_width, block_width) * cdiv(img_height, block_width)));
 }
 
+// Whole binning, asynchronous: M stays on the device (meta), buffers hold `capacity` pairs.
 GSR_API int gsr_bin_gaussians_device(int num_points, const float *xys, const float *depths, const int32_t *radii,
                                      const float *conics, const float *opacities, unsigned img_height,
                                      unsigned img_width, unsigned block_width, int capacity,
@@ -163,169 +325,86 @@ GSR_API int gsr_bin_gaussians_device(int num_points, const float *xys, const flo
   GSR_REQUIRE(num_points >= 0 && capacity >= 0, GSR_ERR_INVALID_ARGUMENT, "bin_gaussians_device: negative size");
   GSR_REQUIRE(block_width > 1 && block_width <= 16, GSR_ERR_INVALID_ARGUMENT,
               "block_width must be between 2 and 16 (got %u)", block_width);
-  GSR_REQUIRE(tile_bins && meta, GSR_ERR_INVALID_ARGUMENT, "bin_gaussians_device: null pointer");
-  cudaStream_t st = (cudaStream_t)stream;
-  const int tiles_x = cdiv(img_width, block_width), tiles_y = cdiv(img_height, block_width);
-  const int num_tiles = tiles_x * tiles_y;
-  GSR_CUDA(cudaMemsetAsync(tile_bins, 0, sizeof(int32_t) * 2 * (size_t)num_tiles, st));
-  if (num_points == 0 || capacity == 0) {
-    GSR_CUDA(cudaMemsetAsync(meta, 0, 4 * sizeof(int32_t), st));
-    if (meta_host_pinned) GSR_CUDA(cudaMemcpyAsync(meta_host_pinned, meta, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    return GSR_OK;
-  }
-  GSR_REQUIRE(xys && depths && radii && conics && opacities && gaussian_ids_sorted && workspace,
-              GSR_ERR_INVALID_ARGUMENT, "bin_gaussians_device: null pointer");
+  GSR_REQUIRE(img_height > 0 && img_width > 0, GSR_ERR_INVALID_ARGUMENT, "bin_gaussians_device: empty image");
+  GSR_REQUIRE(tile_bins && meta && workspace, GSR_ERR_INVALID_ARGUMENT, "bin_gaussians_device: null pointer");
+  GSR_REQUIRE(num_points == 0 || (xys && depths && radii && conics && opacities), GSR_ERR_INVALID_ARGUMENT,
+              "bin_gaussians_device: null pointer");
+  GSR_REQUIRE(capacity == 0 || gaussian_ids_sorted, GSR_ERR_INVALID_ARGUMENT, "bin_gaussians_device: null pointer");
   GSR_REQUIRE((uintptr_t)xys % 8 == 0 && (uintptr_t)workspace % 16 == 0 && (uintptr_t)tile_bins % 8 == 0,
               GSR_ERR_INVALID_ARGUMENT, "bin_gaussians_device: misaligned pointer");
-  GSR_REQUIRE(workspace_bytes >= gsr_bin_device_workspace_bytes(num_points, capacity), GSR_ERR_WORKSPACE,
+  const int tiles_x = cdiv(img_width, block_width), tiles_y = cdiv(img_height, block_width);
+  GSR_REQUIRE(workspace_bytes >= layout_bytes(num_points, capacity, tiles_x * tiles_y), GSR_ERR_WORKSPACE,
               "bin_gaussians_device: workspace %zu < %zu bytes", workspace_bytes,
-              gsr_bin_device_workspace_bytes(num_points, capacity));
-  const size_t n = num_points, c = capacity;
-  char *ws = (char *)workspace;
-  unsigned *dkeys_a = (unsigned *)ws; ws += al256(4 * n);
-  unsigned *dkeys_b = (unsigned *)ws; ws += al256(4 * n);
-  int *ids_a = (int *)ws;             ws += al256(4 * n);
-  int *ids_b = (int *)ws;             ws += al256(4 * n);
-  int *counts = (int *)ws;            ws += al256(4 * n);
-  int *cum = (int *)ws;               ws += al256(4 * n);
-  unsigned long long *masks = (unsigned long long *)ws; ws += al256(8 * n);
-  void *scan_ws = ws;                 ws += al256(rs::scan_workspace_bytes(num_points));
-  unsigned *tkeys_a = (unsigned *)ws; ws += al256(4 * c);
-  unsigned *tkeys_b = (unsigned *)ws; ws += al256(4 * c);
-  int *pids_tmp = (int *)ws;          ws += al256(4 * c);
-  void *sort_ws = ws;
-
-  const unsigned grid_n = cdiv(num_points, BD_THREADS);
-  prep_kernel<<<grid_n, BD_THREADS, 0, st>>>(num_points, reinterpret_cast<const float2 *>(xys), depths, radii, conics,
-                                             opacities, tiles_x, tiles_y, (int)block_width, dkeys_a, ids_a, counts, masks);
-  GSR_CHECK_LAUNCH("prep_kernel");
-  // Gaussians by depth (32 bits = 4 passes: back in the A buffers)
-  int rc = rs::sort_pairs<unsigned, int>(dkeys_a, ids_a, dkeys_b, ids_b, num_points, nullptr, 0, 32, sort_ws, st);
-  if (rc != GSR_OK) return rc;
-  const int *perm = (rs::num_passes(0, 32) & 1) ? ids_b : ids_a;
-  rc = rs::inclusive_scan(num_points, perm, counts, cum, capacity, meta, scan_ws, st);
+              layout_bytes(num_points, capacity, tiles_x * tiles_y));
+  cudaStream_t st = (cudaStream_t)stream;
+  const BinLayout L = carve(workspace, num_points, capacity, tiles_x * tiles_y);
+  int rc = run_count(num_points, xys, radii, conics, opacities, tiles_x, tiles_y, block_width, capacity, L, tile_bins, meta, st);
   if (rc != GSR_OK) return rc;
   if (meta_host_pinned)
     GSR_CUDA(cudaMemcpyAsync(meta_host_pinned, meta, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  // pairs by tile id: the result must END in gaussian_ids_sorted
-  const int tile_bits = bits_for_tiles(num_tiles);
-  const bool odd = rs::num_passes(0, tile_bits) & 1;
-  int *pids_first = odd ? pids_tmp : gaussian_ids_sorted;  // the buffer the emit kernel writes
-  int *pids_second = odd ? gaussian_ids_sorted : pids_tmp;
-  emit_capped_kernel<<<grid_n, BD_THREADS, 0, st>>>(num_points, perm, reinterpret_cast<const float2 *>(xys), radii, conics,
-                                                    opacities, cum, masks, tiles_x, tiles_y, (int)block_width, capacity,
-                                                    tkeys_a, pids_first);
-  GSR_CHECK_LAUNCH("emit_capped_kernel");
-  rc = rs::sort_pairs<unsigned, int>(tkeys_a, pids_first, tkeys_b, pids_second, capacity, meta + 2, 0, tile_bits, sort_ws, st);
+  return run_fill_sort(num_points, xys, depths, radii, conics, opacities, tiles_x, tiles_y, block_width, capacity, L, tile_bins,
+                       gaussian_ids_sorted, st);
+}
+
+// Two-call form with a host-visible M: gsr_bin_count (capacity "unbounded": tile_bins are exact), the caller reads
+// meta_host_pinned[0] = M after synchronising, allocates gaussian_ids_sorted [M] and a workspace for capacity M, and
+// calls gsr_bin_fill_sort with the SAME masks / cursors (kept in the first workspace: pass it as `count_workspace`).
+GSR_API size_t gsr_bin_count_workspace_bytes(int num_points, unsigned img_height, unsigned img_width, unsigned block_width) {
+  return gsr_bin_device_workspace_bytes(num_points, 1, img_height, img_width, block_width);
+}
+
+GSR_API int gsr_bin_count(int num_points, const float *xys, const int32_t *radii, const float *conics,
+                          const float *opacities, unsigned img_height, unsigned img_width, unsigned block_width,
+                          int32_t *tile_bins, int32_t *meta, int32_t *meta_host_pinned, void *count_workspace,
+                          size_t workspace_bytes, void *stream) {
+  using namespace gsr;
+  GSR_REQUIRE(num_points >= 0, GSR_ERR_INVALID_ARGUMENT, "bin_count: num_points < 0");
+  GSR_REQUIRE(block_width > 1 && block_width <= 16, GSR_ERR_INVALID_ARGUMENT,
+              "block_width must be between 2 and 16 (got %u)", block_width);
+  GSR_REQUIRE(img_height > 0 && img_width > 0, GSR_ERR_INVALID_ARGUMENT, "bin_count: empty image");
+  GSR_REQUIRE(tile_bins && meta && count_workspace, GSR_ERR_INVALID_ARGUMENT, "bin_count: null pointer");
+  GSR_REQUIRE(num_points == 0 || (xys && radii && conics && opacities), GSR_ERR_INVALID_ARGUMENT, "bin_count: null pointer");
+  GSR_REQUIRE((uintptr_t)xys % 8 == 0 && (uintptr_t)count_workspace % 16 == 0 && (uintptr_t)tile_bins % 8 == 0,
+              GSR_ERR_INVALID_ARGUMENT, "bin_count: misaligned pointer");
+  const int tiles_x = cdiv(img_width, block_width), tiles_y = cdiv(img_height, block_width);
+  GSR_REQUIRE(workspace_bytes >= layout_bytes(num_points, 1, tiles_x * tiles_y), GSR_ERR_WORKSPACE,
+              "bin_count: workspace %zu < %zu bytes", workspace_bytes, layout_bytes(num_points, 1, tiles_x * tiles_y));
+  cudaStream_t st = (cudaStream_t)stream;
+  const BinLayout L = carve(count_workspace, num_points, 1, tiles_x * tiles_y);
+  const int rc = run_count(num_points, xys, radii, conics, opacities, tiles_x, tiles_y, block_width, 0x7fffffff, L, tile_bins,
+                           meta, st);
   if (rc != GSR_OK) return rc;
-  const unsigned *sorted_keys = odd ? tkeys_b : tkeys_a;
-  bin_edges_dev_kernel<<<cdiv(capacity, BD_THREADS), BD_THREADS, 0, st>>>(capacity, meta + 2, sorted_keys,
-                                                                          reinterpret_cast<int2 *>(tile_bins));
-  GSR_CHECK_LAUNCH("bin_edges_dev_kernel");
+  if (meta_host_pinned)
+    GSR_CUDA(cudaMemcpyAsync(meta_host_pinned, meta, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   return GSR_OK;
 }
 
-// ---- two-call form with a host-visible M (the caller synchronises between the calls and sizes the outputs exactly) ----
-GSR_API size_t gsr_bin_prepare_workspace_bytes(int num_points) {
-  using namespace gsr;
-  const size_t n = num_points > 0 ? num_points : 1;
-  // depth keys a/b, ids b, counts + scan + sort workspaces + meta
-  return 4 * al256(4 * n) + al256(rs::scan_workspace_bytes((int)n)) + al256(rs::workspace_bytes((int)n)) + 512;
+GSR_API size_t gsr_bin_fill_workspace_bytes(int num_intersects) {
+  const size_t c = num_intersects > 0 ? num_intersects : 1;
+  return 2 * ((8 * c + 255) & ~(size_t)255) + 256;  // keys + keys_tmp
 }
 
-GSR_API int gsr_bin_prepare(int num_points, const float *xys, const float *depths, const int32_t *radii,
-                            const float *conics, const float *opacities, unsigned img_height,
-                            unsigned img_width, unsigned block_width, int32_t *perm, int32_t *cum_tiles,
-                            uint64_t *masks, int32_t *total_host_pinned, void *workspace, size_t workspace_bytes,
-                            void *stream) {
+GSR_API int gsr_bin_fill_sort(int num_points, int num_intersects, const float *xys, const float *depths,
+                              const int32_t *radii, const float *conics, const float *opacities,
+                              unsigned img_height, unsigned img_width, unsigned block_width, const int32_t *tile_bins,
+                              void *count_workspace, int32_t *gaussian_ids_sorted, void *fill_workspace,
+                              size_t fill_workspace_bytes, void *stream) {
   using namespace gsr;
-  GSR_REQUIRE(num_points >= 0, GSR_ERR_INVALID_ARGUMENT, "bin_prepare: num_points < 0");
+  GSR_REQUIRE(num_points >= 0 && num_intersects >= 0, GSR_ERR_INVALID_ARGUMENT, "bin_fill_sort: negative size");
   GSR_REQUIRE(block_width > 1 && block_width <= 16, GSR_ERR_INVALID_ARGUMENT,
               "block_width must be between 2 and 16 (got %u)", block_width);
-  if (num_points == 0) {
-    if (total_host_pinned) *total_host_pinned = 0;
-    return GSR_OK;
-  }
-  GSR_REQUIRE(xys && depths && radii && conics && opacities && perm && cum_tiles && masks && workspace,
-              GSR_ERR_INVALID_ARGUMENT, "bin_prepare: null pointer");
-  GSR_REQUIRE((uintptr_t)xys % 8 == 0 && (uintptr_t)masks % 8 == 0 && (uintptr_t)workspace % 16 == 0,
-              GSR_ERR_INVALID_ARGUMENT, "bin_prepare: misaligned pointer");
-  GSR_REQUIRE(workspace_bytes >= gsr_bin_prepare_workspace_bytes(num_points), GSR_ERR_WORKSPACE,
-              "bin_prepare: workspace %zu < %zu bytes", workspace_bytes, gsr_bin_prepare_workspace_bytes(num_points));
-  cudaStream_t st = (cudaStream_t)stream;
-  const size_t n = num_points;
-  char *ws = (char *)workspace;
-  unsigned *dkeys_a = (unsigned *)ws; ws += al256(4 * n);
-  unsigned *dkeys_b = (unsigned *)ws; ws += al256(4 * n);
-  int *ids_b = (int *)ws;             ws += al256(4 * n);
-  int *counts = (int *)ws;            ws += al256(4 * n);
-  void *scan_ws = ws;                 ws += al256(rs::scan_workspace_bytes(num_points));
-  int *meta = (int *)ws;              ws += 256;
-  void *sort_ws = ws;
-  const int tiles_x = cdiv(img_width, block_width), tiles_y = cdiv(img_height, block_width);
-  static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "mask type");
-  prep_kernel<<<cdiv(num_points, BD_THREADS), BD_THREADS, 0, st>>>(
-      num_points, reinterpret_cast<const float2 *>(xys), depths, radii, conics, opacities, tiles_x, tiles_y,
-      (int)block_width, dkeys_a, perm, counts, reinterpret_cast<unsigned long long *>(masks));
-  GSR_CHECK_LAUNCH("prep_kernel");
-  // 4 passes: the sorted ids end in the A buffer = the caller's `perm`
-  int rc = rs::sort_pairs<unsigned, int>(dkeys_a, perm, dkeys_b, ids_b, num_points, nullptr, 0, 32, sort_ws, st);
-  if (rc != GSR_OK) return rc;
-  static_assert(((32 + 7) / 8) % 2 == 0, "depth sort must end in the A buffers");
-  rc = rs::inclusive_scan(num_points, perm, counts, cum_tiles, 0x7fffffff, meta, scan_ws, st);
-  if (rc != GSR_OK) return rc;
-  if (total_host_pinned)
-    GSR_CUDA(cudaMemcpyAsync(total_host_pinned, meta, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  return GSR_OK;
-}
-
-GSR_API size_t gsr_bin_emit_workspace_bytes(int num_intersects) {
-  using namespace gsr;
-  const size_t m = num_intersects > 0 ? num_intersects : 1;
-  return 3 * al256(4 * m) + al256(rs::workspace_bytes((int)m)) + 256;  // tile keys a/b, ids tmp + sort workspace
-}
-
-GSR_API int gsr_bin_emit_sort(int num_points, int num_intersects, const float *xys, const int32_t *radii,
-                              const float *conics, const float *opacities, const int32_t *perm,
-                              const int32_t *cum_tiles, const uint64_t *masks,
-                              unsigned img_height, unsigned img_width, unsigned block_width,
-                              int32_t *gaussian_ids_sorted, int32_t *tile_bins, void *workspace,
-                              size_t workspace_bytes, void *stream) {
-  using namespace gsr;
-  GSR_REQUIRE(num_points >= 0 && num_intersects >= 0, GSR_ERR_INVALID_ARGUMENT, "bin_emit_sort: negative size");
-  GSR_REQUIRE(block_width > 1 && block_width <= 16, GSR_ERR_INVALID_ARGUMENT,
-              "block_width must be between 2 and 16 (got %u)", block_width);
-  cudaStream_t st = (cudaStream_t)stream;
-  const int tiles_x = cdiv(img_width, block_width), tiles_y = cdiv(img_height, block_width);
-  const int num_tiles = tiles_x * tiles_y;
-  GSR_REQUIRE(tile_bins, GSR_ERR_INVALID_ARGUMENT, "bin_emit_sort: null pointer");
-  GSR_CUDA(cudaMemsetAsync(tile_bins, 0, sizeof(int32_t) * 2 * (size_t)num_tiles, st));
   if (num_points == 0 || num_intersects == 0) return GSR_OK;
-  GSR_REQUIRE(xys && radii && conics && opacities && perm && cum_tiles && masks && gaussian_ids_sorted && workspace,
-              GSR_ERR_INVALID_ARGUMENT, "bin_emit_sort: null pointer");
-  GSR_REQUIRE(workspace_bytes >= gsr_bin_emit_workspace_bytes(num_intersects), GSR_ERR_WORKSPACE,
-              "bin_emit_sort: workspace %zu < %zu bytes", workspace_bytes, gsr_bin_emit_workspace_bytes(num_intersects));
-  const size_t m = num_intersects;
-  char *ws = (char *)workspace;
-  unsigned *tkeys_a = (unsigned *)ws; ws += al256(4 * m);
-  unsigned *tkeys_b = (unsigned *)ws; ws += al256(4 * m);
-  int *pids_tmp = (int *)ws;          ws += al256(4 * m);
-  void *sort_ws = ws;
-  const int tile_bits = bits_for_tiles(num_tiles);
-  const bool odd = rs::num_passes(0, tile_bits) & 1;
-  int *pids_first = odd ? pids_tmp : gaussian_ids_sorted;
-  int *pids_second = odd ? gaussian_ids_sorted : pids_tmp;
-  emit_capped_kernel<<<cdiv(num_points, BD_THREADS), BD_THREADS, 0, st>>>(
-      num_points, perm, reinterpret_cast<const float2 *>(xys), radii, conics, opacities, cum_tiles,
-      reinterpret_cast<const unsigned long long *>(masks), tiles_x, tiles_y, (int)block_width, num_intersects, tkeys_a,
-      pids_first);
-  GSR_CHECK_LAUNCH("emit_capped_kernel");
-  int rc = rs::sort_pairs<unsigned, int>(tkeys_a, pids_first, tkeys_b, pids_second, num_intersects, nullptr, 0, tile_bits,
-                                         sort_ws, st);
-  if (rc != GSR_OK) return rc;
-  bin_edges_dev_kernel<<<cdiv(num_intersects, BD_THREADS), BD_THREADS, 0, st>>>(
-      num_intersects, nullptr, odd ? tkeys_b : tkeys_a, reinterpret_cast<int2 *>(tile_bins));
-  GSR_CHECK_LAUNCH("bin_edges_dev_kernel");
-  return GSR_OK;
+  GSR_REQUIRE(xys && depths && radii && conics && opacities && tile_bins && count_workspace && gaussian_ids_sorted &&
+                  fill_workspace,
+              GSR_ERR_INVALID_ARGUMENT, "bin_fill_sort: null pointer");
+  GSR_REQUIRE(fill_workspace_bytes >= gsr_bin_fill_workspace_bytes(num_intersects), GSR_ERR_WORKSPACE,
+              "bin_fill_sort: workspace %zu < %zu bytes", fill_workspace_bytes, gsr_bin_fill_workspace_bytes(num_intersects));
+  GSR_REQUIRE((uintptr_t)fill_workspace % 16 == 0, GSR_ERR_INVALID_ARGUMENT, "bin_fill_sort: misaligned workspace");
+  const int tiles_x = cdiv(img_width, block_width), tiles_y = cdiv(img_height, block_width);
+  BinLayout L = carve(count_workspace, num_points, 1, tiles_x * tiles_y);
+  L.keys = (u64 *)fill_workspace;
+  L.keys_tmp = (u64 *)((char *)fill_workspace + (((size_t)8 * num_intersects + 255) & ~(size_t)255));
+  return run_fill_sort(num_points, xys, depths, radii, conics, opacities, tiles_x, tiles_y, block_width, num_intersects, L,
+                       tile_bins, gaussian_ids_sorted, (cudaStream_t)stream);
 }
 }

@@ -8,7 +8,11 @@
 //     l(dy) = (-b dy - sqrt(a thr - det dy^2)) / a   (convex)      r(dy) = (-b dy + sqrt(a thr - det dy^2)) / a   (concave)
 // whose extrema over the band are attained at the ellipse's leftmost / rightmost point (dy = +- b ext_x / c) clamped into
 // the band, so one row costs two square roots and yields a contiguous range of tiles — instead of one 45-instruction
-// minimisation per tile.  Margins: thr carries +0.1 % + 1e-3, tile rectangles are taken unclipped (both conservative).
+// minimisation per tile.  Margins: thr carries +0.1 % + 1e-3 PLUS a term that scales with the magnitude of the
+// quadratic form's terms at the far end of the bounding box (`extent` pixels): for long thin slanted Gaussians
+// q = a dx^2 + 2 b dx dy + c dy^2 is a difference of terms ~1e5 that cancel to ~10, and the blend kernels / the
+// reference evaluate it in a different order (0.5 (a dx^2 + c dy^2) + b dx dy), so their FP32 rounding differs by up to a
+// few ulp of the LARGEST term; tile rectangles are taken unclipped (conservative as well).
 // Degenerate inputs (non-positive-definite conic, NaN) are never culled.
 #pragma once
 #include "common.cuh"
@@ -21,14 +25,15 @@ struct CullEllipse {
   bool empty;       // opacity < 1/255: no pixel can ever pass the alpha test
 };
 
-__device__ __forceinline__ CullEllipse make_cull_ellipse(float a, float b, float c, float opac) {
+__device__ __forceinline__ CullEllipse make_cull_ellipse(float a, float b, float c, float opac, float extent = 0.f) {
   CullEllipse e;
   e.a = a;
   e.b = b;
   e.det = a * c - b * b;
   e.never_cull = !(a > 0.f && c > 0.f && e.det > 0.f) || !(opac == opac);
   e.empty = !e.never_cull && (255.f * opac < 0.999f);
-  e.thr = 2.f * __logf(255.f * opac) * 1.001f + 1e-3f;
+  // 8 ulp (2^-23 each) of the sum of the absolute terms at distance `extent` in both coordinates
+  e.thr = 2.f * __logf(255.f * opac) * 1.001f + 1e-3f + 9.6e-7f * (a + 2.f * fabsf(b) + c) * extent * extent;
   e.inv_a = 1.f / a;
   const float inv_det = 1.f / e.det;
   e.ext_y = sqrtf(a * e.thr * inv_det);

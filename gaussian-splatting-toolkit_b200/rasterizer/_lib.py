@@ -41,12 +41,12 @@ SIGNATURES = {
     "gsr_map_gaussian_to_intersects": (_i, [_i, _i, _p, _p, _p, _p, _u, _u, _u, _p, _p, _p]),
     "gsr_count_tiles_tight": (_i, [_i, _p, _p, _p, _p, _u, _u, _u, _p, _p]),
     "gsr_map_gaussian_to_intersects_tight": (_i, [_i, _i, _p, _p, _p, _p, _p, _p, _u, _u, _u, _p, _p, _p]),
-    "gsr_bin_prepare_workspace_bytes": (_sz, [_i]),
-    "gsr_bin_prepare": (_i, [_i, _p, _p, _p, _p, _p, _u, _u, _u, _p, _p, _p, _p, _p, _sz, _p]),
-    "gsr_bin_emit_workspace_bytes": (_sz, [_i]),
-    "gsr_bin_emit_sort": (_i, [_i, _i, _p, _p, _p, _p, _p, _p, _p, _u, _u, _u, _p, _p, _p, _sz, _p]),
-    "gsr_bin_device_workspace_bytes": (_sz, [_i, _i]),
+    "gsr_bin_device_workspace_bytes": (_sz, [_i, _i, _u, _u, _u]),
     "gsr_bin_gaussians_device": (_i, [_i, _p, _p, _p, _p, _p, _u, _u, _u, _i, _p, _p, _p, _p, _p, _sz, _p]),
+    "gsr_bin_count_workspace_bytes": (_sz, [_i, _u, _u, _u]),
+    "gsr_bin_count": (_i, [_i, _p, _p, _p, _p, _u, _u, _u, _p, _p, _p, _p, _sz, _p]),
+    "gsr_bin_fill_workspace_bytes": (_sz, [_i]),
+    "gsr_bin_fill_sort": (_i, [_i, _i, _p, _p, _p, _p, _p, _u, _u, _u, _p, _p, _p, _p, _sz, _p]),
     "gsr_sort_workspace_bytes": (_sz, [_i]),
     "gsr_sort_intersects": (_i, [_i, _i, _p, _p, _p, _p, _p, _sz, _p]),
     "gsr_get_tile_bin_edges": (_i, [_i, _p, _i, _p, _p]),

@@ -279,16 +279,16 @@ def _pinned_word(dev_index: int, stream_ptr: int) -> Tensor:
     key = (dev_index, stream_ptr)
     w = _pinned_words.get(key)
     if w is None:
-        w = _pinned_words[key] = torch.zeros(1, dtype=torch.int32).pin_memory()
+        w = _pinned_words[key] = torch.zeros(4, dtype=torch.int32).pin_memory()
     return w
 
 
 def bin_gaussians_fast(xys: Tensor, depths: Tensor, radii: Tensor, conics: Tensor, opacities: Tensor,
                        img_height: int, img_width: int, block_width: int):
-    """Internal binning of rasterize_gaussians: (num_intersects, gaussian_ids_sorted [M] i32, tile_bins [T,2] i32).
-    Two-level sort + exact tile culling (include/gsr_b200.h, gsr_bin_prepare / gsr_bin_emit_sort); the per-tile
-    order is the reference's.  One stream synchronisation to learn M (the reference has the same one:
-    `.item()` at rasterizer/utils.py:124)."""
+    """Internal binning of rasterize_gaussians, synchronous form: (num_intersects, gaussian_ids_sorted [M] i32,
+    tile_bins [T,2] i32) with exactly-sized outputs.  Per-tile counting + per-tile sorts with exact tile culling
+    (include/gsr_b200.h, gsr_bin_count / gsr_bin_fill_sort); the per-tile order is the reference's.  One stream
+    synchronisation to learn M (the reference has the same one: `.item()` at rasterizer/utils.py:124)."""
     _check_input(xys, "xys", torch.float32)
     _check_input(depths, "depths", torch.float32)
     _check_input(radii, "radii", torch.int32)
@@ -296,30 +296,26 @@ def bin_gaussians_fast(xys: Tensor, depths: Tensor, radii: Tensor, conics: Tenso
     _check_input(opacities, "opacities", torch.float32)
     lib = _lib.load()
     n, dev = xys.size(0), xys.device
-    tiles_x = (img_width + block_width - 1) // block_width
-    tiles_y = (img_height + block_width - 1) // block_width
-    perm = torch.empty((n,), dtype=torch.int32, device=dev)
-    cum = torch.empty((n,), dtype=torch.int32, device=dev)
-    masks = torch.empty((n,), dtype=torch.int64, device=dev)
-    ws_bytes = lib.gsr_bin_prepare_workspace_bytes(n)
+    H, W, bw = int(img_height), int(img_width), int(block_width)
+    tiles_x, tiles_y = (W + bw - 1) // bw, (H + bw - 1) // bw
+    ws_bytes = lib.gsr_bin_count_workspace_bytes(n, H, W, bw)
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
     tile_bins = torch.empty((tiles_x * tiles_y, 2), dtype=torch.int32, device=dev)
+    meta = torch.empty((4,), dtype=torch.int32, device=dev)
     with _Guard(xys) as st:
         pin = _pinned_word(dev.index, st.value or 0)
-        _lib.check(lib.gsr_bin_prepare(n, _ptr(xys), _ptr(depths), _ptr(radii), _ptr(conics), _ptr(opacities),
-                                       int(img_height), int(img_width), int(block_width), _ptr(perm), _ptr(cum),
-                                       _ptr(masks), _P(pin.data_ptr()), _ptr(ws), ws_bytes, st), "bin_prepare")
+        _lib.check(lib.gsr_bin_count(n, _ptr(xys), _ptr(radii), _ptr(conics), _ptr(opacities), H, W, bw, _ptr(tile_bins),
+                                     _ptr(meta), _P(pin.data_ptr()), _ptr(ws), ws_bytes, st), "bin_count")
         torch.cuda.current_stream(dev).synchronize()
-        m = int(pin.item())
+        m = int(pin[0].item())
         if m < 1:
             return 0, None, None
         ids_sorted = torch.empty((m,), dtype=torch.int32, device=dev)
-        ws2_bytes = lib.gsr_bin_emit_workspace_bytes(m)
+        ws2_bytes = lib.gsr_bin_fill_workspace_bytes(m)
         ws2 = torch.empty((ws2_bytes,), dtype=torch.uint8, device=dev)
-        _lib.check(lib.gsr_bin_emit_sort(n, m, _ptr(xys), _ptr(radii), _ptr(conics), _ptr(opacities), _ptr(perm),
-                                         _ptr(cum), _ptr(masks),
-                                         int(img_height), int(img_width), int(block_width), _ptr(ids_sorted),
-                                         _ptr(tile_bins), _ptr(ws2), ws2_bytes, st), "bin_emit_sort")
+        _lib.check(lib.gsr_bin_fill_sort(n, m, _ptr(xys), _ptr(depths), _ptr(radii), _ptr(conics), _ptr(opacities), H, W, bw,
+                                         _ptr(tile_bins), _ptr(ws), _ptr(ids_sorted), _ptr(ws2), ws2_bytes, st),
+                   "bin_fill_sort")
     return m, ids_sorted, tile_bins
 
 
@@ -343,7 +339,7 @@ def bin_gaussians_device(xys: Tensor, depths: Tensor, radii: Tensor, conics: Ten
     ids_sorted = torch.empty((max(capacity, 1),), dtype=torch.int32, device=dev)
     tile_bins = torch.empty((tiles_x * tiles_y, 2), dtype=torch.int32, device=dev)
     meta = torch.empty((4,), dtype=torch.int32, device=dev)
-    ws_bytes = lib.gsr_bin_device_workspace_bytes(n, capacity)
+    ws_bytes = lib.gsr_bin_device_workspace_bytes(n, capacity, int(img_height), int(img_width), int(block_width))
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
     with _Guard(xys) as st:
         _lib.check(lib.gsr_bin_gaussians_device(

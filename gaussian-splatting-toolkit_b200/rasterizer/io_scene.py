@@ -39,7 +39,9 @@ def save_checkpoint(checkpoint_dir: str, step: int, params: Dict[str, torch.Tens
                     schedulers: Optional[Dict[str, dict]] = None, save_only_latest_checkpoint: bool = True,
                     extra_pipeline_state: Optional[Dict[str, torch.Tensor]] = None) -> str:
     """trainer.py:443-476.  `optimizers` is a rasterizer.optim.GaussianOptimizers (or anything with a
-    `state_dict()` returning {group: Adam.state_dict()}), or None."""
+    `state_dict()` returning {group: Adam.state_dict()}), or None.  `schedulers` defaults to the optimizers' own
+    `scheduler_state_dict()` ({group: LambdaLR.state_dict()}, trainer.py:470) so that a resumed run continues its
+    learning-rate decay."""
     os.makedirs(checkpoint_dir, exist_ok=True)
     path = checkpoint_path(checkpoint_dir, step)
     pipeline = {_PREFIX + k: v.detach().cpu() for k, v in params.items()}
@@ -50,6 +52,8 @@ def save_checkpoint(checkpoint_dir: str, step: int, params: Dict[str, torch.Tens
         for name, sd in optimizers.state_dict().items():
             opt_sd[name] = {"state": {i: {k: (v.detach().cpu() if torch.is_tensor(v) else v) for k, v in st.items()}
                                       for i, st in sd["state"].items()}, "param_groups": sd["param_groups"]}
+    if schedulers is None and optimizers is not None and hasattr(optimizers, "scheduler_state_dict"):
+        schedulers = optimizers.scheduler_state_dict()
     torch.save({"step": step, "pipeline": pipeline, "optimizers": opt_sd, "schedulers": schedulers or {},
                 "scalers": {}}, path)
     if save_only_latest_checkpoint:

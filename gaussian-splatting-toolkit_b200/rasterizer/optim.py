@@ -132,6 +132,23 @@ class GaussianOptimizers:
             self.sched_steps[name] += 1
             self.lrs[name] = fn(self.sched_steps[name])
 
+    def scheduler_state_dict(self) -> Dict[str, dict]:
+        """{group: LambdaLR.state_dict()} as saved by engine/trainer.py:470 (`{k: v.state_dict() for k, v in
+        self.optimizers.schedulers.items()}`): `last_epoch` carries the number of scheduler steps taken."""
+        return {name: {"base_lrs": [self.lr_init[name]], "last_epoch": int(self.sched_steps[name]),
+                       "_step_count": int(self.sched_steps[name]) + 1, "_get_lr_called_within_step": False,
+                       "_last_lr": [self.lrs[name]], "lr_lambdas": [None]} for name in self.schedulers}
+
+    def load_schedulers(self, loaded: Dict[str, dict]) -> None:
+        """engine/optimizers.py:207-214: restore the scheduler progress (and the learning rate it had produced), so that
+        the next scheduler_step_all() continues the decay instead of restarting it."""
+        for name, sd in loaded.items():
+            if name not in self.schedulers:
+                continue
+            self.sched_steps[name] = int(sd["last_epoch"])
+            last = sd.get("_last_lr")
+            self.lrs[name] = float(last[0]) if last else float(self.schedulers[name](max(self.sched_steps[name], 0)))
+
     # ------------------------------------------------------------------ densification support
     def moments(self, name: str):
         st = self.state[name]

@@ -165,43 +165,44 @@ GSR_API int gsr_map_gaussian_to_intersects_tight(int num_points, int num_interse
                                                  const float *opacities, const int32_t *cum_tiles_touched,
                                                  unsigned img_height, unsigned img_width, unsigned block_width,
                                                  int64_t *isect_ids, int32_t *gaussian_ids, void *stream);
-/* Fast internal binning of rasterize_gaussians (replaces, as a whole, the reference's forward orchestration
- * cumsum -> map_gaussian_to_intersects -> torch.sort(int64) -> torch.gather -> get_tile_bin_edges,
- * rasterizer/rasterize.py:106-138 + utils.py:106-182).  Same per-tile order as the reference (depth ascending,
- * ties in Gaussian-index order) obtained with a two-level sort: Gaussians by depth (32-bit keys), then the
- * emitted (tile, id) pairs stably by tile id only (ceil(log2 T) bits); with exact tile culling as above.
- *   gsr_bin_prepare   : perm [N] i32 (Gaussian ids in depth order), cum_tiles [N] i32 (inclusive scan of the kept
- *                       tile counts in that order), masks [N] u64 (kept tiles of each bounding box, indexed by Gaussian id);
- *                       the total M is copied to *total_host_pinned (pinned host int32) on `stream`.
- *   gsr_bin_emit_sort : after the caller has read M: gaussian_ids_sorted [M] i32, tile_bins [T,2] i32. */
-GSR_API size_t gsr_bin_prepare_workspace_bytes(int num_points);
-GSR_API int gsr_bin_prepare(int num_points, const float *xys, const float *depths, const int32_t *radii,
-                            const float *conics, const float *opacities, unsigned img_height,
-                            unsigned img_width, unsigned block_width, int32_t *perm, int32_t *cum_tiles,
-                            uint64_t *masks, int32_t *total_host_pinned, void *workspace, size_t workspace_bytes,
-                            void *stream);
-GSR_API size_t gsr_bin_emit_workspace_bytes(int num_intersects);
-GSR_API int gsr_bin_emit_sort(int num_points, int num_intersects, const float *xys, const int32_t *radii,
-                              const float *conics, const float *opacities, const int32_t *perm,
-                              const int32_t *cum_tiles, const uint64_t *masks,
-                              unsigned img_height, unsigned img_width, unsigned block_width,
-                              int32_t *gaussian_ids_sorted, int32_t *tile_bins, void *workspace,
-                              size_t workspace_bytes, void *stream);
-/* Asynchronous form of the fast binning: the pair count M stays on the DEVICE.  Every kernel after the scan reads it from
- * `meta` and runs on a grid sized for `capacity`; the call neither synchronises nor allocates, so a whole view can be
- * captured in a CUDA graph (the reference's `.item()`, rasterizer/utils.py:124, is the one host read this removes).
- *   gaussian_ids_sorted [capacity] i32 (entries >= min(M, capacity) are unspecified), tile_bins [T,2] i32,
- *   meta  DEVICE int32[4] = {M, overflow (M > capacity), min(M, capacity), 0}; if meta_host_pinned != NULL the four words
- *   are also copied there on `stream` (read them after an event / at the next call: `overflow` means the farthest
- *   pairs were dropped and the caller must repeat the view with a larger capacity).
- * Sorting and scanning are the library's own kernels (csrc/radix_sort.cuh); per-tile order as above. */
-GSR_API size_t gsr_bin_device_workspace_bytes(int num_points, int capacity);
+/* Internal binning of rasterize_gaussians (replaces, as a whole, the reference's forward orchestration
+ * cumsum -> .item() -> map_gaussian_to_intersects -> torch.sort(int64) -> torch.gather -> get_tile_bin_edges,
+ * rasterizer/rasterize.py:106-138 + utils.py:106-182).  Same per-tile order as the reference (depth ascending, ties in
+ * Gaussian-index order), with exact tile culling as above, obtained WITHOUT a global sort: pairs are counted per tile
+ * (atomics), the tile counts are scanned into tile_bins, the pairs are written unordered into their tile's segment as
+ * 64-bit keys (depth bits << 32 | Gaussian id) and every segment is sorted on its own (one CTA per tile, shared
+ * memory; segments above 4096 pairs fall back to a radix sort in global memory).  csrc/binning_device.cu.
+ *
+ * gsr_bin_gaussians_device — the whole binning in ONE asynchronous call; the pair count M stays on the DEVICE: no kernel
+ *   grid depends on it, the call neither synchronises nor allocates, so a whole view can be captured in a CUDA graph
+ *   (the reference's `.item()`, utils.py:124, is the host read this removes).
+ *     gaussian_ids_sorted [capacity] i32 (entries >= min(M, capacity) unspecified), tile_bins [T,2] i32,
+ *     meta  DEVICE int32[4] = {M, overflow (M > capacity), min(M, capacity), 0}; if meta_host_pinned != NULL the four
+ *     words are also copied there on `stream` (inspect them after an event / at the next call: `overflow` means the lists
+ *     were truncated and the caller must repeat the view with a larger capacity).
+ * gsr_bin_count + gsr_bin_fill_sort — the same in two calls for callers that want exactly-sized outputs: after
+ *   gsr_bin_count the caller synchronises, reads M = meta_host_pinned[0], allocates gaussian_ids_sorted [M] and a fill
+ *   workspace, and calls gsr_bin_fill_sort with the SAME count workspace (it holds the culling masks and fill cursors). */
+GSR_API size_t gsr_bin_device_workspace_bytes(int num_points, int capacity, unsigned img_height, unsigned img_width,
+                                              unsigned block_width);
 GSR_API int gsr_bin_gaussians_device(int num_points, const float *xys, const float *depths, const int32_t *radii,
                                      const float *conics, const float *opacities, unsigned img_height,
                                      unsigned img_width, unsigned block_width, int capacity,
                                      int32_t *gaussian_ids_sorted, int32_t *tile_bins, int32_t *meta,
                                      int32_t *meta_host_pinned /*nullable*/, void *workspace, size_t workspace_bytes,
                                      void *stream);
+GSR_API size_t gsr_bin_count_workspace_bytes(int num_points, unsigned img_height, unsigned img_width,
+                                             unsigned block_width);
+GSR_API int gsr_bin_count(int num_points, const float *xys, const int32_t *radii, const float *conics,
+                          const float *opacities, unsigned img_height, unsigned img_width, unsigned block_width,
+                          int32_t *tile_bins, int32_t *meta, int32_t *meta_host_pinned /*nullable*/,
+                          void *count_workspace, size_t workspace_bytes, void *stream);
+GSR_API size_t gsr_bin_fill_workspace_bytes(int num_intersects);
+GSR_API int gsr_bin_fill_sort(int num_points, int num_intersects, const float *xys, const float *depths,
+                              const int32_t *radii, const float *conics, const float *opacities,
+                              unsigned img_height, unsigned img_width, unsigned block_width, const int32_t *tile_bins,
+                              void *count_workspace, int32_t *gaussian_ids_sorted, void *fill_workspace,
+                              size_t fill_workspace_bytes, void *stream);
 GSR_API size_t gsr_sort_workspace_bytes(int num_intersects);
 GSR_API int gsr_sort_intersects(int num_intersects, int num_tiles, const int64_t *isect_ids,
                                 const int32_t *gaussian_ids, int64_t *isect_ids_sorted,

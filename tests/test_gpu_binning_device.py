@@ -1,4 +1,5 @@
-"""The hand-written sort / scan and the asynchronous (device-side M) binning against the synchronous path and torch."""
+"""The hand-written binning (per-tile counting + per-tile sorts, device-side M), the hand-written radix sort / scan of
+the public utilities, and the asynchronous binning mode."""
 import numpy as np
 import pytest
 import torch
@@ -38,17 +39,16 @@ def test_device_binning_matches_synchronous_binning(case):
     # exactly full buffers are not an overflow
     ids_e, bins_e, meta_e = C.bin_gaussians_device(xys, depths, radii, conics, op, H, W, bw, m)
     assert meta_e.tolist() == [m, 0, m, 0] and torch.equal(ids_e[:m], ids) and torch.equal(bins_e, bins)
-    # overflow: flagged, and the kept pairs are the first `cap` of the depth-ordered emission (the nearest Gaussians)
+    # overflow: flagged; tile_bins are clipped to the capacity, the tiles that still fit completely keep their exact lists
     cap = max(1, m // 2)
     ids_o, bins_o, meta_o = C.bin_gaussians_device(xys, depths, radii, conics, op, H, W, bw, cap)
     assert meta_o.tolist() == [m, 1, cap, 0]
-    b = bins_o.long()
-    assert int((b[:, 1] - b[:, 0]).sum()) == cap
     full, part = bins.long(), bins_o.long()
-    for t in torch.randint(0, bins.shape[0], (64,)).tolist():  # every truncated tile list is a PREFIX of the full one
-        n_part = int(part[t, 1] - part[t, 0])
-        assert n_part <= int(full[t, 1] - full[t, 0])
-        assert torch.equal(ids_o[part[t, 0]:part[t, 1]], ids[full[t, 0]:full[t, 0] + n_part])
+    assert int((part[:, 1] - part[:, 0]).sum()) == cap and int(part.max()) <= cap
+    fits = (full[:, 1] <= cap) & (full[:, 1] > full[:, 0])
+    assert bool(fits.any()) and torch.equal(part[fits], full[fits])
+    last = int(full[fits][:, 1].max())
+    assert torch.equal(ids_o[:last], ids[:last])
 
 
 def test_own_radix_sort_64bit_keys_random_and_ties():
@@ -59,7 +59,7 @@ def test_own_radix_sort_64bit_keys_random_and_ties():
     for m, tiles in ((1, 3), (31, 2), (4096, 100), (4097, 8160), (1_000_003, 32400)):
         tile = torch.randint(0, tiles, (m,), generator=g, device="cuda", dtype=torch.int64)
         depth = torch.randint(0, 2**31 - 1, (m,), generator=g, device="cuda", dtype=torch.int64)
-        depth[::3] = depth[0]  # many exact ties
+        depth[::3] = int(depth[0])  # many exact ties
         keys = (tile << 32) | depth
         vals = torch.arange(m, device="cuda", dtype=torch.int32)
         ks, vs = C.sort_intersects(keys, vals, tiles)
@@ -115,3 +115,23 @@ def test_async_binning_mode_matches_sync_and_reports_overflow():
     finally:
         rasterizer.set_binning_mode("sync")
         binning.reset()
+
+
+def test_long_tiles_take_the_global_radix_path_and_match_key_sort():
+    """More than 4096 pairs in one tile (the in-shared-memory sort's limit): the slow path must give the same lists as
+    the reference orchestration (64-bit key sort)."""
+    from rasterizer import cuda as C
+    from rasterizer.synthetic import make_scene
+
+    scene = make_scene(40_000, 64, 48, 0.05, 0.3, margin=0.6, seed=3)  # 12 tiles, ~10 k Gaussians each
+    s, (cov3d, xys, depths, radii, conics, comp, nth) = _projected(scene)
+    H, W, bw = s["img_height"], s["img_width"], s["block_width"]
+    op = s["opacities"].contiguous()
+    m, ids, bins = C.bin_gaussians_fast(xys, depths, radii, conics, op, H, W, bw)
+    assert int((bins[:, 1] - bins[:, 0]).max()) > 4096
+    tiles = C.count_tiles_tight(xys, radii, conics, op, H, W, bw)
+    cum = torch.cumsum(tiles, 0, dtype=torch.int32)
+    assert int(cum[-1]) == m
+    isect, gids = C.map_gaussian_to_intersects_tight(xys.shape[0], m, xys, depths, radii, conics, op, cum, H, W, bw)
+    ks, order = torch.sort(isect, stable=True)
+    assert torch.equal(ids.long(), gids.long()[order])

@@ -326,3 +326,42 @@ def test_errors_and_edge_cases():
     params["opacities"] = torch.full((64, 1), -20.0, device="cuda").requires_grad_(True)
     info = refinement_after(params, opt, stats, DensifyConfig(), 12000, 10, (64, 64))
     assert info["n_after"] == 0 and params["means"].shape == (0, 3) and params["features_rest"].shape == (0, 3, 3)
+
+
+def test_scheduler_progress_survives_checkpoint_resume(tmp_path):
+    """the means learning-rate decay must CONTINUE after a resume (engine/trainer.py:425-426 load_schedulers),
+    and the saved `schedulers` entry must be loadable by a real torch LambdaLR (what the reference trainer holds)."""
+    from rasterizer.io_scene import load_checkpoint, save_checkpoint
+    from rasterizer.optim import GaussianOptimizers, default_means_scheduler
+
+    def fresh():
+        g = torch.Generator().manual_seed(5)
+        params = {"means": torch.randn(64, 3, generator=g).cuda().requires_grad_(True),
+                  "opacities": torch.randn(64, 1, generator=g).cuda().requires_grad_(True)}
+        return params, GaussianOptimizers(params, schedulers={"means": default_means_scheduler()})
+
+    params, opt = fresh()
+    for step in range(1, 501):
+        opt.scheduler_step_all(step)
+    lr_500 = opt.lrs["means"]
+    assert lr_500 < 1.6e-4 * 0.95
+    save_checkpoint(str(tmp_path), 500, params, optimizers=opt)
+    ck = load_checkpoint(str(tmp_path))
+    assert set(ck["schedulers"]) == {"means"} and ck["schedulers"]["means"]["last_epoch"] == 500
+    params2, opt2 = fresh()
+    opt2.load_state_dict(ck["optimizers"])
+    opt2.load_schedulers(ck["schedulers"])
+    assert opt2.lrs["means"] == lr_500
+    opt.scheduler_step_all(501)
+    opt2.scheduler_step_all(501)
+    assert opt2.lrs["means"] == opt.lrs["means"] < lr_500  # continues, does not restart at lr_init
+    # a torch LambdaLR (the reference's scheduler object) accepts the saved dict and reports the same progress
+    p = torch.nn.Parameter(torch.zeros(1))
+    topt = torch.optim.Adam([p], lr=1.6e-4, eps=1e-15)
+    fn = default_means_scheduler()
+    sched = torch.optim.lr_scheduler.LambdaLR(topt, lr_lambda=lambda s: fn(s) / 1.6e-4)
+    sched.load_state_dict(ck["schedulers"]["means"])
+    assert sched.last_epoch == 500
+    topt.step()
+    sched.step()
+    assert abs(sched.get_last_lr()[0] - opt.lrs["means"]) < 1e-12
