@@ -271,6 +271,7 @@ class PublicApiView:
         for e in self.buf_free:
             e.record()
         self.k = 0
+        self.step_done = [None, None]  # the host runs at most two views ahead of the device (double-buffered inputs)
         self.h2d = sum(t.numel() * t.element_size() for t in (self.h_viewmat, self.h_projmat, self.h_vimg, self.h_valpha))
         self.d2h = sum(t.numel() * t.element_size() for t in (self.h_img, self.h_alpha))
 
@@ -283,6 +284,8 @@ class PublicApiView:
         main = torch.cuda.current_stream()
         i = self.k & 1
         self.k += 1
+        if self.step_done[i] is not None:
+            self.step_done[i].synchronize()  # view k-2 has finished: its buffers (device inputs, pinned outputs) are free
         # this step's inputs: cameras on the compute stream (128 B), upstream gradients on the H2D stream
         self.d_viewmat.copy_(self.h_viewmat, non_blocking=True)
         self.d_projmat.copy_(self.h_projmat, non_blocking=True)
@@ -330,6 +333,9 @@ class PublicApiView:
             for name, p in (("v_mean3d", self.means), ("v_scale", self.scales), ("v_quat", self.quats), ("v_opacity", self.opac)):
                 bk[name].copy_(p.grad.reshape(bk[name].shape))
             dist.all_reduce(bk.flat[bk.offsets["v_coeffs"][1]:])
+        done = torch.cuda.Event()
+        done.record()
+        self.step_done[i] = done
         return (self.coeffs.grad, self.means.grad, self.scales.grad, self.quats.grad, self.opac.grad)
 
     def finish(self):
@@ -685,6 +691,32 @@ def main():
                                               s["clip_thresh"])[6]
         M_ref = int(_nth.sum().item())
 
+    # the same resident view as ONE CUDA graph (N = 1): possible because no kernel's grid depends on the pair count and
+    # nothing in the view reads the device from the host (asynchronous binning); replayed back to back
+    graph_leg = None
+    if world == 1 and os.environ.get("GSR_BENCH_GRAPH", "1") != "0":
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                rv.step()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                g_out = rv.step()
+            ms_g = timed_loop(torch, dist, 1, g.replay, args.steps, args.warmup)
+            assert int(rv.pin_meta[1]) == 0, "pair buffers overflowed in the graph replay"
+            img_stream = rv.step()[0]
+            torch.cuda.synchronize()
+            graph_leg = {"value": args.steps / (ms_g * 1e-3), "unit": UNIT, "ms_per_step": ms_g / args.steps,
+                         "identical_image": bool(torch.equal(img_stream, g_out[0])),
+                         "what": "the resident view (all kernels of a step incl. binning) captured once with "
+                                 "torch.cuda.graph and replayed; same work as `value`, one launch per view"}
+        except Exception as e:  # never let the extra leg break the bench line
+            graph_leg = {"unavailable": f"{type(e).__name__}: {e}"}
+            torch.cuda.synchronize()
+
     # e2e through the public API with host buffers; asynchronous binning (rasterizer.binning): the first call of the
     # signature learns M synchronously (in the warm-up), the timed steps never read the pair count on the host
     import rasterizer
@@ -748,6 +780,8 @@ def main():
             line["config"]["sh_gradient_exchange"] = "NVLink peer loads (symmetric memory)" if peer is not None else "NCCL all-gather"
         if DIAG_NOCOPY:
             line["diagnostic"] = "GSR_E2E_NOCOPY=1: e2e WITHOUT its host copies - not a reportable number"
+        if graph_leg is not None:
+            line["cuda_graph"] = graph_leg
         if xcheck is not None:
             line["exchange_check"] = xcheck
         if world == 1:

@@ -7,22 +7,30 @@
 // Gaussian-index order.  The tile part of the key only PARTITIONS the pairs; only the order INSIDE a tile needs a
 // comparison sort, and a tile holds a few hundred pairs.  So (a counting sort by tile + small independent sorts):
 //
-//   bin_count_kernel   per Gaussian: the tiles of its bounding box that can be reached with alpha >= 1/255 (exact tile
-//                      culling, tile_cull.cuh) as a count and a 64-bit mask; one RED.ADD per kept (Gaussian, tile) pair
-//                      into tile_count[tile]
+//   bin_count_blocks_kernel  block b owns a contiguous range of Gaussians; per Gaussian the tiles of its bounding box
+//                      that can be reached with alpha >= 1/255 (exact tile culling, tile_cull.cuh) are counted into a
+//                      SHARED-MEMORY histogram over the T tiles (packed 16-bit counters, shared atomics — no global
+//                      atomics), the 64-bit tile mask is kept; the block's histogram row goes to base[b][0..T)
+//   bin_colscan_kernel per tile: exclusive prefix of its column over the blocks (in place) -> offset of every block's
+//                      pairs inside the tile's segment; column total -> tile_count[t]
 //   tile_scan_kernel   one block: exclusive scan over the T tiles -> tile_bins [T,2] (clipped to the pair capacity),
-//                      per-tile fill cursors, meta = {M, overflow, min(M, capacity)}
-//   bin_fill_kernel    per Gaussian: slot = atomicAdd(cursor[tile]) for each kept tile; writes the 64-bit key
-//                      (depth bits << 32 | Gaussian id) — unordered inside the tile's segment
-//   tile_sort_kernel   one CTA per tile: bitonic sort of the segment's keys in shared memory (<= 4096 pairs), the low
-//                      words (Gaussian ids) go to gaussian_ids_sorted; longer tiles: stable LSD radix sort of the
-//                      segment in global memory by one warp (slow path, keeps the call correct for any scene)
+//                      segment starts, meta = {M, overflow, min(M, capacity)}
+//   bin_fill_blocks_kernel   same blocks again: slot = tile_start[t] + base[b][t] + (shared-memory cursor of the block
+//                      for t)++; writes the 64-bit key (depth bits << 32 | Gaussian id) — unordered inside the
+//                      (block, tile) group, every group in its own range of the tile's segment
+//   tile_sort_warp_kernel    one WARP per tile with <= 1024 pairs: bitonic sort in registers (E = 4..32 keys per lane;
+//                      in-register stages + shuffle stages, no shared memory, no barrier); the low words (Gaussian
+//                      ids) go to gaussian_ids_sorted
+//   tile_sort_kernel   one CTA per tile with more pairs: bitonic sort in shared memory (<= 4096), above that a stable
+//                      LSD radix sort of the segment in global memory (slow path, keeps the call correct for any scene)
+//   (images with more than 48 K tiles do not fit the shared-memory histogram: bin_count_kernel / bin_fill_kernel do the
+//   same with global atomics)
 //
 // Keys are unique (the id is part of the key), so the result is deterministic and identical to the reference's order
 // although the fill order is not.  No kernel's grid depends on M: the call neither synchronises nor allocates and can
 // be captured in a CUDA graph; if M exceeds the caller's capacity, meta[1] is set (the lists are truncated).
 // Compared with round 1 (depth sort of N + emit + stable sort of M pairs by tile with cub::DeviceRadixSort + bin edges)
-// this moves 12 M bytes once instead of ~50 M and drops both library sorts.
+// this moves 8 M bytes of keys once instead of ~50 M and drops both library sorts.
 #include "common.cuh"
 #include "radix_sort.cuh"
 #include "tile_cull.cuh"
@@ -144,6 +152,153 @@ bin_fill_kernel(int n, const float2 *__restrict__ xys, const float *__restrict__
                      });
 }
 
+// ---- block-privatised counting / filling (no global atomics) --------------------------------------------------------
+constexpr int SMEM_HIST_MAX_TILES = 49152;  // packed u16 counters: 96 KB of dynamic shared memory
+
+__device__ __forceinline__ unsigned smem_count_inc(unsigned *s_hist, int tile) {
+  // packed 16-bit counters: returns the counter's value BEFORE the increment
+  const unsigned old = atomicAdd(s_hist + (tile >> 1), (tile & 1) ? 0x10000u : 1u);
+  return (tile & 1) ? (old >> 16) : (old & 0xffffu);
+}
+
+__global__ void __launch_bounds__(BD_THREADS)
+bin_count_blocks_kernel(int n, int per_block, const float2 *__restrict__ xys, const int *__restrict__ radii,
+                        const float *__restrict__ conics, const float *__restrict__ opacities, int tiles_x, int tiles_y,
+                        int block_width, u64 *__restrict__ masks, unsigned *__restrict__ base /*[B][T]*/) {
+  extern __shared__ unsigned s_hist[];
+  const int num_tiles = tiles_x * tiles_y, words = (num_tiles + 1) >> 1;
+  for (int i = threadIdx.x; i < words; i += BD_THREADS) s_hist[i] = 0u;
+  __syncthreads();
+  const int g0 = blockIdx.x * per_block, g1 = min(n, g0 + per_block);
+  for (int g = g0 + threadIdx.x; g < g1; g += BD_THREADS) {
+    const int r = radii[g];
+    u64 mask = 0ull;
+    if (r > 0)
+      for_each_kept_tile(xys[g], r, conics[3 * (size_t)g], conics[3 * (size_t)g + 1], conics[3 * (size_t)g + 2], opacities[g],
+                         tiles_x, tiles_y, block_width, mask, false, [&](int tile) { smem_count_inc(s_hist, tile); });
+    masks[g] = mask;
+  }
+  __syncthreads();
+  unsigned *row = base + (size_t)blockIdx.x * num_tiles;
+  for (int t = threadIdx.x; t < num_tiles; t += BD_THREADS) row[t] = (s_hist[t >> 1] >> ((t & 1) * 16)) & 0xffffu;
+}
+
+__global__ void __launch_bounds__(BD_THREADS)
+bin_colscan_kernel(int num_blocks, int num_tiles, unsigned *__restrict__ base, unsigned *__restrict__ tile_count) {
+  const int t = blockIdx.x * BD_THREADS + threadIdx.x;
+  if (t >= num_tiles) return;
+  unsigned run = 0;
+#pragma unroll 4
+  for (int b = 0; b < num_blocks; ++b) {
+    const size_t i = (size_t)b * num_tiles + t;
+    const unsigned c = base[i];
+    base[i] = run;
+    run += c;
+  }
+  tile_count[t] = run;
+}
+
+__global__ void __launch_bounds__(BD_THREADS)
+bin_fill_blocks_kernel(int n, int per_block, const float2 *__restrict__ xys, const float *__restrict__ depths,
+                       const int *__restrict__ radii, const float *__restrict__ conics, const float *__restrict__ opacities,
+                       const u64 *__restrict__ masks, int tiles_x, int tiles_y, int block_width, int capacity,
+                       const unsigned *__restrict__ tile_start, const unsigned *__restrict__ base, u64 *__restrict__ keys) {
+  extern __shared__ unsigned s_hist[];
+  const int num_tiles = tiles_x * tiles_y, words = (num_tiles + 1) >> 1;
+  for (int i = threadIdx.x; i < words; i += BD_THREADS) s_hist[i] = 0u;
+  __syncthreads();
+  const unsigned *row = base + (size_t)blockIdx.x * num_tiles;
+  const int g0 = blockIdx.x * per_block, g1 = min(n, g0 + per_block);
+  for (int g = g0 + threadIdx.x; g < g1; g += BD_THREADS) {
+    const int r = radii[g];
+    if (r <= 0) continue;
+    u64 mask = masks[g];
+    const u64 key = ((u64)(unsigned)__float_as_int(depths[g]) << 32) | (u64)(unsigned)g;
+    for_each_kept_tile(xys[g], r, conics[3 * (size_t)g], conics[3 * (size_t)g + 1], conics[3 * (size_t)g + 2], opacities[g],
+                       tiles_x, tiles_y, block_width, mask, true, [&](int tile) {
+                         const unsigned pos = tile_start[tile] + row[tile] + smem_count_inc(s_hist, tile);
+                         if (pos < (unsigned)capacity) keys[pos] = key;
+                       });
+  }
+}
+
+// ---- per-tile sort, one warp per tile, keys in registers --------------------------------------------------------------
+// E keys per lane, element index e = lane * E + r.  Bitonic network over 32 E elements: the stages whose partner
+// distance j is below E exchange registers of one lane, the others exchange with lane ^ (j / E) through shuffles.
+template <int E>
+__device__ __forceinline__ void warp_bitonic_sort(u64 (&k)[E], int lane) {
+  const unsigned full = 0xffffffffu;
+  for (int k2 = 2; k2 <= 32 * E; k2 <<= 1) {
+    for (int j = k2 >> 1; j >= E; j >>= 1) {
+      const int lm = j / E;
+      const bool lower = (lane & lm) == 0;
+#pragma unroll
+      for (int r = 0; r < E; ++r) {
+        const u64 other = __shfl_xor_sync(full, k[r], lm);
+        const bool up = ((lane * E + r) & k2) == 0;
+        const u64 lo = k[r] < other ? k[r] : other, hi = k[r] < other ? other : k[r];
+        k[r] = (lower == up) ? lo : hi;
+      }
+    }
+#pragma unroll
+    for (int jj = E >> 1; jj > 0; jj >>= 1) {
+      if (jj < k2) {
+#pragma unroll
+        for (int r = 0; r < E; ++r) {
+          if ((r & jj) == 0) {
+            const bool up = ((lane * E + r) & k2) == 0;
+            const u64 a = k[r], b = k[r | jj];
+            const bool sw = (a > b) == up;
+            k[r] = sw ? b : a;
+            k[r | jj] = sw ? a : b;
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int E>
+__device__ __forceinline__ void warp_sort_tile(const u64 *__restrict__ seg, int n, int lane, int *__restrict__ ids_out) {
+  u64 k[E];
+#pragma unroll
+  for (int r = 0; r < E; ++r) {
+    const int e = lane * E + r;
+    k[r] = e < n ? seg[e] : ~0ull;
+  }
+  warp_bitonic_sort<E>(k, lane);
+#pragma unroll
+  for (int r = 0; r < E; ++r) {
+    const int e = lane * E + r;
+    if (e < n) ids_out[e] = (int)(unsigned)k[r];
+  }
+}
+
+constexpr int SORT_WARP_MAX = 1024;  // pairs one warp sorts in registers
+constexpr int SORT_WARPS = 4;        // warps (= tiles) per CTA of tile_sort_warp_kernel
+
+// BIG = false: tiles with 1..512 pairs (E <= 16, ~90 registers); BIG = true: 513..1024 pairs (E = 32, ~170 registers) —
+// two kernels so that the common short tiles are not held to the occupancy of the 64-register key array
+template <bool BIG>
+__global__ void __launch_bounds__(32 * SORT_WARPS)
+tile_sort_warp_kernel(int num_tiles, const int2 *__restrict__ tile_bins, const u64 *__restrict__ keys,
+                      int *__restrict__ ids_out) {
+  const int tile = blockIdx.x * SORT_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (tile >= num_tiles) return;
+  const int2 range = tile_bins[tile];
+  const int n = range.y - range.x;
+  const u64 *seg = keys + range.x;
+  int *out = ids_out + range.x;
+  if (BIG) {
+    if (n > 512 && n <= SORT_WARP_MAX) warp_sort_tile<32>(seg, n, lane, out);
+  } else {
+    if (n <= 0 || n > 512) return;
+    if (n <= 128) warp_sort_tile<4>(seg, n, lane, out);
+    else if (n <= 256) warp_sort_tile<8>(seg, n, lane, out);
+    else warp_sort_tile<16>(seg, n, lane, out);
+  }
+}
+
 // ---- per-tile sort ---------------------------------------------------------------------------------------------------
 // slow path for tiles with more than SORT_SMEM_MAX pairs: stable LSD radix sort (8-bit digits) of n keys between two
 // global buffers, ONE warp scattering in order (the other warps only help with the histogram).  Only the bits that can
@@ -215,7 +370,7 @@ tile_sort_kernel(const int2 *__restrict__ tile_bins, u64 *__restrict__ keys, u64
   __shared__ unsigned s_hist[256];
   const int2 range = tile_bins[blockIdx.x];
   const int n = range.y - range.x, tid = threadIdx.x;
-  if (n <= 0) return;
+  if (n <= SORT_WARP_MAX) return;  // sorted by tile_sort_warp_kernel
   u64 *seg = keys + range.x;
   if (n > SORT_SMEM_MAX) {
     long_tile_radix_sort(seg, keys_tmp + range.x, n, id_bits, s_hist, ids_out + range.x);
@@ -252,37 +407,69 @@ inline int bits_for(long long n) {
 
 struct BinLayout {  // carved from the caller's workspace
   u64 *masks, *keys, *keys_tmp;
-  unsigned *tile_count, *cursors;
+  unsigned *tile_count, *cursors, *base;
+  int per_block, num_blocks;  // Gaussians per block / blocks of the shared-memory-histogram kernels (0 = global atomics)
 };
+
+// Gaussians per block: about two blocks per SM, a multiple of the block size, at most 65535 (16-bit counters)
+inline void block_partition(int num_points, int num_tiles, int &per_block, int &num_blocks) {
+  per_block = num_blocks = 0;
+  if (num_tiles > SMEM_HIST_MAX_TILES || num_points <= 0) return;
+  long long per = ((long long)num_points + 295) / 296;
+  per = ((per + BD_THREADS - 1) / BD_THREADS) * BD_THREADS;
+  if (per < 2048) per = 2048;
+  if (per > 65280) per = 65280;
+  per_block = (int)per;
+  num_blocks = (int)(((long long)num_points + per - 1) / per);
+}
 
 inline size_t layout_bytes(int num_points, int capacity, int num_tiles) {
   const size_t n = num_points > 0 ? num_points : 1, c = capacity > 0 ? capacity : 1, t = num_tiles > 0 ? num_tiles : 1;
-  return al256(8 * n) + 2 * al256(8 * c) + 2 * al256(4 * t) + 256;
+  int per_block, num_blocks;
+  block_partition(num_points, num_tiles, per_block, num_blocks);
+  return al256(8 * n) + 2 * al256(8 * c) + 2 * al256(4 * t) + al256(4 * t * (size_t)(num_blocks > 0 ? num_blocks : 1)) + 256;
 }
 
 inline BinLayout carve(void *workspace, int num_points, int capacity, int num_tiles) {
   const size_t n = num_points > 0 ? num_points : 1, c = capacity > 0 ? capacity : 1, t = num_tiles > 0 ? num_tiles : 1;
   char *ws = (char *)workspace;
   BinLayout L;
+  block_partition(num_points, num_tiles, L.per_block, L.num_blocks);
+  // the capacity-independent part first, so that gsr_bin_count (capacity 1) and gsr_bin_fill_sort agree on it
   L.masks = (u64 *)ws;           ws += al256(8 * n);
-  L.keys = (u64 *)ws;            ws += al256(8 * c);
-  L.keys_tmp = (u64 *)ws;        ws += al256(8 * c);
   L.tile_count = (unsigned *)ws; ws += al256(4 * t);
-  L.cursors = (unsigned *)ws;
+  L.cursors = (unsigned *)ws;    ws += al256(4 * t);
+  L.base = (unsigned *)ws;       ws += al256(4 * t * (size_t)(L.num_blocks > 0 ? L.num_blocks : 1));
+  L.keys = (u64 *)ws;            ws += al256(8 * c);
+  L.keys_tmp = (u64 *)ws;
   return L;
 }
 
-// count + scan: tile_bins / cursors / meta for `capacity`
+// count + scan: tile_bins / segment starts / meta for `capacity`
 int run_count(int num_points, const float *xys, const int32_t *radii, const float *conics, const float *opacities,
               int tiles_x, int tiles_y, unsigned block_width, int capacity, const BinLayout &L, int32_t *tile_bins,
               int32_t *meta, cudaStream_t st) {
   const int num_tiles = tiles_x * tiles_y;
-  GSR_CUDA(cudaMemsetAsync(L.tile_count, 0, sizeof(unsigned) * (size_t)num_tiles, st));
-  if (num_points > 0) {
-    bin_count_kernel<<<cdiv(num_points, BD_THREADS), BD_THREADS, 0, st>>>(
-        num_points, reinterpret_cast<const float2 *>(xys), radii, conics, opacities, tiles_x, tiles_y, (int)block_width,
-        L.masks, L.tile_count);
-    GSR_CHECK_LAUNCH("bin_count_kernel");
+  if (L.num_blocks > 0) {
+    const size_t smem = sizeof(unsigned) * (size_t)((num_tiles + 1) >> 1);
+    if (smem > 48 * 1024) {
+      GSR_CUDA(cudaFuncSetAttribute(bin_count_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      GSR_CUDA(cudaFuncSetAttribute(bin_fill_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    bin_count_blocks_kernel<<<L.num_blocks, BD_THREADS, smem, st>>>(
+        num_points, L.per_block, reinterpret_cast<const float2 *>(xys), radii, conics, opacities, tiles_x, tiles_y,
+        (int)block_width, L.masks, L.base);
+    GSR_CHECK_LAUNCH("bin_count_blocks_kernel");
+    bin_colscan_kernel<<<cdiv(num_tiles, BD_THREADS), BD_THREADS, 0, st>>>(L.num_blocks, num_tiles, L.base, L.tile_count);
+    GSR_CHECK_LAUNCH("bin_colscan_kernel");
+  } else {
+    GSR_CUDA(cudaMemsetAsync(L.tile_count, 0, sizeof(unsigned) * (size_t)num_tiles, st));
+    if (num_points > 0) {
+      bin_count_kernel<<<cdiv(num_points, BD_THREADS), BD_THREADS, 0, st>>>(
+          num_points, reinterpret_cast<const float2 *>(xys), radii, conics, opacities, tiles_x, tiles_y, (int)block_width,
+          L.masks, L.tile_count);
+      GSR_CHECK_LAUNCH("bin_count_kernel");
+    }
   }
   tile_scan_kernel<<<1, 1024, 0, st>>>(num_tiles, L.tile_count, capacity, reinterpret_cast<int2 *>(tile_bins), L.cursors, meta);
   GSR_CHECK_LAUNCH("tile_scan_kernel");
@@ -293,12 +480,27 @@ int run_fill_sort(int num_points, const float *xys, const float *depths, const i
                   const float *opacities, int tiles_x, int tiles_y, unsigned block_width, int capacity, const BinLayout &L,
                   const int32_t *tile_bins, int32_t *gaussian_ids_sorted, cudaStream_t st) {
   if (num_points <= 0 || capacity <= 0) return GSR_OK;
-  bin_fill_kernel<<<cdiv(num_points, BD_THREADS), BD_THREADS, 0, st>>>(
-      num_points, reinterpret_cast<const float2 *>(xys), depths, radii, conics, opacities, L.masks, tiles_x, tiles_y,
-      (int)block_width, capacity, L.cursors, L.keys);
-  GSR_CHECK_LAUNCH("bin_fill_kernel");
-  tile_sort_kernel<<<tiles_x * tiles_y, BD_THREADS, 0, st>>>(reinterpret_cast<const int2 *>(tile_bins), L.keys, L.keys_tmp,
-                                                             bits_for(num_points), gaussian_ids_sorted);
+  const int num_tiles = tiles_x * tiles_y;
+  if (L.num_blocks > 0) {
+    const size_t smem = sizeof(unsigned) * (size_t)((num_tiles + 1) >> 1);
+    bin_fill_blocks_kernel<<<L.num_blocks, BD_THREADS, smem, st>>>(
+        num_points, L.per_block, reinterpret_cast<const float2 *>(xys), depths, radii, conics, opacities, L.masks, tiles_x,
+        tiles_y, (int)block_width, capacity, L.cursors, L.base, L.keys);
+    GSR_CHECK_LAUNCH("bin_fill_blocks_kernel");
+  } else {
+    bin_fill_kernel<<<cdiv(num_points, BD_THREADS), BD_THREADS, 0, st>>>(
+        num_points, reinterpret_cast<const float2 *>(xys), depths, radii, conics, opacities, L.masks, tiles_x, tiles_y,
+        (int)block_width, capacity, L.cursors, L.keys);
+    GSR_CHECK_LAUNCH("bin_fill_kernel");
+  }
+  tile_sort_warp_kernel<false><<<cdiv(num_tiles, SORT_WARPS), 32 * SORT_WARPS, 0, st>>>(
+      num_tiles, reinterpret_cast<const int2 *>(tile_bins), L.keys, gaussian_ids_sorted);
+  GSR_CHECK_LAUNCH("tile_sort_warp_kernel<small>");
+  tile_sort_warp_kernel<true><<<cdiv(num_tiles, SORT_WARPS), 32 * SORT_WARPS, 0, st>>>(
+      num_tiles, reinterpret_cast<const int2 *>(tile_bins), L.keys, gaussian_ids_sorted);
+  GSR_CHECK_LAUNCH("tile_sort_warp_kernel<big>");
+  tile_sort_kernel<<<num_tiles, BD_THREADS, 0, st>>>(reinterpret_cast<const int2 *>(tile_bins), L.keys, L.keys_tmp,
+                                                     bits_for(num_points), gaussian_ids_sorted);
   GSR_CHECK_LAUNCH("tile_sort_kernel");
   return GSR_OK;
 }

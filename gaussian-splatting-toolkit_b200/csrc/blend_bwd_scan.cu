@@ -58,50 +58,80 @@ __device__ __forceinline__ void process_group(const LaneGaussian &G, const float
                                               float *__restrict__ v_opacity) {
   const unsigned full = 0xffffffffu;
   float a_r = 0.f, a_g = 0.f, a_b = 0.f, a_xx = 0.f, a_xy = 0.f, a_yy = 0.f, a_x = 0.f, a_y = 0.f, a_w = 0.f;
-#pragma unroll 2
-  for (int p = 0; p < 32; ++p) {
-    const float4 c = pixc[p];
-    const float4 st = pixs[p];
-    const float dx = G.x - st.x, dy = G.y - st.y;
-    const float gx = G.A * dx, gy = G.C * dy;
-    const float power = dx * (gx + G.B * dy) + gy * dy;  // = -sigma log2(e)
-    const float vis = exp2f(power);
-    const float alpha = fminf(0.99f, G.o * vis);
-    const bool valid = (G.sidx <= __float_as_int(c.w)) && !(power > 0.f || alpha < 1.f / 255.f);
-    const float alpha_e = valid ? alpha : 0.f;
-    const float vis_e = valid ? vis : 0.f;
-    const float ra = 1.f / (1.f - alpha_e);
-    // inclusive product scan over the lanes (lane order = back to front): R_j = prod_{i<=j} ra_i
-    float R = ra;
+  // Two pixels per iteration, written out so that their two shuffle chains are independent and interleave (one chain
+  // alone is latency-bound: 10 dependent SHFLs; ncu of the first version: issue slots 55 % busy, short-scoreboard
+  // stalls 4.1 per issue).  All shared-memory loads of the pair come first, the carry stores last.
+  constexpr int U = 2;
+  for (int p = 0; p < 32; p += U) {
+    float4 c[U], st[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      c[u] = pixc[p + u];
+      st[u] = pixs[p + u];
+    }
+    float dx[U], dy[U], vis_e[U], alpha_e[U], ra[U], R[U], T[U], fac[U], dj[U], cj[U], S[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      dx[u] = G.x - st[u].x;
+      dy[u] = G.y - st[u].y;
+      const float gx = G.A * dx[u], gy = G.C * dy[u];
+      const float power = dx[u] * (gx + G.B * dy[u]) + gy * dy[u];  // = -sigma log2(e)
+      const float vis = exp2f(power);
+      const float alpha = fminf(0.99f, G.o * vis);
+      const bool valid = (G.sidx <= __float_as_int(c[u].w)) && !(power > 0.f || alpha < 1.f / 255.f);
+      alpha_e[u] = valid ? alpha : 0.f;
+      vis_e[u] = valid ? vis : 0.f;
+      ra[u] = 1.f / (1.f - alpha_e[u]);
+      R[u] = ra[u];
+    }
+    // inclusive product scans over the lanes (lane order = back to front): R_j = prod_{i<=j} ra_i
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-      const float up = __shfl_up_sync(full, R, d);
-      if (lane >= d) R *= up;
+      float up[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) up[u] = __shfl_up_sync(full, R[u], d);
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (lane >= d) R[u] *= up[u];
     }
-    const float T = st.z * R;  // transmittance in front of this Gaussian
-    const float fac = alpha_e * T;
-    const float dj = G.r * c.x + G.g * c.y + G.b * c.z;
-    const float cj = fac * dj;
-    float S = cj;  // inclusive sum scan: S_j = sum_{i<=j} alpha_i T_i d_i
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      T[u] = st[u].z * R[u];  // transmittance in front of this Gaussian
+      fac[u] = alpha_e[u] * T[u];
+      dj[u] = G.r * c[u].x + G.g * c[u].y + G.b * c[u].z;
+      cj[u] = fac[u] * dj[u];
+      S[u] = cj[u];
+    }
+    // inclusive sum scans: S_j = sum_{i<=j} alpha_i T_i d_i
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-      const float up = __shfl_up_sync(full, S, d);
-      if (lane >= d) S += up;
+      float up[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) up[u] = __shfl_up_sync(full, S[u], d);
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (lane >= d) S[u] += up[u];
     }
-    const float s_behind = st.w + (S - cj);
-    const float v_alpha = T * dj - ra * s_behind;
-    const float w = vis_e * v_alpha;
-    a_r += fac * c.x;
-    a_g += fac * c.y;
-    a_b += fac * c.z;
-    const float wdx = w * dx, wdy = w * dy;
-    a_xx += wdx * dx;
-    a_xy += wdx * dy;
-    a_yy += wdy * dy;
-    a_x += wdx;
-    a_y += wdy;
-    a_w += w;
-    if (lane == 31) *reinterpret_cast<float2 *>(&pixs[p].z) = make_float2(T, st.w + S);  // carry to the next group
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const float s_behind = st[u].w + (S[u] - cj[u]);
+      const float v_alpha = T[u] * dj[u] - ra[u] * s_behind;
+      const float w = vis_e[u] * v_alpha;
+      a_r += fac[u] * c[u].x;
+      a_g += fac[u] * c[u].y;
+      a_b += fac[u] * c[u].z;
+      const float wdx = w * dx[u], wdy = w * dy[u];
+      a_xx += wdx * dx[u];
+      a_xy += wdx * dy[u];
+      a_yy += wdy * dy[u];
+      a_x += wdx;
+      a_y += wdy;
+      a_w += w;
+    }
+    if (lane == 31) {  // carry to the next group
+#pragma unroll
+      for (int u = 0; u < U; ++u) *reinterpret_cast<float2 *>(&pixs[p + u].z) = make_float2(T[u], st[u].w + S[u]);
+    }
   }
   __syncwarp();
   if (G.id >= 0) {
@@ -123,7 +153,8 @@ __device__ __forceinline__ void process_group(const LaneGaussian &G, const float
 
 }  // namespace
 
-__global__ void __launch_bounds__(BLEND_THREADS, 3)
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(BLEND_THREADS, MIN_CTAS)
 blend_backward_scan_kernel(int tiles_x, int img_w, int img_h, const int *__restrict__ gaussian_ids_sorted,
                            const int2 *__restrict__ tile_bins, const float2 *__restrict__ xys,
                            const float *__restrict__ conics, const float *__restrict__ colors,
@@ -224,11 +255,12 @@ blend_backward_scan_kernel(int tiles_x, int img_w, int img_h, const int *__restr
   }
 }
 
-// GSR_BWD_KERNEL = pixel (default) | scan — read once; A/B switch between the two adjoint kernels
+// GSR_BWD_KERNEL = pixel (default) | scan (3 CTAs / SM) | scan4 (registers capped for 4 CTAs / SM) — read once; A/B switch
 int blend_bwd_use_scan() {
   static const int v = [] {
     const char *e = getenv("GSR_BWD_KERNEL");
-    return (e && e[0] == 's') ? 1 : 0;
+    if (!(e && e[0] == 's')) return 0;
+    return (e[1] && e[2] && e[3] && e[4] == '4') ? 4 : 3;
   }();
   return v;
 }
@@ -238,9 +270,16 @@ int launch_blend_backward_scan(dim3 grid, cudaStream_t st, int img_w, int img_h,
                                const float *opacities, const float *background, const float *final_Ts,
                                const int *final_idx, const float *v_output, const float *v_output_alpha, float *v_xy,
                                float *v_conic, float *v_colors, float *v_opacity) {
-  blend_backward_scan_kernel<<<grid, BLEND_THREADS, 0, st>>>((int)grid.x, img_w, img_h, gaussian_ids_sorted, tile_bins, xys,
-                                                             conics, colors, opacities, background, final_Ts, final_idx,
-                                                             v_output, v_output_alpha, v_xy, v_conic, v_colors, v_opacity);
+  if (blend_bwd_use_scan() == 4)
+    blend_backward_scan_kernel<4><<<grid, BLEND_THREADS, 0, st>>>((int)grid.x, img_w, img_h, gaussian_ids_sorted, tile_bins,
+                                                                  xys, conics, colors, opacities, background, final_Ts,
+                                                                  final_idx, v_output, v_output_alpha, v_xy, v_conic,
+                                                                  v_colors, v_opacity);
+  else
+    blend_backward_scan_kernel<3><<<grid, BLEND_THREADS, 0, st>>>((int)grid.x, img_w, img_h, gaussian_ids_sorted, tile_bins,
+                                                                  xys, conics, colors, opacities, background, final_Ts,
+                                                                  final_idx, v_output, v_output_alpha, v_xy, v_conic,
+                                                                  v_colors, v_opacity);
   GSR_CHECK_LAUNCH("blend_backward_scan_kernel");
   return GSR_OK;
 }

@@ -57,10 +57,21 @@ class _Signature:
 _signatures: Dict[Tuple, _Signature] = {}
 _pending: List[Tuple[torch.Tensor, "torch.cuda.Event", Tuple, int]] = []  # (pinned meta, event, signature key, capacity)
 _free_slots: List[torch.Tensor] = []
+_RING = 64  # pinned {M, overflow, ..} slots, allocated ONCE (pinning is a slow, synchronising call): the host can run
+            # at most _RING asynchronous rasterize calls ahead of the device
 
 
 def _slot() -> torch.Tensor:
-    return _free_slots.pop() if _free_slots else torch.zeros(4, dtype=torch.int32).pin_memory()
+    global _free_slots
+    if not _free_slots and not _pending:
+        ring = torch.zeros(_RING, 4, dtype=torch.int32).pin_memory()
+        _free_slots = [ring[i] for i in range(_RING)]
+    if not _free_slots:
+        _inspect(block=False)
+    if not _free_slots:  # every slot belongs to a call still in flight: wait for the oldest one
+        _pending[0][1].synchronize()
+        _inspect(block=False)
+    return _free_slots.pop()
 
 
 def _inspect(block: bool) -> None:

@@ -336,8 +336,9 @@ def test_scheduler_progress_survives_checkpoint_resume(tmp_path):
 
     def fresh():
         g = torch.Generator().manual_seed(5)
-        params = {"means": torch.randn(64, 3, generator=g).cuda().requires_grad_(True),
-                  "opacities": torch.randn(64, 1, generator=g).cuda().requires_grad_(True)}
+        shapes = {"means": (64, 3), "scales": (64, 3), "quats": (64, 4), "features_dc": (64, 3), "features_rest": (64, 15, 3),
+                  "opacities": (64, 1)}
+        params = {k: torch.randn(*sh, generator=g).cuda().requires_grad_(True) for k, sh in shapes.items()}
         return params, GaussianOptimizers(params, schedulers={"means": default_means_scheduler()})
 
     params, opt = fresh()

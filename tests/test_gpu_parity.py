@@ -74,8 +74,10 @@ def _check_view(ours, ref, has_backward=True, int_slack=2e-4, grad_norm_rel=1e-4
     if not has_backward:
         return
     for k in ("v_xy", "v_conic", "v_colors", "v_opacity", "v_coeffs", "v_mean3d", "v_scale", "v_quat"):
+        # the whole-tensor norm may be carried by the few threshold-flip outliers (counted by frac_bad); everything
+        # else must agree to 5e-5
         assert_float_parity(to_np(ours[k]).reshape(to_np(ref[k]).shape), ref[k], k, max_norm_rel=grad_norm_rel, max_frac_bad=grad_frac_bad,
-                            min_bad_count=16)
+                            min_bad_count=16, max_norm_rel_trim=5e-5)
 
 
 @pytest.mark.parametrize("name", list(_scenes().keys()))
@@ -91,7 +93,8 @@ def test_view_vs_oracle(oracle, name):
     assert ours["num_intersects"] == ref["num_intersects"] or abs(ours["num_intersects"] - ref["num_intersects"]) < 1e-3 * ref["num_intersects"]
     # the all-opaque scene is built to sit on the alpha / transmittance thresholds: one flipped Gaussian moves 48
     # entries of v_coeffs (observed 5.5e-4 of the elements)
-    _check_view(ours, ref, amb=ref["ambiguous"], grad_frac_bad=2e-3 if "opaque" in name else 5e-4)
+    opaque = "opaque" in name
+    _check_view(ours, ref, amb=ref["ambiguous"], grad_frac_bad=2e-3 if opaque else 5e-4, grad_norm_rel=3e-4 if opaque else 1e-4)
 
 
 @pytest.mark.parametrize("name", ["cfg1_10k_256", "ragged_4k_200x120_bw12_rot"])
