@@ -161,16 +161,18 @@ __device__ __forceinline__ unsigned smem_count_inc(unsigned *s_hist, int tile) {
   return (tile & 1) ? (old >> 16) : (old & 0xffffu);
 }
 
-__global__ void __launch_bounds__(BD_THREADS)
+constexpr int BLK_THREADS = 1024;  // few, fat blocks: one shared-memory histogram per block, full occupancy per SM
+
+__global__ void __launch_bounds__(BLK_THREADS)
 bin_count_blocks_kernel(int n, int per_block, const float2 *__restrict__ xys, const int *__restrict__ radii,
                         const float *__restrict__ conics, const float *__restrict__ opacities, int tiles_x, int tiles_y,
                         int block_width, u64 *__restrict__ masks, unsigned *__restrict__ base /*[B][T]*/) {
   extern __shared__ unsigned s_hist[];
   const int num_tiles = tiles_x * tiles_y, words = (num_tiles + 1) >> 1;
-  for (int i = threadIdx.x; i < words; i += BD_THREADS) s_hist[i] = 0u;
+  for (int i = threadIdx.x; i < words; i += BLK_THREADS) s_hist[i] = 0u;
   __syncthreads();
   const int g0 = blockIdx.x * per_block, g1 = min(n, g0 + per_block);
-  for (int g = g0 + threadIdx.x; g < g1; g += BD_THREADS) {
+  for (int g = g0 + threadIdx.x; g < g1; g += BLK_THREADS) {
     const int r = radii[g];
     u64 mask = 0ull;
     if (r > 0)
@@ -180,36 +182,57 @@ bin_count_blocks_kernel(int n, int per_block, const float2 *__restrict__ xys, co
   }
   __syncthreads();
   unsigned *row = base + (size_t)blockIdx.x * num_tiles;
-  for (int t = threadIdx.x; t < num_tiles; t += BD_THREADS) row[t] = (s_hist[t >> 1] >> ((t & 1) * 16)) & 0xffffu;
+  for (int t = threadIdx.x; t < num_tiles; t += BLK_THREADS) row[t] = (s_hist[t >> 1] >> ((t & 1) * 16)) & 0xffffu;
 }
 
-__global__ void __launch_bounds__(BD_THREADS)
+// exclusive prefix of every column of base [B][T] over the blocks, in place; column totals -> tile_count.
+// CTA = 32 columns x 32 row chunks: coalesced 128-byte rows, the chunk sums are scanned through shared memory.
+__global__ void __launch_bounds__(1024)
 bin_colscan_kernel(int num_blocks, int num_tiles, unsigned *__restrict__ base, unsigned *__restrict__ tile_count) {
-  const int t = blockIdx.x * BD_THREADS + threadIdx.x;
-  if (t >= num_tiles) return;
-  unsigned run = 0;
-#pragma unroll 4
-  for (int b = 0; b < num_blocks; ++b) {
-    const size_t i = (size_t)b * num_tiles + t;
-    const unsigned c = base[i];
-    base[i] = run;
-    run += c;
+  __shared__ unsigned s_sum[32][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int t = blockIdx.x * 32 + cx;
+  const int per = (num_blocks + 31) / 32;
+  const int b0 = min(num_blocks, ry * per), b1 = min(num_blocks, b0 + per);
+  unsigned sum = 0;
+  if (t < num_tiles)
+    for (int b = b0; b < b1; ++b) sum += base[(size_t)b * num_tiles + t];
+  s_sum[ry][cx] = sum;
+  __syncthreads();
+  if (ry == 0) {  // one warp: thread cx scans its column's 32 chunk sums
+    unsigned run = 0;
+#pragma unroll
+    for (int y = 0; y < 32; ++y) {
+      const unsigned v = s_sum[y][cx];
+      s_sum[y][cx] = run;
+      run += v;
+    }
+    if (t < num_tiles) tile_count[t] = run;
   }
-  tile_count[t] = run;
+  __syncthreads();
+  if (t < num_tiles) {
+    unsigned run = s_sum[ry][cx];
+    for (int b = b0; b < b1; ++b) {
+      const size_t i = (size_t)b * num_tiles + t;
+      const unsigned c = base[i];
+      base[i] = run;
+      run += c;
+    }
+  }
 }
 
-__global__ void __launch_bounds__(BD_THREADS)
+__global__ void __launch_bounds__(BLK_THREADS)
 bin_fill_blocks_kernel(int n, int per_block, const float2 *__restrict__ xys, const float *__restrict__ depths,
                        const int *__restrict__ radii, const float *__restrict__ conics, const float *__restrict__ opacities,
                        const u64 *__restrict__ masks, int tiles_x, int tiles_y, int block_width, int capacity,
                        const unsigned *__restrict__ tile_start, const unsigned *__restrict__ base, u64 *__restrict__ keys) {
   extern __shared__ unsigned s_hist[];
   const int num_tiles = tiles_x * tiles_y, words = (num_tiles + 1) >> 1;
-  for (int i = threadIdx.x; i < words; i += BD_THREADS) s_hist[i] = 0u;
+  for (int i = threadIdx.x; i < words; i += BLK_THREADS) s_hist[i] = 0u;
   __syncthreads();
   const unsigned *row = base + (size_t)blockIdx.x * num_tiles;
   const int g0 = blockIdx.x * per_block, g1 = min(n, g0 + per_block);
-  for (int g = g0 + threadIdx.x; g < g1; g += BD_THREADS) {
+  for (int g = g0 + threadIdx.x; g < g1; g += BLK_THREADS) {
     const int r = radii[g];
     if (r <= 0) continue;
     u64 mask = masks[g];
@@ -230,14 +253,13 @@ __device__ __forceinline__ void warp_bitonic_sort(u64 (&k)[E], int lane) {
   const unsigned full = 0xffffffffu;
   for (int k2 = 2; k2 <= 32 * E; k2 <<= 1) {
     for (int j = k2 >> 1; j >= E; j >>= 1) {
+      // partner lane = lane ^ (j / E); k2 >= 2 E here, so the direction bit of element lane * E + r does not depend on r
       const int lm = j / E;
-      const bool lower = (lane & lm) == 0;
+      const bool take_min = ((lane & lm) == 0) == (((lane * E) & k2) == 0);
 #pragma unroll
       for (int r = 0; r < E; ++r) {
         const u64 other = __shfl_xor_sync(full, k[r], lm);
-        const bool up = ((lane * E + r) & k2) == 0;
-        const u64 lo = k[r] < other ? k[r] : other, hi = k[r] < other ? other : k[r];
-        k[r] = (lower == up) ? lo : hi;
+        if ((k[r] > other) == take_min) k[r] = other;
       }
     }
 #pragma unroll
@@ -248,9 +270,10 @@ __device__ __forceinline__ void warp_bitonic_sort(u64 (&k)[E], int lane) {
           if ((r & jj) == 0) {
             const bool up = ((lane * E + r) & k2) == 0;
             const u64 a = k[r], b = k[r | jj];
-            const bool sw = (a > b) == up;
-            k[r] = sw ? b : a;
-            k[r | jj] = sw ? a : b;
+            if ((a > b) == up) {
+              k[r] = b;
+              k[r | jj] = a;
+            }
           }
         }
       }
@@ -416,7 +439,7 @@ inline void block_partition(int num_points, int num_tiles, int &per_block, int &
   per_block = num_blocks = 0;
   if (num_tiles > SMEM_HIST_MAX_TILES || num_points <= 0) return;
   long long per = ((long long)num_points + 295) / 296;
-  per = ((per + BD_THREADS - 1) / BD_THREADS) * BD_THREADS;
+  per = ((per + 1023) / 1024) * 1024;
   if (per < 2048) per = 2048;
   if (per > 65280) per = 65280;
   per_block = (int)per;
@@ -456,11 +479,11 @@ int run_count(int num_points, const float *xys, const int32_t *radii, const floa
       GSR_CUDA(cudaFuncSetAttribute(bin_count_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       GSR_CUDA(cudaFuncSetAttribute(bin_fill_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
-    bin_count_blocks_kernel<<<L.num_blocks, BD_THREADS, smem, st>>>(
+    bin_count_blocks_kernel<<<L.num_blocks, BLK_THREADS, smem, st>>>(
         num_points, L.per_block, reinterpret_cast<const float2 *>(xys), radii, conics, opacities, tiles_x, tiles_y,
         (int)block_width, L.masks, L.base);
     GSR_CHECK_LAUNCH("bin_count_blocks_kernel");
-    bin_colscan_kernel<<<cdiv(num_tiles, BD_THREADS), BD_THREADS, 0, st>>>(L.num_blocks, num_tiles, L.base, L.tile_count);
+    bin_colscan_kernel<<<cdiv(num_tiles, 32), 1024, 0, st>>>(L.num_blocks, num_tiles, L.base, L.tile_count);
     GSR_CHECK_LAUNCH("bin_colscan_kernel");
   } else {
     GSR_CUDA(cudaMemsetAsync(L.tile_count, 0, sizeof(unsigned) * (size_t)num_tiles, st));
@@ -483,7 +506,7 @@ int run_fill_sort(int num_points, const float *xys, const float *depths, const i
   const int num_tiles = tiles_x * tiles_y;
   if (L.num_blocks > 0) {
     const size_t smem = sizeof(unsigned) * (size_t)((num_tiles + 1) >> 1);
-    bin_fill_blocks_kernel<<<L.num_blocks, BD_THREADS, smem, st>>>(
+    bin_fill_blocks_kernel<<<L.num_blocks, BLK_THREADS, smem, st>>>(
         num_points, L.per_block, reinterpret_cast<const float2 *>(xys), depths, radii, conics, opacities, L.masks, tiles_x,
         tiles_y, (int)block_width, capacity, L.cursors, L.base, L.keys);
     GSR_CHECK_LAUNCH("bin_fill_blocks_kernel");
