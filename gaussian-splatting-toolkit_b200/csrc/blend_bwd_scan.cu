@@ -10,9 +10,9 @@
 //                              pixels of the block.  The nine gradient sums are private registers (no reduction, one set
 //                              of REDs per 32 visits); what crosses lanes is the per-pixel state, and that is a PREFIX
 //                              SCAN over the lanes: the transmittance behind Gaussian j is T_in * prod_{i<=j} 1/(1-alpha_i)
-//                              (back to front), the colour sum behind it a prefix sum — two warp-shuffle scans
-//                              (10 SHFL + 10 ALU) per pixel step, with the per-pixel carry (T, s) kept in shared memory
-//                              between groups of 32 survivors.
+//                              (back to front), the colour sum behind it a prefix sum; both come out of ONE warp-shuffle
+//                              scan of affine maps (10 SHFL + 15 ALU per pixel step, five dependent steps), with the
+//                              per-pixel carry (T, s) kept in shared memory between groups of 32 survivors.
 //
 // The per-pixel colour bookkeeping of the reference (three running sums S_c and three v_out terms,
 // backward.cu:243-262) collapses to ONE scalar because the upstream gradient is constant per pixel:
@@ -69,7 +69,11 @@ __device__ __forceinline__ void process_group(const LaneGaussian &G, const float
       c[u] = pixc[p + u];
       st[u] = pixs[p + u];
     }
-    float dx[U], dy[U], vis_e[U], alpha_e[U], ra[U], R[U], T[U], fac[U], dj[U], cj[U], S[U];
+    // Per Gaussian the pixel state (T, s) moves by an AFFINE map:  T <- ra T,  s <- s + (alpha ra d) T  (T on the right is
+    // the transmittance BEFORE the Gaussian).  Maps compose associatively, (R_a, C_a) then (R_b, C_b) = (R_a R_b,
+    // C_a + C_b R_a), so ONE inclusive scan of the pair (R, C) over the lanes gives both the transmittance and the colour
+    // sum in front of every Gaussian — five dependent shuffle steps instead of two scans of five.
+    float dx[U], dy[U], vis_e[U], alpha_e[U], ra[U], R[U], Cc[U], dj[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       dx[u] = G.x - st[u].x;
@@ -82,44 +86,37 @@ __device__ __forceinline__ void process_group(const LaneGaussian &G, const float
       alpha_e[u] = valid ? alpha : 0.f;
       vis_e[u] = valid ? vis : 0.f;
       ra[u] = 1.f / (1.f - alpha_e[u]);
-      R[u] = ra[u];
-    }
-    // inclusive product scans over the lanes (lane order = back to front): R_j = prod_{i<=j} ra_i
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      float up[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) up[u] = __shfl_up_sync(full, R[u], d);
-#pragma unroll
-      for (int u = 0; u < U; ++u)
-        if (lane >= d) R[u] *= up[u];
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      T[u] = st[u].z * R[u];  // transmittance in front of this Gaussian
-      fac[u] = alpha_e[u] * T[u];
       dj[u] = G.r * c[u].x + G.g * c[u].y + G.b * c[u].z;
-      cj[u] = fac[u] * dj[u];
-      S[u] = cj[u];
+      R[u] = ra[u];
+      Cc[u] = alpha_e[u] * ra[u] * dj[u];
     }
-    // inclusive sum scans: S_j = sum_{i<=j} alpha_i T_i d_i
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-      float up[U];
+      float rup[U], cup[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) up[u] = __shfl_up_sync(full, S[u], d);
+      for (int u = 0; u < U; ++u) {
+        rup[u] = __shfl_up_sync(full, R[u], d);
+        cup[u] = __shfl_up_sync(full, Cc[u], d);
+      }
 #pragma unroll
       for (int u = 0; u < U; ++u)
-        if (lane >= d) S[u] += up[u];
+        if (lane >= d) {
+          Cc[u] = cup[u] + Cc[u] * rup[u];
+          R[u] *= rup[u];
+        }
     }
+    float T[U], s_after[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const float s_behind = st[u].w + (S[u] - cj[u]);
+      T[u] = st[u].z * R[u];                    // transmittance in front of this Gaussian
+      s_after[u] = st[u].w + Cc[u] * st[u].z;   // colour sum including this Gaussian
+      const float fac = alpha_e[u] * T[u];
+      const float s_behind = s_after[u] - fac * dj[u];
       const float v_alpha = T[u] * dj[u] - ra[u] * s_behind;
       const float w = vis_e[u] * v_alpha;
-      a_r += fac[u] * c[u].x;
-      a_g += fac[u] * c[u].y;
-      a_b += fac[u] * c[u].z;
+      a_r += fac * c[u].x;
+      a_g += fac * c[u].y;
+      a_b += fac * c[u].z;
       const float wdx = w * dx[u], wdy = w * dy[u];
       a_xx += wdx * dx[u];
       a_xy += wdx * dy[u];
@@ -130,7 +127,7 @@ __device__ __forceinline__ void process_group(const LaneGaussian &G, const float
     }
     if (lane == 31) {  // carry to the next group
 #pragma unroll
-      for (int u = 0; u < U; ++u) *reinterpret_cast<float2 *>(&pixs[p + u].z) = make_float2(T[u], st[u].w + S[u]);
+      for (int u = 0; u < U; ++u) *reinterpret_cast<float2 *>(&pixs[p + u].z) = make_float2(T[u], s_after[u]);
     }
   }
   __syncwarp();

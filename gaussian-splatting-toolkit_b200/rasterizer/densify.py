@@ -222,6 +222,7 @@ def refinement_after(params: Dict[str, Tensor], optimizers: Optional[GaussianOpt
             _lib.check(_lib.load().gsr_opacity_reset(op.numel(), float(max_logit), _ptr(op),
                                                      _ptr(m) if m is not None else null,
                                                      _ptr(v) if v is not None else null, st), "opacity_reset")
+            torch.autograd.graph.increment_version(op)  # written through a raw pointer (see optim.py)
         info["opacity_reset"] = 1
     stats.reset()  # :491-493
     return info

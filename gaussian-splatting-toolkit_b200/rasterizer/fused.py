@@ -51,6 +51,11 @@ def render_gaussians(means3d: Tensor, scales: Tensor, quats: Tensor, features_dc
     assert block_width > 1 and block_width <= 16, "block_width must be between 2 and 16"
     if rasterize_mode not in ("classic", "antialiased"):
         raise ValueError("Unknown rasterize_mode: %s" % rasterize_mode)   # vanilla_gs.py:817-818
+    if features_rest.dim() != 3 or features_rest.shape[1] == 0:
+        # sh_degree = 0 models colour with sigmoid(features_dc) (vanilla_gs.py:808), not with the SH band + 0.5 clamp this
+        # operator fuses: refuse instead of silently rendering different colours than the separate operators
+        raise ValueError("render_gaussians needs at least one SH band beyond dc (features_rest [N,K-1,3], K >= 4); "
+                         "for sh_degree = 0 models use project_gaussians + rasterize_gaussians with sigmoid colours")
     if background is None:
         background = torch.ones(3, dtype=torch.float32, device=means3d.device)
     assert background.shape[0] == 3, "incorrect shape of background color tensor, expected shape 3"

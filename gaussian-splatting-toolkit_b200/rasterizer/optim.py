@@ -118,6 +118,10 @@ class GaussianOptimizers:
             _lib.check(_lib.load().gsr_adam_step_multi(n, ps, gs, ms, vs, numels, lrs, steps, self.betas[0],
                                                        self.betas[1], self.eps, float(grad_scale), stream),
                        "adam_step_multi")
+        # the kernel wrote through raw pointers: bump the autograd version counters, so that anything keyed on them (the
+        # binning cache of rasterize.py, autograd's saved-tensor check) sees the parameters as modified
+        for name, p, _ in names:
+            torch.autograd.graph.increment_version(p)
 
     step = optimizer_step_all
 

@@ -18,7 +18,7 @@ def _cases():
         "3k_120x90_bw8_deg2of3_rot": lambda: make_scene(3000, 120, 90, 0.03, 0.3, margin=1.0, seed=62, block_width=8,
                                                          degrees_to_use=2,
                                                          viewmat=look_at_viewmat(yaw_deg=14.0, pitch_deg=-6.0, shift=(0.1, 0.0, 0.2))),
-        "1k_64x64_deg0": lambda: make_scene(1000, 64, 64, 0.05, 0.3, margin=0.9, seed=63, sh_degree=0),
+        "1k_64x64_deg1": lambda: make_scene(1000, 64, 64, 0.05, 0.3, margin=0.9, seed=63, sh_degree=1),
         "2k_96x64_deg4_opaque": lambda: make_scene(2000, 96, 64, 0.08, 0.5, margin=0.9, seed=64, sh_degree=4),
     }
 
@@ -170,3 +170,15 @@ def test_fused_render_vs_reference_cuda_golden():
                    v_features_rest=p["features_rest"].grad)
         for k, v in got.items():
             assert_float_parity(to_np(v).reshape(z["ref_" + k].shape), z["ref_" + k], k, max_norm_rel=5e-5, max_frac_bad=5e-4)
+
+
+def test_fused_render_refuses_sh_degree_zero_models():
+    """sh_degree = 0 models colour with sigmoid(features_dc) (vanilla_gs.py:808), which the fused operator does not
+    implement: it must say so instead of rendering SH-band-0 + 0.5 colours."""
+    from rasterizer.fused import render_gaussians
+
+    n = 16
+    z = lambda *s: torch.zeros(*s, device="cuda")
+    with pytest.raises(ValueError, match="sh_degree = 0"):
+        render_gaussians(z(n, 3), z(n, 3), torch.ones(n, 4, device="cuda"), z(n, 3), z(n, 0, 3), z(n, 1),
+                         torch.eye(4, device="cuda"), torch.eye(4, device="cuda"), 50.0, 50.0, 16.0, 16.0, 32, 32, 0)

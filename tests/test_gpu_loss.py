@@ -57,3 +57,22 @@ def test_l1_ssim_loss_errors_and_determinism():
     assert torch.equal(x, y)
     same = l1_ssim_loss(a.cuda(), a.cuda())
     assert abs(float(same)) < 1e-6     # identical images: L1 = 0, SSIM = 1
+
+
+def test_l1_ssim_kernels_vs_vendor_free_known_answers():
+    """The CUDA loss against tests/golden/ssim_kat.npz: SSIM / L1 values produced by an independent numpy + scipy float64
+    implementation of the published algorithm (Wang et al. 2004; tests/golden/gen_golden_ssim.py) — the pin that replaces
+    the absent pytorch_msssim package."""
+    import os
+
+    from rasterizer.losses import l1_ssim_loss
+
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ssim_kat.npz"))
+    for name in ("noise_32x40", "noisy_copy_48x36", "blurred_edge_40x40", "dark_vs_bright_24x24"):
+        gt, pred = torch.from_numpy(z[name + "_x"]).cuda(), torch.from_numpy(z[name + "_y"]).cuda()
+        loss, l1, ssim = l1_ssim_loss(pred, gt, 0.2, return_terms=True)
+        want_s, want_l1 = float(z[name + "_ssim"]), float(z[name + "_l1"])
+        print(f"[ssim KAT {name}] ssim {float(ssim):.8f} (golden {want_s:.8f})  l1 {float(l1):.8f} (golden {want_l1:.8f})")
+        assert abs(float(ssim) - want_s) <= 2e-5 * abs(want_s) + 2e-6
+        assert abs(float(l1) - want_l1) <= 1e-5 * want_l1 + 1e-7
+        assert abs(float(loss) - (0.8 * want_l1 + 0.2 * (1 - want_s))) <= 1e-5
