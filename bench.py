@@ -668,6 +668,8 @@ def main():
     for _ in range(args.warmup):
         resident_step()
     recording["on"] = True
+    if exchange is not None:
+        exchange.timing = True
     sampler.start()
     lib = _lib.load()
     launches0 = int(lib.gsr_launch_count())
@@ -675,6 +677,8 @@ def main():
     launches = int(lib.gsr_launch_count()) - launches0
     clocks = sampler.stop()
     recording["on"] = False
+    if exchange is not None:
+        exchange.timing = False
     ms_per_step = ms_total / args.steps
     value = world * args.steps / (ms_total * 1e-3)
     stages = rv.stage_ms()
@@ -684,6 +688,8 @@ def main():
     if ar_events:
         stages["grad_exchange_tail(allreduce 11N + join of the %s SH adjoint started after blend_bwd)" % ("NVLink-peer-load" if peer is not None else "NCCL-allgather")] = (
             sum(a.elapsed_time(b) for a, b in ar_events) / len(ar_events))
+    if exchange is not None and exchange.peer is not None:
+        stages["grad_exchange_breakdown"] = exchange.breakdown_ms()
     M = rv.M
     with torch.no_grad():
         _nth = rv.C.project_gaussians_forward(N, s["means3d"], s["scales"], s["glob_scale"], s["quats"], s["viewmat"],

@@ -130,23 +130,69 @@ def _rotation_matrix(a: np.ndarray, b: np.ndarray) -> np.ndarray:
     return (np.eye(3, dtype=np.float32) + K + (K @ K) * ((1 - c) / (s ** 2 + 1e-8))).astype(np.float32)
 
 
+def focus_of_attention(poses: np.ndarray, initial_focus: np.ndarray) -> np.ndarray:
+    """camera_utils.py:496-549: the point closest to the optical axes of the cameras that have it in front of them
+    (iterated until the set of such cameras stops changing).  poses [n,4,4] / [n,3,4] camera-to-world, float32."""
+    dirs = -poses[:, :3, 2:3]
+    origins = poses[:, :3, 3:4]
+    focus = np.asarray(initial_focus, dtype=np.float32)
+    active = np.sum(dirs[..., 0] * (focus - origins[..., 0]), axis=-1) > 0
+    done = False
+    while int(active.sum()) > 1 and not done:
+        dirs, origins = dirs[active], origins[active]
+        m = np.eye(3, dtype=np.float32) - dirs * np.transpose(dirs, (0, 2, 1))
+        mt_m = np.transpose(m, (0, 2, 1)) @ m
+        focus = (np.linalg.inv(mt_m.mean(0)) @ (mt_m @ origins).mean(0)[:, 0]).astype(np.float32)
+        active = np.sum(dirs[..., 0] * (focus - origins[..., 0]), axis=-1) > 0
+        if active.all():
+            done = True
+    return focus
+
+
 def auto_orient_and_center_poses(poses: np.ndarray, method: str = "up", center_method: str = "poses"):
-    """camera_utils.py:552-668 for the methods the reference's dataparser uses by default ("up" / "none" orientation,
-    "poses" / "none" centring).  poses: [n,4,4] or [n,3,4] camera-to-world.  Returns (poses [n,3,4], transform [3,4])."""
+    """camera_utils.py:552-660: orientation "pca" | "up" | "vertical" | "none", centring "poses" | "focus" | "none".
+    poses: [n,4,4] or [n,3,4] camera-to-world.  Returns (poses [n,3,4], transform [3,4]); float32 arithmetic like the
+    reference."""
     poses = np.asarray(poses, dtype=np.float32)
     if poses.shape[-2] == 3:
         poses = np.concatenate([poses, np.tile(np.array([[[0, 0, 0, 1]]], np.float32), (poses.shape[0], 1, 1))], axis=1)
     origins = poses[:, :3, 3]
     mean_origin = origins.mean(axis=0)
+    translation_diff = origins - mean_origin
     if center_method == "poses":
         translation = mean_origin
+    elif center_method == "focus":
+        translation = focus_of_attention(poses, mean_origin)
     elif center_method == "none":
         translation = np.zeros_like(mean_origin)
     else:
-        raise NotImplementedError(f"center_method {center_method!r} (only 'poses' and 'none')")
-    if method == "up":
+        raise ValueError(f"Unknown value for center_method: {center_method}")
+    if method == "pca":
+        # eigenvectors are defined up to sign and the reference uses them as LAPACK returns them: same routine
+        # (torch.linalg.eigh) so that the same signs come out
+        _, eigvec_t = torch.linalg.eigh(torch.from_numpy(np.ascontiguousarray(translation_diff.T @ translation_diff)))
+        eigvec = np.ascontiguousarray(eigvec_t.numpy()[:, ::-1])  # largest principal direction first (torch.flip, :603)
+        if np.linalg.det(eigvec) < 0:
+            eigvec[:, 2] = -eigvec[:, 2]
+        # NOTE the reference multiplies by `eigvec` itself, not its transpose (:608) — reproduced
+        transform = np.concatenate([eigvec, eigvec @ -translation[:, None]], axis=-1)
+        oriented = transform @ poses
+        if oriented.mean(axis=0)[2, 1] < 0:
+            oriented[:, 1:3] = -1 * oriented[:, 1:3]
+    elif method in ("up", "vertical"):
         up = poses[:, :3, 1].mean(axis=0)
         up = up / np.linalg.norm(up)
+        if method == "vertical":
+            # the 3-D direction that projects most vertically in all cameras: total least squares ||X u|| -> min
+            # over the cameras' x axes (:616-647)
+            _, S_t, Vh_t = torch.linalg.svd(torch.from_numpy(np.ascontiguousarray(poses[:, :3, 0])), full_matrices=False)
+            S, Vh = S_t.numpy(), Vh_t.numpy()
+            if S[1] > 0.17 * math.sqrt(poses.shape[0]):
+                up_vertical = Vh[2, :]
+                up = up_vertical if np.dot(up_vertical, up) > 0 else -up_vertical
+            else:  # degenerate configuration: project "up" on the plane orthogonal to the first singular vector
+                up = up - Vh[0, :] * np.dot(up, Vh[0, :])
+                up = up / np.linalg.norm(up)
         rotation = _rotation_matrix(up, np.array([0, 0, 1], np.float32))
         transform = np.concatenate([rotation, rotation @ -translation[:, None]], axis=-1)
         oriented = transform @ poses
@@ -156,7 +202,7 @@ def auto_orient_and_center_poses(poses: np.ndarray, method: str = "up", center_m
         transform = transform[:3, :]
         oriented = transform @ poses
     else:
-        raise NotImplementedError(f"orientation method {method!r} (only 'up' and 'none')")
+        raise ValueError(f"Unknown value for method: {method}")
     return oriented.astype(np.float32), transform.astype(np.float32)
 
 

@@ -235,6 +235,29 @@ class GradientExchange:
         self.bucket, self.means3d, self.degree, self.peer, self.group = bucket, means3d, degree, peer, group
         self.side = torch.cuda.Stream(means3d.device) if peer is not None else None
         self._pending = None
+        # optional per-component device timing (bench.py): lists of CUDA-event tuples, see breakdown_ms()
+        self.timing = False
+        self._ev_side, self._ev_main = [], []
+
+    def _ev(self):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def breakdown_ms(self) -> Dict[str, float]:
+        """Average device times of the exchange's components over the timed calls (call after a synchronize):
+        side stream = publish colour gradients + 'all published' barrier, then the peer-load multi-view SH adjoint;
+        main stream = NCCL all-reduce of the 11 N other floats, then the join with the side stream + 'all consumed' barrier."""
+        out = {}
+        if self._ev_side:
+            n = len(self._ev_side)
+            out["side.publish_and_barrier"] = sum(a.elapsed_time(b) for a, b, _ in self._ev_side) / n
+            out["side.sh_adjoint_multiview_peer_loads"] = sum(b.elapsed_time(c) for _, b, c in self._ev_side) / n
+        if self._ev_main:
+            n = len(self._ev_main)
+            out["main.nccl_allreduce_11N"] = sum(a.elapsed_time(b) for a, b, _ in self._ev_main) / n
+            out["main.join_side_and_barrier"] = sum(b.elapsed_time(c) for _, b, c in self._ev_main) / n
+        return out
 
     def start_sh(self, v_rgb_sh: torch.Tensor, cam_pos: torch.Tensor, degrees_to_use: int) -> None:
         from . import cuda as _C
@@ -245,13 +268,17 @@ class GradientExchange:
         peer, cur = self.peer, torch.cuda.current_stream()
         self.side.wait_stream(cur)
         with torch.cuda.stream(self.side):
+            e0 = self._ev() if self.timing else None
             if v_rgb_sh.data_ptr() != peer.local_rgb.data_ptr():
                 peer.local_rgb.copy_(v_rgb_sh)
                 v_rgb_sh.record_stream(self.side)
             peer.local_cam.copy_(cam_pos.reshape(3))
             peer.hdl.barrier(channel=0)
+            e1 = self._ev() if self.timing else None
             _C.compute_sh_backward_multiview(self.degree, degrees_to_use, self.means3d, peer.peer_cam, peer.peer_rgb,
                                              out=self.bucket["v_coeffs"])
+            if self.timing:
+                self._ev_side.append((e0, e1, self._ev()))
 
     def finish(self, average: bool = False) -> None:
         bucket = self.bucket
@@ -261,9 +288,13 @@ class GradientExchange:
             exchange_gradients(bucket, v_rgb_sh, self.means3d, cam_pos, self.degree, degrees_to_use, self.group, average)
             return
         hi = bucket.offsets["v_coeffs"][1]
+        e0 = self._ev() if self.timing else None
         dist.all_reduce(bucket.flat[hi:], group=self.group)
+        e1 = self._ev() if self.timing else None
         torch.cuda.current_stream().wait_stream(self.side)
         self.peer.hdl.barrier(channel=1)
+        if self.timing:
+            self._ev_main.append((e0, e1, self._ev()))
         if average:
             bucket.flat.div_(dist.get_world_size(self.group))
 

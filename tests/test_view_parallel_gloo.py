@@ -89,3 +89,22 @@ def test_bucket_layout_is_contiguous_and_aligned():
         assert b[name].data_ptr() == b.flat.data_ptr() + 4 * lo and b[name].is_contiguous()
         end = hi
     assert end == b.flat.numel()
+
+
+def test_gradient_bucket_segments_are_16_byte_aligned_for_any_n():
+    """after densification N is arbitrary (odd); the projection adjoint needs a 16-byte aligned v_quat
+    segment, so every segment offset is padded to a multiple of 4 floats."""
+    import torch
+
+    from rasterizer.view_parallel import SEGMENTS, GradientBucket, segment_shapes
+
+    for n in (1, 7, 1001, 33_149):
+        b = GradientBucket(n, sh_bases=16, device="cpu")
+        shapes = segment_shapes(n, 16)
+        for name in SEGMENTS:
+            lo, hi = b.offsets[name]
+            assert lo % 4 == 0 and (b[name].data_ptr() - b.flat.data_ptr()) == 4 * lo
+            assert tuple(b[name].shape) == shapes[name] and hi - lo == b[name].numel()
+        b["v_quat"].fill_(1.0)
+        b["v_opacity"].fill_(2.0)
+        assert float(b.flat.sum()) == 4.0 * n + 2.0 * n  # segments do not overlap, padding stays zero
