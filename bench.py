@@ -54,6 +54,8 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg4"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--only-resident", action="store_true", help="profiling aid: only the resident leg (no graph / e2e / "
+                    "fused / reference-extension legs); the JSON line is tagged diagnostic")
     ap.add_argument("--cpu-budget-s", type=float, default=200.0, help="wall-clock bound of the reference arm")
     return ap.parse_args()
 
@@ -700,7 +702,7 @@ def main():
     # the same resident view as ONE CUDA graph (N = 1): possible because no kernel's grid depends on the pair count and
     # nothing in the view reads the device from the host (asynchronous binning); replayed back to back
     graph_leg = None
-    if world == 1 and os.environ.get("GSR_BENCH_GRAPH", "1") != "0":
+    if world == 1 and os.environ.get("GSR_BENCH_GRAPH", "1") != "0" and not args.only_resident:
         try:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
@@ -734,6 +736,13 @@ def main():
     def e2e_step():
         pv.step()
 
+    if args.only_resident:
+        if rank == 0:
+            print(json.dumps({"diagnostic": "--only-resident", "value": value, "ms_per_step": ms_per_step, "stages_ms": stages,
+                              "gpu_launches": launches}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
     e2e_ms = timed_loop(torch, dist, world, e2e_step, args.steps, args.warmup, finish=pv.finish)
     e2e_value = world * args.steps / (e2e_ms * 1e-3)
     _binning.check()  # every asynchronous call of the e2e leg stayed within its pair-buffer capacity (raises otherwise)

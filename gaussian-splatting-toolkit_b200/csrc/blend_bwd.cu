@@ -206,207 +206,8 @@ blend_backward_kernel(int tiles_x, int img_w, int img_h, int block_width,
   }
 }
 
-// ---- sub-warp units (experimental; 16x16 tiles only) ------------------------------------------------
-// Sum 8 per-lane values over the UL = 16 or 8 consecutive lanes of a unit.  UL = 16: lane k (k = lane & 15) with
-// (k & 1) == 0 holds the total of value ((k>>3)&1)*4 + ((k>>2)&1)*2 + ((k>>1)&1);  UL = 8: lane k = lane & 7 holds the
-// total of value k.
-template <int UL>
-__device__ __forceinline__ float unit_transpose_reduce8(float v[8], int lane) {
-  const unsigned full = 0xffffffffu;
-  constexpr int O4 = UL / 2, O2 = UL / 4, O1 = UL / 8;  // xor offsets of the three transposing stages
-  {
-    const bool hi = lane & O4;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float send = hi ? v[i] : v[i + 4];
-      const float keep = hi ? v[i + 4] : v[i];
-      v[i] = keep + __shfl_xor_sync(full, send, O4);
-    }
-  }
-  {
-    const bool hi = lane & O2;
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const float send = hi ? v[i] : v[i + 2];
-      const float keep = hi ? v[i + 2] : v[i];
-      v[i] = keep + __shfl_xor_sync(full, send, O2);
-    }
-  }
-  {
-    const bool hi = lane & O1;
-    const float send = hi ? v[0] : v[1];
-    const float keep = hi ? v[1] : v[0];
-    v[0] = keep + __shfl_xor_sync(full, send, O1);
-  }
-  if (UL == 16) v[0] += __shfl_xor_sync(full, v[0], 1);
-  return v[0];
-}
-
-template <int UL>
-__device__ __forceinline__ float unit_sum(float x) {
-  const unsigned full = 0xffffffffu;
-#pragma unroll
-  for (int o = UL / 2; o > 0; o >>= 1) x += __shfl_xor_sync(full, x, o);
-  return x;
-}
-
-template <int UNITS>
-__global__ void __launch_bounds__(BLEND_THREADS)
-blend_backward_units_kernel(int tiles_x, int img_w, int img_h, const int *__restrict__ gaussian_ids_sorted,
-                            const int2 *__restrict__ tile_bins, const float2 *__restrict__ xys,
-                            const float *__restrict__ conics, const float *__restrict__ colors,
-                            const float *__restrict__ opacities, const float *__restrict__ background,
-                            const float *__restrict__ final_Ts, const int *__restrict__ final_idx,
-                            const float *__restrict__ v_output, const float *__restrict__ v_output_alpha,
-                            float *__restrict__ v_xy, float *__restrict__ v_conic, float *__restrict__ v_colors,
-                            float *__restrict__ v_opacity) {
-  __shared__ float4 s_rec[2][3][BLEND_THREADS];
-  __shared__ unsigned char s_list[BLEND_THREADS / 32][UNITS][BLEND_THREADS];
-  __shared__ int s_warp_max[BLEND_THREADS / 32];
-  constexpr int UL = 32 / UNITS;
-
-  const unsigned full = 0xffffffffu;
-  const int tile_x = blockIdx.x, tile_y = blockIdx.y;
-  const int tile_id = tile_y * tiles_x + tile_x;
-  const int tr = threadIdx.x, nthreads = BLEND_THREADS, lane = tr & 31, warp = tr >> 5;
-  const int unit = lane / UL, k = lane % UL;
-  const unsigned unit_mask = ((UL == 32) ? 0xffffffffu : ((1u << UL) - 1u)) << (unit * UL);
-  int lx, ly;
-  map_pixel_units<UNITS>(lx, ly);
-  const int ipx = tile_x * 16 + lx, ipy = tile_y * 16 + ly;
-  const bool inside = (ipx < img_w) && (ipy < img_h);
-  const float px = (float)ipx, py = (float)ipy;
-  const int pix = inside ? (ipy * img_w + ipx) : 0;
-  const int wpx0 = tile_x * 16 + ((warp & 1) << 3), wpy0 = tile_y * 16 + ((warp >> 1) << 2);
-
-  const int2 range = tile_bins[tile_id];
-
-  const float T_final = inside ? final_Ts[pix] : 1.f;
-  float T = T_final;
-  float buf_r = 0.f, buf_g = 0.f, buf_b = 0.f;
-  const int bin_final = inside ? final_idx[pix] : -1;
-  float vo_r = 0.f, vo_g = 0.f, vo_b = 0.f, vo_a = 0.f;
-  if (inside) {
-    vo_r = v_output[3 * (size_t)pix];
-    vo_g = v_output[3 * (size_t)pix + 1];
-    vo_b = v_output[3 * (size_t)pix + 2];
-    vo_a = v_output_alpha[pix];
-  }
-  const float c_final = T_final * (vo_a - (background[0] * vo_r + background[1] * vo_g + background[2] * vo_b));
-
-  const int warp_bin_final = __reduce_max_sync(full, bin_final);
-  if (lane == 0) s_warp_max[warp] = warp_bin_final;
-  __syncthreads();
-  int cta_bin_final = -1;
-  for (int w = 0; w < (nthreads >> 5); ++w) cta_bin_final = max(cta_bin_final, s_warp_max[w]);
-
-  const int end = min(range.y, cta_bin_final + 1);
-  const int count = end - range.x;
-  if (count <= 0) return;  // uniform across the CTA
-  const int num_batches = (count + nthreads - 1) / nthreads;
-
-  // per-lane destination of the reduced totals inside a unit (see unit_transpose_reduce8):
-  //   UL = 16: lanes k = 0,2,..,14 own values 0..7, lane k = 1 owns the ninth (opacity);
-  //   UL = 8 : lane k owns value k, lane k = 0 additionally issues the opacity in a second RED
-  float *dst_base = nullptr;
-  int dst_stride = 0;
-  {
-    int vi;
-    if (UL == 16) vi = (k & 1) == 0 ? (((k >> 3) & 1) * 4 + ((k >> 2) & 1) * 2 + ((k >> 1) & 1)) : (k == 1 ? 8 : -1);
-    else vi = k;
-    if (vi >= 0 && vi < 3) { dst_base = v_colors + vi; dst_stride = 3; }
-    else if (vi >= 3 && vi < 6) { dst_base = v_conic + (vi - 3); dst_stride = 3; }
-    else if (vi >= 6 && vi < 8) { dst_base = v_xy + (vi - 6); dst_stride = 2; }
-    else if (vi == 8) { dst_base = v_opacity; dst_stride = 1; }
-  }
-
-  BlendRecord rec;
-  if (end - 1 - tr >= range.x)
-    rec = gather_record(gaussian_ids_sorted[end - 1 - tr], xys, conics, colors, opacities);
-
-  for (int b = 0; b < num_batches; ++b) {
-    const int buf = b & 1;
-    const int batch_end = end - 1 - nthreads * b;  // sorted index held by slot 0; slot t holds batch_end - t
-    if (batch_end - tr >= range.x) {
-      s_rec[buf][0][tr] = rec.r0;
-      s_rec[buf][1][tr] = rec.r1;
-      s_rec[buf][2][tr] = rec.r2;
-    }
-    __syncthreads();
-    {
-      const int nxt = batch_end - nthreads - tr;
-      if (nxt >= range.x) rec = gather_record(gaussian_ids_sorted[nxt], xys, conics, colors, opacities);
-    }
-    const int batch_size = min(nthreads, batch_end + 1 - range.x);
-    const int t_begin = max(0, batch_end - warp_bin_final);
-    if (t_begin >= batch_size) continue;
-    int n_u[UNITS];
-    compact_survivors_units<UNITS>(s_rec[buf][0], s_rec[buf][1], t_begin, batch_size, wpx0, wpy0, img_w, img_h,
-                                   s_list[warp], lane, n_u);
-    int my_n = n_u[0], n_max = n_u[0];
-#pragma unroll
-    for (int u = 1; u < UNITS; ++u) {
-      my_n = (unit == u) ? n_u[u] : my_n;
-      n_max = max(n_max, n_u[u]);
-    }
-    const unsigned char *my_list = s_list[warp][unit];
-    for (int i = 0; i < n_max; ++i) {
-      const bool act = i < my_n;
-      const int t = act ? my_list[i] : t_begin;  // any staged slot; masked by `act`
-      const float4 q0 = s_rec[buf][0][t];
-      const float4 q1 = s_rec[buf][1][t];
-      const float dx = q0.x - px, dy = q0.y - py;
-      const float gx = q1.x * dx, gy = q1.z * dy;
-      const float power = dx * (gx + q1.y * dy) + gy * dy;
-      const float vis = exp2f(power);
-      const float opac = q1.w;
-      const float alpha = fminf(0.99f, opac * vis);
-      const bool valid = act && inside && (batch_end - t <= bin_final) && !(power > 0.f || alpha < 1.f / 255.f);
-      const unsigned vm = __ballot_sync(full, valid);
-      if (vm == 0u) continue;
-
-      const float alpha_e = valid ? alpha : 0.f;
-      const float vis_e = valid ? vis : 0.f;
-      const float4 q2 = s_rec[buf][2][t];
-      float v[8];
-      const float ra = 1.f / (1.f - alpha_e);
-      T *= ra;
-      const float fac = alpha_e * T;
-      v[0] = fac * vo_r;
-      v[1] = fac * vo_g;
-      v[2] = fac * vo_b;
-      float v_alpha = (q2.x * T - buf_r * ra) * vo_r;
-      v_alpha += (q2.y * T - buf_g * ra) * vo_g;
-      v_alpha += (q2.z * T - buf_b * ra) * vo_b;
-      v_alpha += ra * c_final;
-      buf_r += q2.x * fac;
-      buf_g += q2.y * fac;
-      buf_b += q2.z * fac;
-      const float v_sigma = -opac * vis_e * v_alpha;
-      const float hs = 0.5f * v_sigma;
-      v[3] = hs * dx * dx;
-      v[4] = v_sigma * dx * dy;
-      v[5] = hs * dy * dy;
-      const float ws = -kLn2 * v_sigma;
-      v[6] = ws * (2.f * gx + q1.y * dy);
-      v[7] = ws * (q1.y * dx + 2.f * gy);
-      const float v_opac_l = vis_e * v_alpha;
-      const float tot8 = unit_transpose_reduce8<UL>(v, lane);
-      const float tot_op = unit_sum<UL>(v_opac_l);
-      if ((vm & unit_mask) != 0u) {  // this unit has a contributing pixel (otherwise all its totals are exact zeros)
-        const unsigned g = (unsigned)__float_as_int(q2.w);
-        if (UL == 16) {
-          if (dst_base != nullptr) atomicAdd(dst_base + g * (unsigned)dst_stride, k == 1 ? tot_op : tot8);
-        } else {
-          atomicAdd(dst_base + g * (unsigned)dst_stride, tot8);
-          if (k == 0) atomicAdd(v_opacity + g, tot_op);
-        }
-      }
-    }
-  }
-}
-
-// blend_bwd_scan.cu: the Gaussian-parallel (warp prefix-scan) variant, GSR_BWD_KERNEL=scan
+// blend_bwd_scan.cu: the Gaussian-parallel (warp prefix-scan) adjoint — the default for 16x16 tiles; this file's
+// pixel-parallel kernel serves the other block widths and GSR_BWD_KERNEL=pixel
 int blend_bwd_use_scan();
 int launch_blend_backward_scan(dim3 grid, cudaStream_t st, int img_w, int img_h, const int *gaussian_ids_sorted,
                                const int2 *tile_bins, const float2 *xys, const float *conics, const float *colors,
@@ -446,20 +247,6 @@ extern "C" GSR_API int gsr_rasterize_backward(unsigned img_height, unsigned img_
                                       reinterpret_cast<const int2 *>(tile_bins), reinterpret_cast<const float2 *>(xys),
                                       conics, colors, opacities, background, final_Ts, final_idx, v_output, v_output_alpha,
                                       v_xy, v_conic, v_colors, v_opacity);
-  if (block_width == 16 && blend_units() != 1) {
-    if (blend_units() == 2)
-      blend_backward_units_kernel<2><<<grid, BLEND_THREADS, 0, st>>>(
-          (int)grid.x, (int)img_width, (int)img_height, gaussian_ids_sorted, reinterpret_cast<const int2 *>(tile_bins),
-          reinterpret_cast<const float2 *>(xys), conics, colors, opacities, background, final_Ts, final_idx, v_output,
-          v_output_alpha, v_xy, v_conic, v_colors, v_opacity);
-    else
-      blend_backward_units_kernel<4><<<grid, BLEND_THREADS, 0, st>>>(
-          (int)grid.x, (int)img_width, (int)img_height, gaussian_ids_sorted, reinterpret_cast<const int2 *>(tile_bins),
-          reinterpret_cast<const float2 *>(xys), conics, colors, opacities, background, final_Ts, final_idx, v_output,
-          v_output_alpha, v_xy, v_conic, v_colors, v_opacity);
-    GSR_CHECK_LAUNCH("blend_backward_units_kernel");
-    return GSR_OK;
-  }
   blend_backward_kernel<<<grid, threads, 0, st>>>(
       (int)grid.x, (int)img_width, (int)img_height, (int)block_width, gaussian_ids_sorted,
       reinterpret_cast<const int2 *>(tile_bins), reinterpret_cast<const float2 *>(xys), conics, colors, opacities,

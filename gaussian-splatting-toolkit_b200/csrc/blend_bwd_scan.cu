@@ -150,8 +150,7 @@ __device__ __forceinline__ void process_group(const LaneGaussian &G, const float
 
 }  // namespace
 
-template <int MIN_CTAS>
-__global__ void __launch_bounds__(BLEND_THREADS, MIN_CTAS)
+__global__ void __launch_bounds__(BLEND_THREADS, 3)
 blend_backward_scan_kernel(int tiles_x, int img_w, int img_h, const int *__restrict__ gaussian_ids_sorted,
                            const int2 *__restrict__ tile_bins, const float2 *__restrict__ xys,
                            const float *__restrict__ conics, const float *__restrict__ colors,
@@ -252,12 +251,16 @@ blend_backward_scan_kernel(int tiles_x, int img_w, int img_h, const int *__restr
   }
 }
 
-// GSR_BWD_KERNEL = pixel (default) | scan (3 CTAs / SM) | scan4 (registers capped for 4 CTAs / SM) — read once; A/B switch
+// GSR_BWD_KERNEL = scan (default: this kernel) | pixel (the pixel-parallel kernel of blend_bwd.cu) — read once.
+// Measured at cfg2 on B200 (profiles/r02): pixel-parallel 1.047 ms, this kernel 0.953 ms.  Variants tried and dropped: two
+// separate scans per pixel instead of one affine-map scan (1.22 ms: latency-bound, issue slots 55 % busy); registers
+// capped at 64 for 4 CTAs / SM (0.996 ms); the two pixels of an iteration packed into Blackwell's two-wide FP32
+// instructions (fma.rn.f32x2 / FFMA2: 15 % fewer instructions, but 114 registers -> 2 CTAs / SM and 23 register moves per
+// pixel pair: 1.106 ms).
 int blend_bwd_use_scan() {
   static const int v = [] {
     const char *e = getenv("GSR_BWD_KERNEL");
-    if (!(e && e[0] == 's')) return 0;
-    return (e[1] && e[2] && e[3] && e[4] == '4') ? 4 : 3;
+    return (e && e[0] == 'p') ? 0 : 1;
   }();
   return v;
 }
@@ -267,16 +270,9 @@ int launch_blend_backward_scan(dim3 grid, cudaStream_t st, int img_w, int img_h,
                                const float *opacities, const float *background, const float *final_Ts,
                                const int *final_idx, const float *v_output, const float *v_output_alpha, float *v_xy,
                                float *v_conic, float *v_colors, float *v_opacity) {
-  if (blend_bwd_use_scan() == 4)
-    blend_backward_scan_kernel<4><<<grid, BLEND_THREADS, 0, st>>>((int)grid.x, img_w, img_h, gaussian_ids_sorted, tile_bins,
-                                                                  xys, conics, colors, opacities, background, final_Ts,
-                                                                  final_idx, v_output, v_output_alpha, v_xy, v_conic,
-                                                                  v_colors, v_opacity);
-  else
-    blend_backward_scan_kernel<3><<<grid, BLEND_THREADS, 0, st>>>((int)grid.x, img_w, img_h, gaussian_ids_sorted, tile_bins,
-                                                                  xys, conics, colors, opacities, background, final_Ts,
-                                                                  final_idx, v_output, v_output_alpha, v_xy, v_conic,
-                                                                  v_colors, v_opacity);
+  blend_backward_scan_kernel<<<grid, BLEND_THREADS, 0, st>>>((int)grid.x, img_w, img_h, gaussian_ids_sorted, tile_bins, xys,
+                                                             conics, colors, opacities, background, final_Ts, final_idx,
+                                                             v_output, v_output_alpha, v_xy, v_conic, v_colors, v_opacity);
   GSR_CHECK_LAUNCH("blend_backward_scan_kernel");
   return GSR_OK;
 }

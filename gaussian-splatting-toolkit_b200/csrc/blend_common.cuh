@@ -50,9 +50,6 @@ __device__ __forceinline__ BlendRecord gather_record(int g, const float2 *__rest
   return rec;
 }
 
-// GSR_BLEND_UNITS switch (blend_fwd.cu): 1 = one survivor list per warp (default), 2 / 4 = sub-warp units
-int blend_units();
-
 // thread -> pixel: a warp covers an 8x4 pixel sub-tile for 16x16 tiles, row-major order otherwise
 __device__ __forceinline__ void map_pixel(int block_width, int &lx, int &ly) {
   const int tr = threadIdx.x;
@@ -114,92 +111,6 @@ __device__ __forceinline__ int compact_survivors(const float4 *__restrict__ rec0
   }
   __syncwarp();
   return n;
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// Sub-warp units (experimental): for 16x16 tiles a warp's 8x4 pixel block is split into UNITS blocks of
-// 32 / UNITS pixels, each owned by 32 / UNITS CONSECUTIVE lanes with its OWN survivor list:
-//   UNITS = 2 : two 4x4 blocks (lanes 0-15 left, 16-31 right);  UNITS = 4 : four 4x2 blocks (2 x 2 arrangement).
-// The units walk their lists in lock-step, so a batch costs max(list lengths) iterations instead of the size of the
-// union of the lists (0.86x / 0.79x iterations on the cfg2 scene, tools/sim_halfwarp_units.py).
-template <int UNITS>
-__device__ __forceinline__ void map_pixel_units(int &lx, int &ly) {
-  const int tr = threadIdx.x, w = tr >> 5, l = tr & 31;
-  const int wx0 = (w & 1) << 3, wy0 = (w >> 1) << 2;  // the warp's 8x4 block inside the tile
-  if (UNITS == 2) {
-    const int u = l >> 4, k = l & 15;
-    lx = wx0 + 4 * u + (k & 3);
-    ly = wy0 + (k >> 2);
-  } else {
-    const int u = l >> 3, k = l & 7;
-    lx = wx0 + 4 * (u & 1) + (k & 3);
-    ly = wy0 + 2 * (u >> 1) + (k >> 2);
-  }
-}
-
-// the two conservative tests of compact_survivors for one record against one pixel rectangle (NaN keeps)
-__device__ __forceinline__ bool record_hits_rect(const float4 c, const float4 q, float fx0, float fx1, float fy0,
-                                                 float fy1) {
-  bool hit = !(c.x + c.z < fx0 || c.x - c.z > fx1 || c.y + c.w < fy0 || c.y - c.w > fy1);
-  if (hit && q.x < 0.f) {
-    const float thr = -1.001f * __log2f(255.f * q.w) - 0.01f;
-    const float k = -0.5f * q.y / q.x;
-    const float lo = fx0 - c.x, hi = fx1 - c.x;
-    bool keep = false;
-    for (float fy = fy0; fy <= fy1; fy += 4.f) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float dy = fminf(fy + (float)i, fy1) - c.y;
-        const float dx = fminf(fmaxf(k * dy, lo), hi);
-        const float power = dx * (q.x * dx + q.y * dy) + q.z * dy * dy;
-        keep = keep || !(power < thr);
-      }
-    }
-    hit = keep;
-  }
-  return hit;
-}
-
-// Per-unit compaction: like compact_survivors, but a record that survives the warp's rectangle is then tested against
-// each unit's own rectangle (ux0 = first pixel column of the warp block, uy0 = first row; clipped to the image; an
-// empty rectangle rejects everything) and appended to that unit's list.  n_out[u] = length of unit u's list.
-template <int UNITS>
-__device__ __forceinline__ void compact_survivors_units(const float4 *__restrict__ rec0, const float4 *__restrict__ rec1,
-                                                        int t_begin, int t_end, int wpx0, int wpy0, int img_w, int img_h,
-                                                        unsigned char (*__restrict__ list)[BLEND_THREADS], int lane,
-                                                        int n_out[UNITS]) {
-  constexpr int UW = 4, UH = (UNITS == 2) ? 4 : 2;
-  const unsigned lt_mask = (1u << lane) - 1u;
-  const float wx0 = (float)wpx0, wx1 = (float)min(wpx0 + 7, img_w - 1);
-  const float wy0 = (float)wpy0, wy1 = (float)min(wpy0 + 3, img_h - 1);
-#pragma unroll
-  for (int u = 0; u < UNITS; ++u) n_out[u] = 0;
-  for (int r = t_begin; r < t_end; r += 32) {
-    const int t = r + lane;
-    bool hit_u[UNITS];
-#pragma unroll
-    for (int u = 0; u < UNITS; ++u) hit_u[u] = false;
-    if (t < t_end) {
-      const float4 c = rec0[t];
-      const float4 q = rec1[t];
-      if (record_hits_rect(c, q, wx0, wx1, wy0, wy1)) {
-#pragma unroll
-        for (int u = 0; u < UNITS; ++u) {
-          const int ux = wpx0 + UW * ((UNITS == 2) ? u : (u & 1)), uy = wpy0 + ((UNITS == 2) ? 0 : UH * (u >> 1));
-          if (ux < img_w && uy < img_h)
-            hit_u[u] = record_hits_rect(c, q, (float)ux, (float)min(ux + UW - 1, img_w - 1), (float)uy,
-                                        (float)min(uy + UH - 1, img_h - 1));
-        }
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < UNITS; ++u) {
-      const unsigned m = __ballot_sync(0xffffffffu, hit_u[u]);
-      if (hit_u[u]) list[u][n_out[u] + __popc(m & lt_mask)] = (unsigned char)t;
-      n_out[u] += __popc(m);
-    }
-  }
-  __syncwarp();
 }
 
 }  // namespace gsr

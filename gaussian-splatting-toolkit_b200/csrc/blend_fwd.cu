@@ -17,8 +17,6 @@
 //   * the per-pixel loop is warp-uniform (votes instead of per-lane `break`), so there is no
 //     BSSY/BSYNC reconvergence traffic; exp(-sigma) is one FMUL-free MUFU.EX2 because log2(e) is folded into
 //     the staged conic.
-#include <stdlib.h>
-
 #include "blend_common.cuh"
 
 namespace gsr {
@@ -115,118 +113,6 @@ blend_forward_kernel(int tiles_x, int img_w, int img_h, int block_width,
   }
 }
 
-// Experimental: the same compositing with SUB-WARP UNITS — 16x16 tiles only.  Every unit (16 or 8
-// consecutive lanes = a 4x4 or 4x2 pixel block) has its own survivor list; the units of a warp step through their
-// lists together, lanes of an exhausted unit idle.  Per pixel the arithmetic and the order of contributions are
-// unchanged, so the image is bitwise the one of blend_forward_kernel.
-template <int UNITS>
-__global__ void __launch_bounds__(BLEND_THREADS)
-blend_forward_units_kernel(int tiles_x, int img_w, int img_h, const int *__restrict__ gaussian_ids_sorted,
-                           const int2 *__restrict__ tile_bins, const float2 *__restrict__ xys,
-                           const float *__restrict__ conics, const float *__restrict__ colors,
-                           const float *__restrict__ opacities, const float *__restrict__ background,
-                           float *__restrict__ out_img, float *__restrict__ final_Ts, int *__restrict__ final_idx) {
-  __shared__ float4 s_rec[2][3][BLEND_THREADS];
-  __shared__ unsigned char s_list[BLEND_THREADS / 32][UNITS][BLEND_THREADS];
-  constexpr int UL = 32 / UNITS;  // lanes per unit
-
-  const unsigned full = 0xffffffffu;
-  const int tile_x = blockIdx.x, tile_y = blockIdx.y;
-  const int tile_id = tile_y * tiles_x + tile_x;
-  const int tr = threadIdx.x, nthreads = BLEND_THREADS, lane = tr & 31, warp = tr >> 5;
-  const int unit = lane / UL;
-  int lx, ly;
-  map_pixel_units<UNITS>(lx, ly);
-  const int ipx = tile_x * 16 + lx, ipy = tile_y * 16 + ly;
-  const bool inside = (ipx < img_w) && (ipy < img_h);
-  const float px = (float)ipx, py = (float)ipy;
-  bool done = !inside;
-  const int wpx0 = tile_x * 16 + ((warp & 1) << 3), wpy0 = tile_y * 16 + ((warp >> 1) << 2);
-
-  const int2 range = tile_bins[tile_id];
-  const int num_batches = (range.y - range.x + nthreads - 1) / nthreads;
-
-  float T = 1.f;
-  int cur_idx = 0;
-  float acc_r = 0.f, acc_g = 0.f, acc_b = 0.f;
-
-  BlendRecord rec;
-  if (num_batches > 0 && range.x + tr < range.y)
-    rec = gather_record(gaussian_ids_sorted[range.x + tr], xys, conics, colors, opacities);
-
-  for (int b = 0; b < num_batches; ++b) {
-    const int buf = b & 1;
-    const int batch_start = range.x + nthreads * b;
-    if (batch_start + tr < range.y) {
-      s_rec[buf][0][tr] = rec.r0;
-      s_rec[buf][1][tr] = rec.r1;
-      s_rec[buf][2][tr] = rec.r2;
-    }
-    if (__syncthreads_count(done) >= nthreads) break;
-    {
-      const int nxt = batch_start + nthreads + tr;
-      if (nxt < range.y) rec = gather_record(gaussian_ids_sorted[nxt], xys, conics, colors, opacities);
-    }
-    if (__all_sync(full, done)) continue;
-
-    const int batch_size = min(nthreads, range.y - batch_start);
-    int n_u[UNITS];
-    compact_survivors_units<UNITS>(s_rec[buf][0], s_rec[buf][1], 0, batch_size, wpx0, wpy0, img_w, img_h, s_list[warp],
-                                   lane, n_u);
-    int my_n = n_u[0], n_max = n_u[0];
-#pragma unroll
-    for (int u = 1; u < UNITS; ++u) {
-      my_n = (unit == u) ? n_u[u] : my_n;
-      n_max = max(n_max, n_u[u]);
-    }
-    const unsigned char *my_list = s_list[warp][unit];
-    for (int i = 0; i < n_max; ++i) {
-      const bool act = i < my_n;
-      const int t = act ? my_list[i] : 0;  // slot 0 of a non-empty batch always holds a record; masked by `act`
-      const float4 q0 = s_rec[buf][0][t];
-      const float4 q1 = s_rec[buf][1][t];
-      const float dx = q0.x - px, dy = q0.y - py;
-      const float power = dx * (q1.x * dx + q1.y * dy) + q1.z * dy * dy;  // = -sigma * log2(e)
-      const float alpha = fminf(0.999f, q1.w * exp2f(power));
-      const bool contrib = act && !done && !(power > 0.f || alpha < 1.f / 255.f);
-      if (__any_sync(full, contrib)) {
-        const float next_T = T * (1.f - alpha);
-        const bool stop = contrib && (next_T <= 1e-4f);
-        done = done || stop;
-        if (contrib && !stop) {
-          const float4 q2 = s_rec[buf][2][t];
-          const float vis = alpha * T;
-          acc_r += q2.x * vis;
-          acc_g += q2.y * vis;
-          acc_b += q2.z * vis;
-          T = next_T;
-          cur_idx = batch_start + t;
-        }
-        if (__all_sync(full, done)) break;
-      }
-    }
-  }
-
-  if (inside) {
-    const int pix = ipy * img_w + ipx;
-    final_Ts[pix] = T;
-    final_idx[pix] = cur_idx;
-    out_img[3 * (size_t)pix] = acc_r + T * background[0];
-    out_img[3 * (size_t)pix + 1] = acc_g + T * background[1];
-    out_img[3 * (size_t)pix + 2] = acc_b + T * background[2];
-  }
-}
-
-// GSR_BLEND_UNITS = 1 (default: one list per warp) | 2 | 4 — read once; experimental switch for A/B runs
-int blend_units() {
-  static const int units = [] {
-    const char *e = getenv("GSR_BLEND_UNITS");
-    const int u = e ? atoi(e) : 1;
-    return (u == 2 || u == 4) ? u : 1;
-  }();
-  return units;
-}
-
 }  // namespace gsr
 
 extern "C" GSR_API int gsr_rasterize_forward(unsigned img_height, unsigned img_width, unsigned block_width,
@@ -247,18 +133,6 @@ extern "C" GSR_API int gsr_rasterize_forward(unsigned img_height, unsigned img_w
               "rasterize_forward: xys / tile_bins must be 8-byte aligned");
   const dim3 grid(cdiv(img_width, block_width), cdiv(img_height, block_width), 1);
   const unsigned threads = cdiv(block_width * block_width, 32) * 32;
-  if (block_width == 16 && blend_units() != 1) {
-    if (blend_units() == 2)
-      blend_forward_units_kernel<2><<<grid, BLEND_THREADS, 0, (cudaStream_t)stream>>>(
-          (int)grid.x, (int)img_width, (int)img_height, gaussian_ids_sorted, reinterpret_cast<const int2 *>(tile_bins),
-          reinterpret_cast<const float2 *>(xys), conics, colors, opacities, background, out_img, final_Ts, final_idx);
-    else
-      blend_forward_units_kernel<4><<<grid, BLEND_THREADS, 0, (cudaStream_t)stream>>>(
-          (int)grid.x, (int)img_width, (int)img_height, gaussian_ids_sorted, reinterpret_cast<const int2 *>(tile_bins),
-          reinterpret_cast<const float2 *>(xys), conics, colors, opacities, background, out_img, final_Ts, final_idx);
-    GSR_CHECK_LAUNCH("blend_forward_units_kernel");
-    return GSR_OK;
-  }
   blend_forward_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(
       (int)grid.x, (int)img_width, (int)img_height, (int)block_width, gaussian_ids_sorted,
       reinterpret_cast<const int2 *>(tile_bins), reinterpret_cast<const float2 *>(xys), conics, colors, opacities,

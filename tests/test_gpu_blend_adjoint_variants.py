@@ -1,0 +1,48 @@
+"""The two adjoint kernels of the 3-channel compositing — Gaussian-parallel (blend_bwd_scan.cu, default) and
+pixel-parallel (blend_bwd.cu, GSR_BWD_KERNEL=pixel) — must give the same gradients up to the order of the FP32 sums.
+The switch is read once per process, so each variant runs in its own interpreter."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+_SCRIPT = r"""
+import sys, os, numpy as np, torch
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "gaussian-splatting-toolkit_b200")); sys.path.insert(0, os.path.join({root!r}, "tests"))
+from pipelines import run_view_bindings
+from rasterizer import cuda as C
+from rasterizer.synthetic import make_scene, scene_to_torch
+out = {{}}
+for name, sc in (("a", make_scene(60_000, 500, 300, 0.004, 0.05, margin=1.1, seed=31)),
+                 ("b", make_scene(8_000, 333, 222, 0.02, 0.4, margin=1.0, seed=32)),
+                 ("c", make_scene(300, 40, 24, 0.05, 0.2, seed=1))):
+    r = run_view_bindings(C, scene_to_torch(sc, "cuda"), sort_impl="gsr", binning="fast")
+    for k in ("out_img", "final_Ts", "final_idx", "v_xy", "v_conic", "v_colors", "v_opacity"):
+        out[name + "_" + k] = r[k].detach().cpu().numpy()
+np.savez({path!r}, **out)
+"""
+
+
+def _run(bwd, tmp_path):
+    path = str(tmp_path / f"{bwd}.npz")
+    env = dict(os.environ, GSR_BWD_KERNEL=bwd)
+    subprocess.run([sys.executable, "-c", _SCRIPT.format(root=ROOT, path=path)], check=True, env=env)
+    return np.load(path)
+
+
+def test_gaussian_parallel_adjoint_matches_pixel_parallel(tmp_path):
+    ref = _run("pixel", tmp_path)
+    got = _run("scan", tmp_path)
+    for name in ("a", "b", "c"):
+        for k in ("out_img", "final_Ts", "final_idx"):
+            assert np.array_equal(got[f"{name}_{k}"], ref[f"{name}_{k}"]), (name, k)
+        for k in ("v_xy", "v_conic", "v_colors", "v_opacity"):
+            a, b = got[f"{name}_{k}"].astype(np.float64), ref[f"{name}_{k}"].astype(np.float64)
+            err = np.linalg.norm(a - b) / np.linalg.norm(b)
+            print(f"[adjoint variants] scene {name} {k}: normwise rel {err:.2e}")
+            assert err < 5e-6, (name, k, err)

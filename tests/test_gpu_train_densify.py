@@ -57,6 +57,66 @@ def _cameras():
     return cams, fx, fy
 
 
+def _trained_scene_roundtrip_and_statistics(p, cam, fx_train):
+    """SURVEY 8(f4) 'load a trained-like scene': the trained student goes through the exporter's .ply
+    (rasterizer.io_ply, scripts/exporter.py:83-148) and is rendered at 1920x1080 from a training camera with the
+    reference-facing operators, forward + backward; reports the tile-occupancy statistics such a (non-uniform,
+    object-centric, densified) scene has, and the blend-kernel times next to them."""
+    import rasterizer
+    from rasterizer import cuda as C
+    from rasterizer.io_ply import load_gaussians_ply, save_gaussians_ply
+    from rasterizer.sh import spherical_harmonics
+
+    path = os.path.join(ROOT, "gpurun_out", "trained_cfg3.ply")
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    save_gaussians_ply(path, p["means"], p["features_dc"], p["features_rest"], p["opacities"], p["scales"], p["quats"])
+    z = {k: torch.from_numpy(v).cuda() for k, v in load_gaussians_ply(path).items()}
+    for k in GROUPS:
+        assert torch.equal(z[k], p[k].detach().reshape(z[k].shape)), k   # the .ply round trip is lossless (float32)
+    Wf, Hf, bw = 1920, 1080, 16
+    V, PM0, cam_pos = cam
+    fx = fy = fx_train * Hf / H                        # same vertical field of view as the training camera
+    fovx, fovy = 2 * math.atan(0.5 * Wf / fx), 2 * math.atan(0.5 * Hf / fy)
+    from rasterizer.synthetic import projection_matrix
+
+    PM = torch.from_numpy((projection_matrix(0.001, 1000.0, fovx, fovy).astype(np.float64) @ V.cpu().numpy().astype(np.float64))
+                          .astype(np.float32)).cuda()
+    means = z["means"].clone().requires_grad_(True)
+    scales, quats = torch.exp(z["scales"]), z["quats"] / z["quats"].norm(dim=-1, keepdim=True)
+    coeffs = torch.cat((z["features_dc"][:, None, :], z["features_rest"]), dim=1).contiguous().requires_grad_(True)
+    opac = torch.sigmoid(z["opacities"])
+    w = (torch.rand(Hf, Wf, 3, device="cuda") - 0.5) * 1e-3
+
+    def view():
+        means.grad = coeffs.grad = None
+        xys, depths, radii, conics, comp, nth, cov3d = rasterizer.project_gaussians(
+            means, scales, 1.0, quats, V, PM, fx, fy, Wf / 2.0, Hf / 2.0, Hf, Wf, bw)
+        rgbs = torch.clamp(spherical_harmonics(3, means.detach() - cam_pos[None], coeffs) + 0.5, min=0.0)
+        img, alpha = rasterizer.rasterize_gaussians(xys, depths, radii, conics, nth, rgbs, opac, Hf, Wf, bw,
+                                                    background=torch.zeros(3, device="cuda"), return_alpha=True)
+        (img * w).sum().backward()
+        return xys, depths, radii, conics, nth
+
+    for _ in range(3):
+        xys, depths, radii, conics, nth = view()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        view()
+    e1.record()
+    torch.cuda.synchronize()
+    m, ids, bins = C.bin_gaussians_fast(xys.detach(), depths, radii, conics.detach(), opac.reshape(-1).contiguous(), Hf, Wf, bw)
+    L = (bins[:, 1] - bins[:, 0]).float()
+    out = {"n_gaussians": int(means.shape[0]), "visible": int((radii > 0).sum()), "M_bbox": int(nth.sum()), "M_after_exact_culling": m,
+           "tiles": int(L.numel()), "tile_len_mean": float(L.mean()), "tile_len_p99": float(L.quantile(0.99)),
+           "tile_len_max": float(L.max()), "empty_tiles_frac": float((L == 0).float().mean()),
+           "fwd_bwd_ms_1080p_public_api": e0.elapsed_time(e1) / 10, "ply_bytes": os.path.getsize(path)}
+    print("[cfg3 trained scene @1080p]", out)
+    os.remove(path)
+    return out
+
+
 def test_cfg3_training_with_densification():
     from oracle import densify_ref as dr
     from oracle.build_ref import load_ref
@@ -181,6 +241,7 @@ def test_cfg3_training_with_densification():
     p, t, counts = run_ours()
     report["ours"] = {"iters_per_s": iters / t, "psnr": psnr_of(p), "n_final": int(p["means"].shape[0]), "n_max": max(counts)}
     print("[cfg3] ours", report["ours"])
+    report["trained_scene"] = _trained_scene_roundtrip_and_statistics(p, cams[3], fx)
     ref_ext = load_ref()
     if ref_ext is not None:
         p, t, counts = run_ref(make_ops(ref_ext))
