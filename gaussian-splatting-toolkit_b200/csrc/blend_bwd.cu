@@ -206,9 +206,14 @@ blend_backward_kernel(int tiles_x, int img_w, int img_h, int block_width,
   }
 }
 
-// blend_bwd_scan.cu: the Gaussian-parallel (warp prefix-scan) adjoint — the default for 16x16 tiles; this file's
-// pixel-parallel kernel serves the other block widths and GSR_BWD_KERNEL=pixel
-int blend_bwd_use_scan();
+// 16x16 tiles: blend_bwd_tr.cu (two-phase transposing adjoint, the default) or blend_bwd_scan.cu (warp prefix-scan adjoint,
+// GSR_BWD_KERNEL=scan); this file's pixel-parallel kernel serves the other block widths and GSR_BWD_KERNEL=pixel
+int blend_bwd_mode();  // 0 = pixel, 1 = scan, 8 / 16 / 32 = two-phase with that many rows per group
+int launch_blend_backward_tr(int mode, dim3 grid, cudaStream_t st, int img_w, int img_h, const int *gaussian_ids_sorted,
+                             const int2 *tile_bins, const float2 *xys, const float *conics, const float *colors,
+                             const float *opacities, const float *background, const float *final_Ts,
+                             const int *final_idx, const float *v_output, const float *v_output_alpha, float *v_xy,
+                             float *v_conic, float *v_colors, float *v_opacity);
 int launch_blend_backward_scan(dim3 grid, cudaStream_t st, int img_w, int img_h, const int *gaussian_ids_sorted,
                                const int2 *tile_bins, const float2 *xys, const float *conics, const float *colors,
                                const float *opacities, const float *background, const float *final_Ts,
@@ -242,7 +247,13 @@ extern "C" GSR_API int gsr_rasterize_backward(unsigned img_height, unsigned img_
   GSR_CUDA(cudaMemsetAsync(v_opacity, 0, sizeof(float) * (size_t)num_points, st));
   const dim3 grid(cdiv(img_width, block_width), cdiv(img_height, block_width), 1);
   const unsigned threads = cdiv(block_width * block_width, 32) * 32;
-  if (block_width == 16 && blend_bwd_use_scan())
+  const int mode = block_width == 16 ? blend_bwd_mode() : 0;
+  if (mode >= 8)
+    return launch_blend_backward_tr(mode, grid, st, (int)img_width, (int)img_height, gaussian_ids_sorted,
+                                    reinterpret_cast<const int2 *>(tile_bins), reinterpret_cast<const float2 *>(xys), conics,
+                                    colors, opacities, background, final_Ts, final_idx, v_output, v_output_alpha, v_xy,
+                                    v_conic, v_colors, v_opacity);
+  if (mode == 1)
     return launch_blend_backward_scan(grid, st, (int)img_width, (int)img_height, gaussian_ids_sorted,
                                       reinterpret_cast<const int2 *>(tile_bins), reinterpret_cast<const float2 *>(xys),
                                       conics, colors, opacities, background, final_Ts, final_idx, v_output, v_output_alpha,

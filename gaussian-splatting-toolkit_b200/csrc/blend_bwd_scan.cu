@@ -251,20 +251,12 @@ blend_backward_scan_kernel(int tiles_x, int img_w, int img_h, const int *__restr
   }
 }
 
-// GSR_BWD_KERNEL = scan (default: this kernel) | pixel (the pixel-parallel kernel of blend_bwd.cu) — read once.
+// Selected with GSR_BWD_KERNEL=scan (blend_bwd_tr.cu holds the switch and the default kernel).
 // Measured at cfg2 on B200 (profiles/r02): pixel-parallel 1.047 ms, this kernel 0.953 ms.  Variants tried and dropped: two
 // separate scans per pixel instead of one affine-map scan (1.22 ms: latency-bound, issue slots 55 % busy); registers
 // capped at 64 for 4 CTAs / SM (0.996 ms); the two pixels of an iteration packed into Blackwell's two-wide FP32
 // instructions (fma.rn.f32x2 / FFMA2: 15 % fewer instructions, but 114 registers -> 2 CTAs / SM and 23 register moves per
 // pixel pair: 1.106 ms).
-int blend_bwd_use_scan() {
-  static const int v = [] {
-    const char *e = getenv("GSR_BWD_KERNEL");
-    return (e && e[0] == 'p') ? 0 : 1;
-  }();
-  return v;
-}
-
 int launch_blend_backward_scan(dim3 grid, cudaStream_t st, int img_w, int img_h, const int *gaussian_ids_sorted,
                                const int2 *tile_bins, const float2 *xys, const float *conics, const float *colors,
                                const float *opacities, const float *background, const float *final_Ts,

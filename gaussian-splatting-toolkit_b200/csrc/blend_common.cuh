@@ -74,9 +74,12 @@ __device__ __forceinline__ void map_pixel(int block_width, int &lx, int &ly) {
 //      BASELINE scene it removes another 16 % of the (warp, Gaussian) pairs the box lets through (the box
 //      keeps the corners of the bounding box of a slanted ellipse), leaving 0.2 % false positives.
 // Anything not provably below the threshold is kept (NaNs, A >= 0): comparisons are written so NaN keeps.
+// PAD > 0: the PAD entries after the last survivor are set to `pad_slot` (a record that never contributes), so that a
+// consumer may unroll / read ahead past the end of the list without a remainder loop.
+template <typename ListT = unsigned char, int PAD = 0>
 __device__ __forceinline__ int compact_survivors(const float4 *__restrict__ rec0, const float4 *__restrict__ rec1,
                                                  int t_begin, int t_end, float fx0, float fx1, float fy0, float fy1,
-                                                 unsigned char *__restrict__ list, int lane) {
+                                                 ListT *__restrict__ list, int lane, int pad_slot = 0) {
   int n = 0;
   const unsigned lt_mask = (1u << lane) - 1u;
   for (int r = t_begin; r < t_end; r += 32) {
@@ -106,9 +109,10 @@ __device__ __forceinline__ int compact_survivors(const float4 *__restrict__ rec0
       }
     }
     const unsigned m = __ballot_sync(0xffffffffu, hit);
-    if (hit) list[n + __popc(m & lt_mask)] = (unsigned char)t;
+    if (hit) list[n + __popc(m & lt_mask)] = (ListT)t;
     n += __popc(m);
   }
+  if (PAD > 0 && lane < PAD) list[n + lane] = (ListT)pad_slot;
   __syncwarp();
   return n;
 }

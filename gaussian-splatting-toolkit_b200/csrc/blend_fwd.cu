@@ -21,15 +21,17 @@
 
 namespace gsr {
 
-__global__ void __launch_bounds__(BLEND_THREADS)
+__global__ void __launch_bounds__(BLEND_THREADS, 4)
 blend_forward_kernel(int tiles_x, int img_w, int img_h, int block_width,
                      const int *__restrict__ gaussian_ids_sorted, const int2 *__restrict__ tile_bins,
                      const float2 *__restrict__ xys, const float *__restrict__ conics,
                      const float *__restrict__ colors, const float *__restrict__ opacities,
                      const float *__restrict__ background, float *__restrict__ out_img,
                      float *__restrict__ final_Ts, int *__restrict__ final_idx) {
-  __shared__ float4 s_rec[2][3][BLEND_THREADS];
-  __shared__ unsigned char s_list[BLEND_THREADS / 32][BLEND_THREADS];
+  // slot kNull of every plane holds a record that never contributes (opacity 0): the survivor lists are padded with it
+  constexpr int kNull = BLEND_THREADS, kUnroll = 4;
+  __shared__ float4 s_rec[2][3][BLEND_THREADS + 1];
+  __shared__ unsigned short s_list[BLEND_THREADS / 32][BLEND_THREADS + kUnroll + 2];
 
   const unsigned full = 0xffffffffu;
   const int tile_x = blockIdx.x, tile_y = blockIdx.y;
@@ -40,7 +42,7 @@ blend_forward_kernel(int tiles_x, int img_w, int img_h, int block_width,
   const int ipx = tile_x * block_width + lx, ipy = tile_y * block_width + ly;
   const bool inside = (ly < block_width) && (ipx < img_w) && (ipy < img_h);
   const float px = (float)ipx, py = (float)ipy;
-  bool done = !inside;
+  const bool done = !inside;
 
   // the warp's pixel rectangle (inside pixels only); empty warps get an impossible rectangle
   const float fx0 = (float)__reduce_min_sync(full, inside ? ipx : 0x7fffffff);
@@ -54,6 +56,10 @@ blend_forward_kernel(int tiles_x, int img_w, int img_h, int block_width,
   float T = 1.f;
   int cur_idx = 0;
   float acc_r = 0.f, acc_g = 0.f, acc_b = 0.f;
+  // a finished pixel has slot_stop = -1; contributors need slot < slot_stop (one ISETP instead of a flag round trip)
+  int slot_stop = done ? -1 : 0x7fffffff;
+
+  if (tr < 6) s_rec[tr & 1][tr >> 1][kNull] = tr < 2 ? make_float4(0.f, 0.f, -1e30f, -1e30f) : make_float4(0.f, 0.f, 0.f, 0.f);
 
   BlendRecord rec;
   if (num_batches > 0 && range.x + tr < range.y)
@@ -68,39 +74,53 @@ blend_forward_kernel(int tiles_x, int img_w, int img_h, int block_width,
       s_rec[buf][2][tr] = rec.r2;
     }
     // one barrier per batch: publishes buffer `buf` and counts finished pixels (forward.cu:327-329)
-    if (__syncthreads_count(done) >= nthreads) break;
+    if (__syncthreads_count(slot_stop < 0) >= nthreads) break;
     {
       const int nxt = batch_start + nthreads + tr;
       if (nxt < range.y) rec = gather_record(gaussian_ids_sorted[nxt], xys, conics, colors, opacities);
     }
-    if (__all_sync(full, done)) continue;  // this warp is finished; it still stages and syncs
+    if (__all_sync(full, slot_stop < 0)) continue;  // this warp is finished; it still stages and syncs
 
     const int batch_size = min(nthreads, range.y - batch_start);
-    const int n_list = compact_survivors(s_rec[buf][0], s_rec[buf][1], 0, batch_size, fx0, fx1, fy0, fy1, s_list[warp], lane);
-    for (int i = 0; i < n_list; ++i) {
-      const int t = s_list[warp][i];
-      const float4 q0 = s_rec[buf][0][t];
-      const float4 q1 = s_rec[buf][1][t];
-      const float dx = q0.x - px, dy = q0.y - py;
-      const float power = dx * (q1.x * dx + q1.y * dy) + q1.z * dy * dy;  // = -sigma * log2(e)
-      const float alpha = fminf(0.999f, q1.w * exp2f(power));
-      const bool contrib = !done && !(power > 0.f || alpha < 1.f / 255.f);
-      if (__any_sync(full, contrib)) {
+    const unsigned short *lp = s_list[warp];
+    const int n_list = compact_survivors<unsigned short, kUnroll + 2>(s_rec[buf][0], s_rec[buf][1], 0, batch_size, fx0, fx1,
+                                                                      fy0, fy1, s_list[warp], lane, kNull);
+    // Software-pipelined walk, kUnroll survivors per trip (the list is padded with the null record, so there is no
+    // remainder loop); the next record is loaded while this one is evaluated, and the all-pixels-done vote is taken
+    // once per trip — visits after the last pixel has finished change nothing (no lane contributes).
+    int slot = lp[0];
+    float2 c0 = *reinterpret_cast<const float2 *>(&s_rec[buf][0][slot]);
+    float4 q1 = s_rec[buf][1][slot];
+    float4 q2 = s_rec[buf][2][slot];
+    int slot_n = lp[1];
+    int last_slot = -1;
+    for (int i = 0; i < n_list; i += kUnroll) {
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const float2 n0 = *reinterpret_cast<const float2 *>(&s_rec[buf][0][slot_n]);
+        const float4 n1 = s_rec[buf][1][slot_n];
+        const float4 n2 = s_rec[buf][2][slot_n];
+        const int slot_nn = lp[i + u + 2];
+        const float dx = c0.x - px, dy = c0.y - py;
+        const float power = dx * (q1.x * dx + q1.y * dy) + q1.z * dy * dy;  // = -sigma * log2(e)
+        const float alpha = fminf(0.999f, q1.w * exp2f(power));
+        const bool contrib = (slot < slot_stop) && !(power > 0.f || alpha < 1.f / 255.f);
         const float next_T = T * (1.f - alpha);
         const bool stop = contrib && (next_T <= 1e-4f);
-        done = done || stop;
+        if (stop) slot_stop = -1;
         if (contrib && !stop) {
-          const float4 q2 = s_rec[buf][2][t];
           const float vis = alpha * T;
           acc_r += q2.x * vis;
           acc_g += q2.y * vis;
           acc_b += q2.z * vis;
           T = next_T;
-          cur_idx = batch_start + t;
+          last_slot = slot;
         }
-        if (__all_sync(full, done)) break;
+        slot = slot_n; c0 = n0; q1 = n1; q2 = n2; slot_n = slot_nn;
       }
+      if (__all_sync(full, slot_stop < 0)) break;
     }
+    if (last_slot >= 0) cur_idx = batch_start + last_slot;
   }
 
   if (inside) {

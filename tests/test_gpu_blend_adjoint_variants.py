@@ -1,5 +1,6 @@
-"""The two adjoint kernels of the 3-channel compositing — Gaussian-parallel (blend_bwd_scan.cu, default) and
-pixel-parallel (blend_bwd.cu, GSR_BWD_KERNEL=pixel) — must give the same gradients up to the order of the FP32 sums.
+"""The adjoint kernels of the 3-channel compositing — two-phase transposing (blend_bwd_tr.cu, default), warp prefix-scan
+(blend_bwd_scan.cu, GSR_BWD_KERNEL=scan) and pixel-parallel (blend_bwd.cu, GSR_BWD_KERNEL=pixel) — must give the same
+gradients up to the order of the FP32 sums.
 The switch is read once per process, so each variant runs in its own interpreter."""
 import os
 import subprocess
@@ -35,14 +36,17 @@ def _run(bwd, tmp_path):
     return np.load(path)
 
 
-def test_gaussian_parallel_adjoint_matches_pixel_parallel(tmp_path):
+@pytest.mark.parametrize("variant", ["tr", "tr8", "tr32", "scan"])
+def test_adjoint_variants_match_pixel_parallel(tmp_path, variant):
+    """tr / tr8 / tr32 = two-phase transposing adjoint (blend_bwd_tr.cu; tr = 16 rows per group is the default kernel),
+    scan = warp prefix-scan adjoint (blend_bwd_scan.cu)."""
     ref = _run("pixel", tmp_path)
-    got = _run("scan", tmp_path)
+    got = _run(variant, tmp_path)
     for name in ("a", "b", "c"):
         for k in ("out_img", "final_Ts", "final_idx"):
             assert np.array_equal(got[f"{name}_{k}"], ref[f"{name}_{k}"]), (name, k)
         for k in ("v_xy", "v_conic", "v_colors", "v_opacity"):
             a, b = got[f"{name}_{k}"].astype(np.float64), ref[f"{name}_{k}"].astype(np.float64)
             err = np.linalg.norm(a - b) / np.linalg.norm(b)
-            print(f"[adjoint variants] scene {name} {k}: normwise rel {err:.2e}")
-            assert err < 5e-6, (name, k, err)
+            print(f"[adjoint variants] {variant} scene {name} {k}: normwise rel {err:.2e}")
+            assert err < 5e-6, (variant, name, k, err)

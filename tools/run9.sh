@@ -1,0 +1,11 @@
+set -x
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+R=r2_run9
+python -m pytest tests/test_gpu_blend_adjoint_variants.py tests/test_gpu_parity.py -m gpu -q -x -s > gpurun_out/${R}_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${R}_pytest.log
+grep "adjoint variants" gpurun_out/${R}_pytest.log | head -60; tail -4 gpurun_out/${R}_pytest.log
+for mode in tr tr8 tr32 scan; do
+GSR_BWD_KERNEL=$mode python bench.py --steps 20 --warmup 5 --only-resident > gpurun_out/${R}_bench_$mode.json 2> gpurun_out/${R}_bench_$mode.err; echo "bench $mode rc=$?"; cat gpurun_out/${R}_bench_$mode.json | cut -c1-600
+done
+ncu --set full --clock-control none --import-source on -k "regex:blend_backward" -s 1 -c 1 -o gpurun_out/${R}_tr16 python bench.py --steps 1 --warmup 1 --only-resident > gpurun_out/${R}_ncu.log 2>&1
+ls -la gpurun_out/*.ncu-rep
