@@ -52,7 +52,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg4"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg4", "cfg3view"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--only-resident", action="store_true", help="profiling aid: only the resident leg (no graph / e2e / "
                     "fused / reference-extension legs); the JSON line is tagged diagnostic")
@@ -401,7 +401,9 @@ def fused_leg(torch, s, scene_np, steps, warmup):
 def workload_text(name, scene_np):
     N, W, H = scene_np["means3d"].shape[0], scene_np["img_width"], scene_np["img_height"]
     return (f"{name}: {N} Gaussians, {W}x{H}, SH degree {scene_np['sh_degree']}, fwd+bwd, block_width "
-            f"{scene_np['block_width']}, seeded scene of SURVEY 8(d)")
+            f"{scene_np['block_width']}, seeded scene of SURVEY 8(d)"
+            + (" — clustered / object-centric variant (85 % of the Gaussians in a blob around the look-at point)"
+               if name == "cfg3view" else ""))
 
 
 def make_scene_for_rank(workload, rank):
@@ -752,9 +754,11 @@ def main():
         ab = algorithmic_bytes(N, M, P, T)
         t_bwd = stages["blend_bwd"] * 1e-3
         achieved = ab["blend_bwd"] / t_bwd / 1e9
-        facts, facts_src = ncu_facts("blend_backward_kernel")
+        bwd_kernel = {"p": "blend_backward_kernel", "s": "blend_backward_scan_kernel"}.get(
+            os.environ.get("GSR_BWD_KERNEL", "tr")[:1], "blend_backward_tr_kernel<16, 3>")
+        facts, facts_src = ncu_facts(bwd_kernel)
         roofline = {
-            "kernel": "blend_backward_kernel (gsr_rasterize_backward)", "bound": "hbm", "achieved": achieved, "peak": peak,
+            "kernel": f"{bwd_kernel} (gsr_rasterize_backward)", "bound": "hbm", "achieved": achieved, "peak": peak,
             "unit": "GB/s", "frac": achieved / peak, "traffic": facts["dram_bytes"] if facts else None,
             "traffic_source": facts_src, "peak_source": peak_src,
             "ncu_issue_slot_utilization": (facts["issue_active_pct"] / 100.0) if facts else None,

@@ -20,9 +20,11 @@
 //                      (block, tile) group, every group in its own range of the tile's segment
 //   tile_sort_warp_kernel    one WARP per tile with <= 1024 pairs: bitonic sort in registers (E = 4..32 keys per lane;
 //                      in-register stages + shuffle stages, no shared memory, no barrier); the low words (Gaussian
-//                      ids) go to gaussian_ids_sorted
-//   tile_sort_kernel   one CTA per tile with more pairs: bitonic sort in shared memory (<= 4096), above that a stable
-//                      LSD radix sort of the segment in global memory (slow path, keeps the call correct for any scene)
+//                      ids) go to gaussian_ids_sorted.  <false>: all tiles up to 512 pairs; <true>: the 513..1024-pair
+//                      tiles, from a list tile_scan_kernel builds
+//   tile_sort_long_kernel    tiles with more pairs (list-driven persistent grid, 1024-thread CTAs): all-ascending bitonic
+//                      network with virtual padding — in shared memory up to 8192 pairs, chunked shared memory + a few
+//                      in-place global steps above (any length; object-centric scenes put thousands of pairs in a tile)
 //   (images with more than 48 K tiles do not fit the shared-memory histogram: bin_count_kernel / bin_fill_kernel do the
 //   same with global atomics)
 //
@@ -38,8 +40,20 @@
 namespace gsr {
 namespace {
 
+inline int num_sms() {
+  static int cached[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (cached[dev] == 0) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    cached[dev] = n > 0 ? n : 148;
+  }
+  return cached[dev];
+}
+
 constexpr int BD_THREADS = 256;
-constexpr int SORT_SMEM_MAX = 4096;  // pairs a CTA sorts in shared memory (32 KB of 64-bit keys)
 typedef unsigned long long u64;
 
 // tiles kept for Gaussian g: calls f(tile_id) for each; returns the count.  `mask` caches the decision for boxes of
@@ -91,45 +105,81 @@ bin_count_kernel(int n, const float2 *__restrict__ xys, const int *__restrict__ 
   masks[g] = mask;
 }
 
-// one block of 1024 threads: exclusive scan of tile_count; tile_bins (clipped to capacity), cursors = segment starts
+constexpr int SORT_WARP_SMALL = 512;  // tiles up to this size: tile_sort_warp_kernel<false> over all tiles
+constexpr int SORT_WARP_MAX = 1024;   // (SORT_WARP_SMALL, SORT_WARP_MAX]: tile_sort_warp_kernel<true> over the `mid` list
+                                      // above: tile_sort_long_kernel over the `long` list
+// lists = {mid_count, long_count, long_cursor, 0, mid[T], long[T]}
+__host__ __device__ inline int *list_mid(int *lists) { return lists + 4; }
+__host__ __device__ inline int *list_long(int *lists, int num_tiles) { return lists + 4 + num_tiles; }
+
+// one block of 1024 threads: exclusive scan of tile_count -> tile_bins (clipped to capacity), cursors = segment starts,
+// meta, and the lists of the tiles whose sort needs more than the short-tile kernel.  The counts are staged through
+// shared memory in coalesced chunks (a thread's serial walk over its tiles used to wait on one global load per tile).
+constexpr int SCAN_CHUNK = 8192;
 __global__ void __launch_bounds__(1024)
 tile_scan_kernel(int num_tiles, const unsigned *__restrict__ tile_count, int capacity, int2 *__restrict__ tile_bins,
-                 unsigned *__restrict__ cursors, int *__restrict__ meta) {
+                 unsigned *__restrict__ cursors, int *__restrict__ meta, int *__restrict__ lists) {
+  __shared__ unsigned s_cnt[SCAN_CHUNK];
   __shared__ unsigned long long s_warp[32];
+  __shared__ int s_nmid, s_nlong;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int per = (num_tiles + 1023) / 1024;
-  const int lo = min(num_tiles, tid * per), hi = min(num_tiles, lo + per);
-  unsigned long long sum = 0;
-  for (int i = lo; i < hi; ++i) sum += tile_count[i];
-  unsigned long long inc = sum;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const unsigned long long up = __shfl_up_sync(0xffffffffu, inc, d);
-    if (lane >= d) inc += up;
-  }
-  if (lane == 31) s_warp[warp] = inc;
-  __syncthreads();
-  unsigned long long base = 0, total = 0;
-  for (int w = 0; w < 32; ++w) {
-    const unsigned long long t = s_warp[w];
-    if (w < warp) base += t;
-    total += t;
-  }
-  unsigned long long run = base + inc - sum;
+  constexpr int PER = SCAN_CHUNK / 1024;
+  if (tid == 0) s_nmid = s_nlong = 0;
+  unsigned long long carry = 0;  // pairs in the chunks before this one
   const unsigned long long cap = (unsigned long long)capacity;
-  for (int i = lo; i < hi; ++i) {
-    const unsigned long long nxt = run + tile_count[i];
-    const int s = (int)min(run, cap), e = (int)min(nxt, cap);
-    tile_bins[i] = (e > s) ? make_int2(s, e) : make_int2(0, 0);  // empty tiles are (0, 0), like the reference's zeros
-    cursors[i] = (unsigned)min(run, 0xffffffffull);
-    run = nxt;
+  int *mid = list_mid(lists), *lng = list_long(lists, num_tiles);
+  for (int c0 = 0; c0 < num_tiles; c0 += SCAN_CHUNK) {
+    __syncthreads();  // the previous chunk's s_cnt / s_warp are no longer read
+    for (int i = tid; i < SCAN_CHUNK; i += 1024) s_cnt[i] = (c0 + i < num_tiles) ? tile_count[c0 + i] : 0u;
+    __syncthreads();
+    unsigned v[PER];
+    unsigned long long sum = 0;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      v[i] = s_cnt[tid * PER + i];
+      sum += v[i];
+    }
+    unsigned long long inc = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned long long up = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += up;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    unsigned long long base = 0, total = 0;
+    for (int w = 0; w < 32; ++w) {
+      const unsigned long long t = s_warp[w];
+      if (w < warp) base += t;
+      total += t;
+    }
+    unsigned long long run = carry + base + inc - sum;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int tile = c0 + tid * PER + i;
+      const unsigned long long nxt = run + v[i];
+      if (tile < num_tiles) {
+        const int b = (int)min(run, cap), e = (int)min(nxt, cap);
+        tile_bins[tile] = (e > b) ? make_int2(b, e) : make_int2(0, 0);  // empty tiles are (0, 0), like the reference's zeros
+        cursors[tile] = (unsigned)min(run, 0xffffffffull);
+        if (e - b > SORT_WARP_MAX) lng[atomicAdd(&s_nlong, 1)] = tile;
+        else if (e - b > SORT_WARP_SMALL) mid[atomicAdd(&s_nmid, 1)] = tile;
+      }
+      run = nxt;
+    }
+    carry += total;
   }
+  __syncthreads();
   if (tid == 0) {
     // the reference keeps M in an int32 too (torch.cumsum(dtype=int32), rasterizer/utils.py:123)
-    meta[0] = (int)min(total, 0x7fffffffull);
-    meta[1] = total > cap ? 1 : 0;
-    meta[2] = (int)min(total, cap);
+    meta[0] = (int)min(carry, 0x7fffffffull);
+    meta[1] = carry > cap ? 1 : 0;
+    meta[2] = (int)min(carry, cap);
     meta[3] = 0;
+    lists[0] = s_nmid;
+    lists[1] = s_nlong;
+    lists[2] = 0;
+    lists[3] = 0;
   }
 }
 
@@ -297,128 +347,196 @@ __device__ __forceinline__ void warp_sort_tile(const u64 *__restrict__ seg, int 
   }
 }
 
-constexpr int SORT_WARP_MAX = 1024;  // pairs one warp sorts in registers
 constexpr int SORT_WARPS = 4;        // warps (= tiles) per CTA of tile_sort_warp_kernel
 
-// BIG = false: tiles with 1..512 pairs (E <= 16, ~90 registers); BIG = true: 513..1024 pairs (E = 32, ~170 registers) —
-// two kernels so that the common short tiles are not held to the occupancy of the 64-register key array
+// BIG = false: every tile with 1..512 pairs (E <= 16, ~90 registers), one warp per tile; BIG = true: the tiles of the
+// `mid` list (513..1024 pairs, E = 32, ~170 registers), a fixed grid striding over the list — two kernels so that the
+// common short tiles are not held to the occupancy of the 64-register key array, and the second costs a few
+// microseconds when the list is short
 template <bool BIG>
 __global__ void __launch_bounds__(32 * SORT_WARPS)
 tile_sort_warp_kernel(int num_tiles, const int2 *__restrict__ tile_bins, const u64 *__restrict__ keys,
-                      int *__restrict__ ids_out) {
-  const int tile = blockIdx.x * SORT_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (tile >= num_tiles) return;
-  const int2 range = tile_bins[tile];
-  const int n = range.y - range.x;
-  const u64 *seg = keys + range.x;
-  int *out = ids_out + range.x;
+                      const int *__restrict__ lists, int *__restrict__ ids_out) {
+  const int w = blockIdx.x * SORT_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (BIG) {
-    if (n > 512 && n <= SORT_WARP_MAX) warp_sort_tile<32>(seg, n, lane, out);
+    const int n_mid = lists[0];
+    const int *mid = list_mid(const_cast<int *>(lists));
+    for (int k = w; k < n_mid; k += gridDim.x * SORT_WARPS) {
+      const int2 range = tile_bins[mid[k]];
+      warp_sort_tile<32>(keys + range.x, range.y - range.x, lane, ids_out + range.x);
+    }
   } else {
-    if (n <= 0 || n > 512) return;
+    if (w >= num_tiles) return;
+    const int2 range = tile_bins[w];
+    const int n = range.y - range.x;
+    const u64 *seg = keys + range.x;
+    int *out = ids_out + range.x;
+    if (n <= 0 || n > SORT_WARP_SMALL) return;
     if (n <= 128) warp_sort_tile<4>(seg, n, lane, out);
     else if (n <= 256) warp_sort_tile<8>(seg, n, lane, out);
     else warp_sort_tile<16>(seg, n, lane, out);
   }
 }
 
-// ---- per-tile sort ---------------------------------------------------------------------------------------------------
-// slow path for tiles with more than SORT_SMEM_MAX pairs: stable LSD radix sort (8-bit digits) of n keys between two
-// global buffers, ONE warp scattering in order (the other warps only help with the histogram).  Only the bits that can
-// differ are sorted: the id bits [0, id_bits) and the depth bits [32, 64).
-__device__ void long_tile_radix_pass(const u64 *src, u64 *dst, int n, int shift, unsigned *s_hist /*[256]*/) {
-  const unsigned full = 0xffffffffu;
-  const int tid = threadIdx.x, lane = tid & 31;
-  for (int i = tid; i < 256; i += BD_THREADS) s_hist[i] = 0u;
-  __syncthreads();
-  for (int i = tid; i < n; i += BD_THREADS) atomicAdd(&s_hist[(unsigned)(src[i] >> shift) & 255u], 1u);
-  __syncthreads();
-  if (tid < 32) {
-    unsigned carry = 0;  // exclusive scan of the 256 counters
-    for (int c = 0; c < 256; c += 32) {
-      const unsigned v = s_hist[c + lane];
-      unsigned inc = v;
+// ---- long tiles (more than SORT_WARP_MAX pairs) ----------------------------------------------------------------------
+// A persistent grid of 1024-thread CTAs pulls tiles from the `long` list.  Bitonic network in its all-ascending form
+// (stage k = one "flip" step, partner i ^ (k - 1), then "disperse" steps j = k/4 .. 1, partner i + j): every
+// compare-exchange puts the smaller key at the lower index, so the padding up to a power of two is VIRTUAL — a pair whose
+// upper index is >= n is skipped — and a tile of any length is sorted in place.  Up to LONG_CHUNK keys the whole network
+// runs in shared memory; longer tiles sort LONG_CHUNK-key chunks in shared memory, then for every stage k > LONG_CHUNK
+// run the steps whose partner distance spans chunks directly on the (L2-resident) segment and the remaining steps of
+// the stage chunk by chunk in shared memory again.
+constexpr int LONG_THREADS = 1024;
+constexpr int LONG_CHUNK = 8192;  // 64 KB of 64-bit keys: two CTAs per SM
+
+__device__ __forceinline__ void cmp_swap(u64 &a, u64 &b) {
+  if (a > b) {
+    const u64 t = a;
+    a = b;
+    b = t;
+  }
+}
+
+// Shared-memory index of key i: one key of padding after every 8, so that the 8-key groups of the register passes start
+// in different banks (thread g reads keys 8g .. 8g+7: unpadded, 32 lanes would hit two bank pairs, 16-way conflicts)
+__device__ __forceinline__ int sp(int i) { return i + (i >> 3); }
+constexpr int LONG_SMEM_BYTES = (LONG_CHUNK + LONG_CHUNK / 8) * 8;
+
+// The three innermost disperse steps (j = 4, 2, 1) of a stage touch aligned groups of 8 keys only: one thread takes a
+// group through all three in registers (one pass and one barrier instead of three).  FIRST: the stages k = 2, 4, 8
+// instead (flip partners inside the group).  Keys at or beyond n_valid read as +inf and are not written back; every
+// exchange is ascending, so they never move below a real key.
+template <bool FIRST>
+__device__ __forceinline__ void smem_groups_of_8(u64 *s, int m, int n_valid) {
+  for (int g = threadIdx.x; g < (m >> 3); g += LONG_THREADS) {
+    const int base = g << 3;
+    if (base >= n_valid) continue;
+    u64 v[8];
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const unsigned up = __shfl_up_sync(full, inc, d);
-        if (lane >= d) inc += up;
-      }
-      s_hist[c + lane] = carry + inc - v;
-      carry += __shfl_sync(full, inc, 31);
+    for (int i = 0; i < 8; ++i) v[i] = (base + i < n_valid) ? s[sp(base + i)] : ~0ull;
+    if (FIRST) {
+      cmp_swap(v[0], v[1]); cmp_swap(v[2], v[3]); cmp_swap(v[4], v[5]); cmp_swap(v[6], v[7]);   // k = 2
+      cmp_swap(v[0], v[3]); cmp_swap(v[1], v[2]); cmp_swap(v[4], v[7]); cmp_swap(v[5], v[6]);   // k = 4: flip
+      cmp_swap(v[0], v[1]); cmp_swap(v[2], v[3]); cmp_swap(v[4], v[5]); cmp_swap(v[6], v[7]);   //        j = 1
+      cmp_swap(v[0], v[7]); cmp_swap(v[1], v[6]); cmp_swap(v[2], v[5]); cmp_swap(v[3], v[4]);   // k = 8: flip
+    } else {
+      cmp_swap(v[0], v[4]); cmp_swap(v[1], v[5]); cmp_swap(v[2], v[6]); cmp_swap(v[3], v[7]);   // j = 4
     }
-    __syncwarp();
-    const unsigned lt = (1u << lane) - 1u;
-    for (int base = 0; base < n; base += 32) {  // in order => stable
-      const int i = base + lane;
-      const bool valid = i < n;
-      u64 k = 0;
-      unsigned d = 0xffffffffu;
-      if (valid) {
-        k = src[i];
-        d = (unsigned)(k >> shift) & 255u;
-      }
-      const unsigned peers = __match_any_sync(full, d);
-      const unsigned rnk = __popc(peers & lt);
-      unsigned start = 0;
-      if (valid) start = s_hist[d];
-      __syncwarp();
-      if (valid) {
-        dst[start + rnk] = k;
-        if (rnk == 0) s_hist[d] = start + __popc(peers);
-      }
-      __syncwarp();
-    }
+    cmp_swap(v[0], v[2]); cmp_swap(v[1], v[3]); cmp_swap(v[4], v[6]); cmp_swap(v[5], v[7]);     // j = 2
+    cmp_swap(v[0], v[1]); cmp_swap(v[2], v[3]); cmp_swap(v[4], v[5]); cmp_swap(v[6], v[7]);     // j = 1
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (base + i < n_valid) s[sp(base + i)] = v[i];
   }
-  __threadfence_block();
   __syncthreads();
 }
 
-__device__ void long_tile_radix_sort(u64 *a, u64 *b, int n, int id_bits, unsigned *s_hist, int *ids_out) {
-  u64 *src = a, *dst = b;
-  for (int shift = 0; shift < id_bits; shift += 8) {
-    long_tile_radix_pass(src, dst, n, shift, s_hist);
-    u64 *t = src; src = dst; dst = t;
+// steps of stage k >= 16 (flip first when `flip`) with partner distance < m on s[0, m); n_valid = real keys in s
+__device__ __forceinline__ void smem_stage(u64 *s, int m, int n_valid, int k, bool flip) {
+  const int tid = threadIdx.x;
+  if (flip) {
+    const int h = k >> 1;
+    for (int t = tid; t < (m >> 1); t += LONG_THREADS) {
+      const int lo = ((t & ~(h - 1)) << 1) | (t & (h - 1)), hi = lo ^ (k - 1);
+      if (hi < n_valid) {
+        u64 a = s[sp(lo)], b = s[sp(hi)];
+        if (a > b) { s[sp(lo)] = b; s[sp(hi)] = a; }
+      }
+    }
+    __syncthreads();
   }
-  for (int shift = 32; shift < 64; shift += 8) {
-    long_tile_radix_pass(src, dst, n, shift, s_hist);
-    u64 *t = src; src = dst; dst = t;
+  for (int j = flip ? (k >> 2) : min(k >> 2, m >> 1); j >= 8; j >>= 1) {
+    for (int t = tid; t < (m >> 1); t += LONG_THREADS) {
+      const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1)), hi = lo + j;
+      if (hi < n_valid) {
+        u64 a = s[sp(lo)], b = s[sp(hi)];
+        if (a > b) { s[sp(lo)] = b; s[sp(hi)] = a; }
+      }
+    }
+    __syncthreads();
   }
-  for (int i = threadIdx.x; i < n; i += BD_THREADS) ids_out[i] = (int)(unsigned)src[i];
+  smem_groups_of_8<false>(s, m, n_valid);
 }
 
-__global__ void __launch_bounds__(BD_THREADS)
-tile_sort_kernel(const int2 *__restrict__ tile_bins, u64 *__restrict__ keys, u64 *__restrict__ keys_tmp, int id_bits,
-                 int *__restrict__ ids_out) {
-  __shared__ u64 s_keys[SORT_SMEM_MAX];
-  __shared__ unsigned s_hist[256];
-  const int2 range = tile_bins[blockIdx.x];
-  const int n = range.y - range.x, tid = threadIdx.x;
-  if (n <= SORT_WARP_MAX) return;  // sorted by tile_sort_warp_kernel
-  u64 *seg = keys + range.x;
-  if (n > SORT_SMEM_MAX) {
-    long_tile_radix_sort(seg, keys_tmp + range.x, n, id_bits, s_hist, ids_out + range.x);
-    return;
-  }
-  int P = 32;
-  while (P < n) P <<= 1;
-  for (int i = tid; i < P; i += BD_THREADS) s_keys[i] = i < n ? seg[i] : ~0ull;
-  __syncthreads();
-  for (int k = 2; k <= P; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = tid; t < (P >> 1); t += BD_THREADS) {
-        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-        const int p = i | j;
-        const u64 x = s_keys[i], y = s_keys[p];
-        const bool up = (i & k) == 0;
-        if ((x > y) == up) {
-          s_keys[i] = y;
-          s_keys[p] = x;
-        }
-      }
+// the whole network up to stage k_max on s[0, m)
+__device__ __forceinline__ void smem_sort(u64 *s, int m, int n_valid, int k_max) {
+  smem_groups_of_8<true>(s, m, n_valid);
+  for (int k = 16; k <= k_max; k <<= 1) smem_stage(s, m, n_valid, k, true);
+}
+
+__global__ void __launch_bounds__(LONG_THREADS)
+tile_sort_long_kernel(int num_tiles, const int2 *__restrict__ tile_bins, u64 *__restrict__ keys, int *__restrict__ lists,
+                      int *__restrict__ ids_out) {
+  extern __shared__ __align__(16) unsigned char long_smem[];
+  u64 *s = reinterpret_cast<u64 *>(long_smem);
+  __shared__ int s_next;
+  const int tid = threadIdx.x;
+  const int n_long = lists[1];
+  const int *lng = list_long(lists, num_tiles);
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_next = atomicAdd(&lists[2], 1);
+    __syncthreads();
+    const int item = s_next;
+    if (item >= n_long) return;
+    const int2 range = tile_bins[lng[item]];
+    const int n = range.y - range.x;
+    u64 *seg = keys + range.x;
+    int *out = ids_out + range.x;
+    int P = 2048;
+    while (P < n) P <<= 1;
+    if (P <= LONG_CHUNK) {
+      for (int i = tid; i < n; i += LONG_THREADS) s[sp(i)] = seg[i];
+      __syncthreads();
+      smem_sort(s, P, n, P);
+      for (int i = tid; i < n; i += LONG_THREADS) out[i] = (int)(unsigned)s[sp(i)];
+      continue;
+    }
+    const int nchunks = (n + LONG_CHUNK - 1) / LONG_CHUNK;
+    for (int c = 0; c < nchunks; ++c) {  // sort every chunk
+      const int base = c * LONG_CHUNK, nv = min(LONG_CHUNK, n - base);
+      for (int i = tid; i < nv; i += LONG_THREADS) s[sp(i)] = seg[base + i];
+      __syncthreads();
+      smem_sort(s, LONG_CHUNK, nv, LONG_CHUNK);
+      for (int i = tid; i < nv; i += LONG_THREADS) seg[base + i] = s[sp(i)];
       __syncthreads();
     }
+    for (int k = 2 * LONG_CHUNK; k <= P; k <<= 1) {
+      {  // flip step of stage k on the segment
+        const int h = k >> 1;
+        for (int t = tid; t < (P >> 1); t += LONG_THREADS) {
+          const int lo = ((t & ~(h - 1)) << 1) | (t & (h - 1)), hi = lo ^ (k - 1);
+          if (hi < n) {
+            u64 a = seg[lo], b = seg[hi];
+            if (a > b) { seg[lo] = b; seg[hi] = a; }
+          }
+        }
+        __syncthreads();
+      }
+      for (int j = k >> 2; j >= LONG_CHUNK; j >>= 1) {  // disperse steps that span chunks
+        for (int t = tid; t < (P >> 1); t += LONG_THREADS) {
+          const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1)), hi = lo + j;
+          if (hi < n) {
+            u64 a = seg[lo], b = seg[hi];
+            if (a > b) { seg[lo] = b; seg[hi] = a; }
+          }
+        }
+        __syncthreads();
+      }
+      const bool last = (k == P);
+      for (int c = 0; c < nchunks; ++c) {  // disperse steps j = LONG_CHUNK / 2 .. 1, chunk by chunk
+        const int base = c * LONG_CHUNK, nv = min(LONG_CHUNK, n - base);
+        for (int i = tid; i < nv; i += LONG_THREADS) s[sp(i)] = seg[base + i];
+        __syncthreads();
+        smem_stage(s, LONG_CHUNK, nv, k, false);
+        if (last)
+          for (int i = tid; i < nv; i += LONG_THREADS) out[base + i] = (int)(unsigned)s[sp(i)];
+        else
+          for (int i = tid; i < nv; i += LONG_THREADS) seg[base + i] = s[sp(i)];
+        __syncthreads();
+      }
+    }
   }
-  for (int i = tid; i < n; i += BD_THREADS) ids_out[range.x + i] = (int)(unsigned)s_keys[i];
 }
 
 inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -429,8 +547,9 @@ inline int bits_for(long long n) {
 }
 
 struct BinLayout {  // carved from the caller's workspace
-  u64 *masks, *keys, *keys_tmp;
+  u64 *masks, *keys;
   unsigned *tile_count, *cursors, *base;
+  int *lists;  // {mid_count, long_count, long_cursor, 0, mid[T], long[T]} (tile_scan_kernel)
   int per_block, num_blocks;  // Gaussians per block / blocks of the shared-memory-histogram kernels (0 = global atomics)
 };
 
@@ -450,7 +569,8 @@ inline size_t layout_bytes(int num_points, int capacity, int num_tiles) {
   const size_t n = num_points > 0 ? num_points : 1, c = capacity > 0 ? capacity : 1, t = num_tiles > 0 ? num_tiles : 1;
   int per_block, num_blocks;
   block_partition(num_points, num_tiles, per_block, num_blocks);
-  return al256(8 * n) + 2 * al256(8 * c) + 2 * al256(4 * t) + al256(4 * t * (size_t)(num_blocks > 0 ? num_blocks : 1)) + 256;
+  return al256(8 * n) + al256(8 * c) + 2 * al256(4 * t) + al256(4 * t * (size_t)(num_blocks > 0 ? num_blocks : 1)) +
+         al256(4 * (2 * t + 4)) + 256;
 }
 
 inline BinLayout carve(void *workspace, int num_points, int capacity, int num_tiles) {
@@ -463,8 +583,8 @@ inline BinLayout carve(void *workspace, int num_points, int capacity, int num_ti
   L.tile_count = (unsigned *)ws; ws += al256(4 * t);
   L.cursors = (unsigned *)ws;    ws += al256(4 * t);
   L.base = (unsigned *)ws;       ws += al256(4 * t * (size_t)(L.num_blocks > 0 ? L.num_blocks : 1));
-  L.keys = (u64 *)ws;            ws += al256(8 * c);
-  L.keys_tmp = (u64 *)ws;
+  L.lists = (int *)ws;           ws += al256(4 * (2 * t + 4));
+  L.keys = (u64 *)ws;
   return L;
 }
 
@@ -494,7 +614,8 @@ int run_count(int num_points, const float *xys, const int32_t *radii, const floa
       GSR_CHECK_LAUNCH("bin_count_kernel");
     }
   }
-  tile_scan_kernel<<<1, 1024, 0, st>>>(num_tiles, L.tile_count, capacity, reinterpret_cast<int2 *>(tile_bins), L.cursors, meta);
+  tile_scan_kernel<<<1, 1024, 0, st>>>(num_tiles, L.tile_count, capacity, reinterpret_cast<int2 *>(tile_bins), L.cursors, meta,
+                                       L.lists);
   GSR_CHECK_LAUNCH("tile_scan_kernel");
   return GSR_OK;
 }
@@ -516,15 +637,19 @@ int run_fill_sort(int num_points, const float *xys, const float *depths, const i
         (int)block_width, capacity, L.cursors, L.keys);
     GSR_CHECK_LAUNCH("bin_fill_kernel");
   }
-  tile_sort_warp_kernel<false><<<cdiv(num_tiles, SORT_WARPS), 32 * SORT_WARPS, 0, st>>>(
-      num_tiles, reinterpret_cast<const int2 *>(tile_bins), L.keys, gaussian_ids_sorted);
+  const int2 *bins = reinterpret_cast<const int2 *>(tile_bins);
+  tile_sort_warp_kernel<false><<<cdiv(num_tiles, SORT_WARPS), 32 * SORT_WARPS, 0, st>>>(num_tiles, bins, L.keys, L.lists,
+                                                                                        gaussian_ids_sorted);
   GSR_CHECK_LAUNCH("tile_sort_warp_kernel<small>");
-  tile_sort_warp_kernel<true><<<cdiv(num_tiles, SORT_WARPS), 32 * SORT_WARPS, 0, st>>>(
-      num_tiles, reinterpret_cast<const int2 *>(tile_bins), L.keys, gaussian_ids_sorted);
-  GSR_CHECK_LAUNCH("tile_sort_warp_kernel<big>");
-  tile_sort_kernel<<<num_tiles, BD_THREADS, 0, st>>>(reinterpret_cast<const int2 *>(tile_bins), L.keys, L.keys_tmp,
-                                                     bits_for(num_points), gaussian_ids_sorted);
-  GSR_CHECK_LAUNCH("tile_sort_kernel");
+  // the two list-driven kernels: fixed grids, so nothing here depends on a device-side count
+  tile_sort_warp_kernel<true><<<2 * num_sms(), 32 * SORT_WARPS, 0, st>>>(num_tiles, bins, L.keys, L.lists, gaussian_ids_sorted);
+  GSR_CHECK_LAUNCH("tile_sort_warp_kernel<mid>");
+  static const cudaError_t attr = cudaFuncSetAttribute(tile_sort_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                       LONG_SMEM_BYTES);
+  GSR_CUDA(attr);
+  tile_sort_long_kernel<<<2 * num_sms(), LONG_THREADS, LONG_SMEM_BYTES, st>>>(num_tiles, bins, L.keys, L.lists,
+                                                                                   gaussian_ids_sorted);
+  GSR_CHECK_LAUNCH("tile_sort_long_kernel");
   return GSR_OK;
 }
 
@@ -606,7 +731,7 @@ GSR_API int gsr_bin_count(int num_points, const float *xys, const int32_t *radii
 
 GSR_API size_t gsr_bin_fill_workspace_bytes(int num_intersects) {
   const size_t c = num_intersects > 0 ? num_intersects : 1;
-  return 2 * ((8 * c + 255) & ~(size_t)255) + 256;  // keys + keys_tmp
+  return ((8 * c + 255) & ~(size_t)255) + 256;  // keys
 }
 
 GSR_API int gsr_bin_fill_sort(int num_points, int num_intersects, const float *xys, const float *depths,
@@ -628,7 +753,6 @@ GSR_API int gsr_bin_fill_sort(int num_points, int num_intersects, const float *x
   const int tiles_x = cdiv(img_width, block_width), tiles_y = cdiv(img_height, block_width);
   BinLayout L = carve(count_workspace, num_points, 1, tiles_x * tiles_y);
   L.keys = (u64 *)fill_workspace;
-  L.keys_tmp = (u64 *)((char *)fill_workspace + (((size_t)8 * num_intersects + 255) & ~(size_t)255));
   return run_fill_sort(num_points, xys, depths, radii, conics, opacities, tiles_x, tiles_y, block_width, num_intersects, L,
                        tile_bins, gaussian_ids_sorted, (cudaStream_t)stream);
 }

@@ -13,10 +13,10 @@
 //            as one float2 into a [G][33] matrix (row = Gaussian; the odd row stride keeps both phases conflict-free).
 //   phase 2  lane = GAUSSIAN (32 / G lanes share a row and split its 32 pixels).  Each lane sums its row:
 //                v_rgb += fac * v_out,  (sum w dx^2, sum w dx dy, sum w dy^2, sum w dx, sum w dy, sum w)
-//            in private registers, the 32 / G partial sums are combined with log2(32 / G) shuffles, and ONE set of nine
+//            in private registers (the geometric sums through pixel-grid moments of w: 3 instructions per pixel), the 32 / G partial sums are combined with log2(32 / G) shuffles, and ONE set of nine
 //            RED.ADD per (warp, Gaussian) goes to global memory.
 //
-// Per (warp, Gaussian) visit this costs ~38 + ~17 instructions and no dependent shuffle chain, against 116 for the
+// Per (warp, Gaussian) visit this costs ~36 + ~10 instructions and no dependent shuffle chain, against 116 for the
 // shuffle butterfly of blend_bwd.cu and 72 (10 of them SHFL on the critical path) for the affine-map scan of
 // blend_bwd_scan.cu.  Staging (double-buffered packed records, register prefetch), exact warp compaction and the early cut
 // at max(final_idx) are those of blend_bwd.cu (tried and dropped: staging two batches ahead so that tiles of <= 512 pairs
@@ -56,25 +56,49 @@ __device__ __forceinline__ void sum_rows(const RowGaussian &R, int rows, const f
   const int row = lane & (G - 1), sub = lane / G;
   const float2 *wrow = wf + row * kRowStride + sub * G;
   const float4 *vo = vout + sub * G;
-  // pixel p = sub * G + i sits at (x0 + (p & 7), y0 + (p >> 3)); G is a multiple of 8, so p & 7 = i & 7
-  const float gx = R.x - x0, gy = R.y - (y0 + (float)((sub * G) >> 3));
-  float a_r = 0.f, a_g = 0.f, a_b = 0.f, a_xx = 0.f, a_xy = 0.f, a_yy = 0.f, a_x = 0.f, a_y = 0.f, a_w = 0.f;
+  // Pixel p = sub * G + 8 r + c sits at (x0 + c, y0 + sub * NR + r).  With the block-centred constants cx = c - 3.5 and
+  // cy = r - (NR - 1) / 2 the geometric sums are polynomials in the Gaussian's offset (gx, gy) from the centre of the
+  // lane's pixels, dx = gx - cx, dy = gy - cy, whose coefficients are MOMENTS of w over the pixels:
+  //   sum w dx^2 = gx^2 W - 2 gx Mx + Mxx,  sum w dx dy = gx gy W - gx My - gy Mx + Mxy,  sum w dx = gx W - Mx, ...
+  // cx, cx^2 are compile-time constants and cy is constant per pixel row, so a pixel costs 1 FADD + 2 FFMA (row sums W_r,
+  // X_r = sum w cx, XX_r = sum w cx^2) instead of the 10 instructions of the direct form.
+  constexpr int NR = G / 8;
+  float a_r = 0.f, a_g = 0.f, a_b = 0.f;
+  float Wr[NR], Xr[NR], XXr[NR];
 #pragma unroll
-  for (int i = 0; i < G; ++i) {
-    const float2 e = wrow[i];
-    const float4 c = vo[i];
-    const float dx = gx - (float)(i & 7), dy = gy - (float)(i >> 3);
-    a_r += e.y * c.x;
-    a_g += e.y * c.y;
-    a_b += e.y * c.z;
-    const float wdx = e.x * dx, wdy = e.x * dy;
-    a_xx += wdx * dx;
-    a_xy += wdx * dy;
-    a_yy += wdy * dy;
-    a_x += wdx;
-    a_y += wdy;
-    a_w += e.x;
+  for (int r = 0; r < NR; ++r) {
+    Wr[r] = Xr[r] = XXr[r] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float2 e = wrow[8 * r + c];
+      const float4 v = vo[8 * r + c];
+      a_r += e.y * v.x;
+      a_g += e.y * v.y;
+      a_b += e.y * v.z;
+      const float cx = (float)c - 3.5f;
+      Wr[r] += e.x;
+      Xr[r] += e.x * cx;
+      XXr[r] += e.x * (cx * cx);
+    }
   }
+  float W = 0.f, Mx = 0.f, Mxx = 0.f, My = 0.f, Myy = 0.f, Mxy = 0.f;
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    const float cy = (float)r - 0.5f * (float)(NR - 1);
+    W += Wr[r];
+    Mx += Xr[r];
+    Mxx += XXr[r];
+    My += cy * Wr[r];
+    Myy += (cy * cy) * Wr[r];
+    Mxy += cy * Xr[r];
+  }
+  const float gx = R.x - (x0 + 3.5f), gy = R.y - (y0 + (float)(sub * NR) + 0.5f * (float)(NR - 1));
+  float a_xx = gx * (gx * W - 2.f * Mx) + Mxx;
+  float a_xy = gx * (gy * W - My) - gy * Mx + Mxy;
+  float a_yy = gy * (gy * W - 2.f * My) + Myy;
+  float a_x = gx * W - Mx;
+  float a_y = gy * W - My;
+  float a_w = W;
 #pragma unroll
   for (int o = G; o < 32; o <<= 1) {
     a_r += __shfl_xor_sync(full, a_r, o);
@@ -209,6 +233,7 @@ blend_backward_tr_kernel(int tiles_x, int img_w, int img_h, const int *__restric
       float4 q1 = S.rec[buf][1][slot];
       float4 q2 = S.rec[buf][2][slot];
       int slot_n = lp[1];  // the list is padded: reading one or two entries past its end is harmless
+#pragma unroll 2
       for (int k = 0; k < take; ++k) {
         const float2 n0 = *reinterpret_cast<const float2 *>(&S.rec[buf][0][slot_n]);
         const float4 n1 = S.rec[buf][1][slot_n];

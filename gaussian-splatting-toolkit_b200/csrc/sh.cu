@@ -190,6 +190,114 @@ sh_backward_kernel(int n, int K, int deg_use, const float *__restrict__ viewdirs
   stage_out(v_coeffs + (size_t)g0 * row_len, smem, rows * row_len, row_len, stride, vec_ok != 0);
 }
 
+// ---- row lengths that are a multiple of 4 floats (K = 4, 16: degrees 1 and 3) -------------------------------------------
+// The block of 128 rows is moved with 16-byte cp.async copies (LDGSTS: global -> shared without passing through
+// registers, every copy of a thread in flight at once) into rows padded to a stride of 3K + 4 floats: 16-byte aligned and
+// = 4 (mod 8) words, so the row-per-thread 128-bit shared-memory accesses of the compute phase are conflict-free (a
+// quarter warp covers eight different 16-byte slots of a 128-byte wavefront).  All index arithmetic is compile-time.
+__device__ __forceinline__ void sh_cp_async16(float *smem_dst, const float *gmem_src) {
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(gmem_src) : "memory");
+}
+
+template <int K>
+__global__ void __launch_bounds__(SH_THREADS)
+sh_forward_vec_kernel(int n, int deg_use, const float *__restrict__ viewdirs, const float *__restrict__ coeffs,
+                      float *__restrict__ colors) {
+  constexpr int RL = 3 * K, ST = (RL % 8 == 4) ? RL : RL + 4;  // = 4 (mod 8) words
+  __shared__ __align__(16) float s[SH_THREADS * ST];
+  const int tid = threadIdx.x;
+  const int g0 = blockIdx.x * SH_THREADS;
+  const int rows = min(SH_THREADS, n - g0);
+  const float *src = coeffs + (size_t)g0 * RL;
+  const int nvec = rows * (RL / 4);
+#pragma unroll
+  for (int q = 0; q < RL / 4; ++q) {
+    const int i = tid + q * SH_THREADS;
+    if (i < nvec) {
+      const int r = i / (RL / 4), c = i - r * (RL / 4);
+      sh_cp_async16(s + r * ST + 4 * c, src + 4 * i);
+    }
+  }
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+  float Y[25];
+  const int g = g0 + tid;
+  if (tid < rows) sh_basis(deg_use, viewdirs[3 * (size_t)g], viewdirs[3 * (size_t)g + 1], viewdirs[3 * (size_t)g + 2], Y);
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+  __syncthreads();
+  if (tid < rows) {
+    float c[RL];
+#pragma unroll
+    for (int q = 0; q < RL / 4; ++q) {
+      const float4 v = *reinterpret_cast<const float4 *>(s + tid * ST + 4 * q);
+      c[4 * q] = v.x; c[4 * q + 1] = v.y; c[4 * q + 2] = v.z; c[4 * q + 3] = v.w;
+    }
+    float out[3];
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      float acc = GSR_SH_C0 * c[ch];
+      if (K >= 4 && deg_use >= 1) acc += Y[1] * c[3 + ch] + Y[2] * c[6 + ch] + Y[3] * c[9 + ch];
+      if (K >= 9 && deg_use >= 2) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 4; k < 9; ++k) t += Y[k] * c[(3 * k + ch) % RL];
+        acc += t;
+      }
+      if (K >= 16 && deg_use >= 3) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 9; k < 16; ++k) t += Y[k] * c[(3 * k + ch) % RL];
+        acc += t;
+      }
+      out[ch] = acc;
+    }
+    colors[3 * (size_t)g] = out[0];
+    colors[3 * (size_t)g + 1] = out[1];
+    colors[3 * (size_t)g + 2] = out[2];
+  }
+}
+
+template <int K>
+__global__ void __launch_bounds__(SH_THREADS)
+sh_backward_vec_kernel(int n, int deg_use, const float *__restrict__ viewdirs, const float *__restrict__ v_colors,
+                       float *__restrict__ v_coeffs) {
+  constexpr int RL = 3 * K, ST = (RL % 8 == 4) ? RL : RL + 4;  // = 4 (mod 8) words
+  __shared__ __align__(16) float s[SH_THREADS * ST];
+  const int tid = threadIdx.x;
+  const int g0 = blockIdx.x * SH_THREADS;
+  const int rows = min(SH_THREADS, n - g0);
+  const int Ku = num_sh_bases(deg_use);
+  if (tid < rows) {
+    const int g = g0 + tid;
+    float Y[25];
+    Y[0] = GSR_SH_C0;
+    sh_basis(deg_use, viewdirs[3 * (size_t)g], viewdirs[3 * (size_t)g + 1], viewdirs[3 * (size_t)g + 2], Y);
+    const float v[3] = {v_colors[3 * (size_t)g], v_colors[3 * (size_t)g + 1], v_colors[3 * (size_t)g + 2]};
+    float o[RL];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const float y = (k < Ku) ? Y[k] : 0.f;
+      o[3 * k] = y * v[0];
+      o[3 * k + 1] = y * v[1];
+      o[3 * k + 2] = y * v[2];
+    }
+#pragma unroll
+    for (int q = 0; q < RL / 4; ++q)
+      *reinterpret_cast<float4 *>(s + tid * ST + 4 * q) = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+  }
+  __syncthreads();
+  float4 *dst = reinterpret_cast<float4 *>(v_coeffs + (size_t)g0 * RL);
+  const int nvec = rows * (RL / 4);
+#pragma unroll
+  for (int q = 0; q < RL / 4; ++q) {
+    const int i = tid + q * SH_THREADS;
+    if (i < nvec) {
+      const int r = i / (RL / 4), c = i - r * (RL / 4);
+      __stcs(dst + i, *reinterpret_cast<const float4 *>(s + r * ST + 4 * c));  // written once, read by the optimizer later
+    }
+  }
+}
+
 // Multi-view SH adjoint: v_coeffs[n,k,c] = sum_v Y_k(means[n] - cam[v]) * v_colors_v[n,c].
 // This is the compute half of the view-parallel gradient exchange: instead of all-reducing the
 // 3K-float SH gradient of every rank (192 B per Gaussian at degree 3), ranks exchange only the 3-float colour
@@ -310,8 +418,15 @@ GSR_API int gsr_compute_sh_forward(int num_points, int degree, int degrees_to_us
   const size_t smem = (size_t)SH_THREADS * sh_row_stride(3 * K) * sizeof(float);
   // every CTA's block starts at g0*3K floats: 16-byte aligned iff the base is and 128*3K*4 % 16 == 0 (always)
   const int vec_ok = ((uintptr_t)coeffs % 16 == 0) ? 1 : 0;
-  sh_forward_kernel<<<cdiv(num_points, SH_THREADS), SH_THREADS, smem, (cudaStream_t)stream>>>(
-      num_points, K, degrees_to_use, viewdirs, coeffs, colors, vec_ok);
+  if (vec_ok && K == 16)
+    sh_forward_vec_kernel<16><<<cdiv(num_points, SH_THREADS), SH_THREADS, 0, (cudaStream_t)stream>>>(
+        num_points, degrees_to_use, viewdirs, coeffs, colors);
+  else if (vec_ok && K == 4)
+    sh_forward_vec_kernel<4><<<cdiv(num_points, SH_THREADS), SH_THREADS, 0, (cudaStream_t)stream>>>(
+        num_points, degrees_to_use, viewdirs, coeffs, colors);
+  else
+    sh_forward_kernel<<<cdiv(num_points, SH_THREADS), SH_THREADS, smem, (cudaStream_t)stream>>>(
+        num_points, K, degrees_to_use, viewdirs, coeffs, colors, vec_ok);
   GSR_CHECK_LAUNCH("sh_forward_kernel");
   return GSR_OK;
 }
@@ -328,8 +443,15 @@ GSR_API int gsr_compute_sh_backward(int num_points, int degree, int degrees_to_u
   const int K = num_sh_bases(degree);
   const size_t smem = (size_t)SH_THREADS * sh_row_stride(3 * K) * sizeof(float);
   const int vec_ok = ((uintptr_t)v_coeffs % 16 == 0) ? 1 : 0;
-  sh_backward_kernel<<<cdiv(num_points, SH_THREADS), SH_THREADS, smem, (cudaStream_t)stream>>>(
-      num_points, K, degrees_to_use, viewdirs, v_colors, v_coeffs, vec_ok);
+  if (vec_ok && K == 16)
+    sh_backward_vec_kernel<16><<<cdiv(num_points, SH_THREADS), SH_THREADS, 0, (cudaStream_t)stream>>>(
+        num_points, degrees_to_use, viewdirs, v_colors, v_coeffs);
+  else if (vec_ok && K == 4)
+    sh_backward_vec_kernel<4><<<cdiv(num_points, SH_THREADS), SH_THREADS, 0, (cudaStream_t)stream>>>(
+        num_points, degrees_to_use, viewdirs, v_colors, v_coeffs);
+  else
+    sh_backward_kernel<<<cdiv(num_points, SH_THREADS), SH_THREADS, smem, (cudaStream_t)stream>>>(
+        num_points, K, degrees_to_use, viewdirs, v_colors, v_coeffs, vec_ok);
   GSR_CHECK_LAUNCH("sh_backward_kernel");
   return GSR_OK;
 }

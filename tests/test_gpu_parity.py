@@ -370,6 +370,35 @@ def test_fast_binning_large_boxes_and_ties():
     assert m == M and torch.equal(ids, vs) and torch.equal(bins2, bins)
 
 
+@pytest.mark.parametrize("n,img,rmax", [(3000, 64, 40), (12_000, 64, 60), (40_000, 48, 100), (70_000, 32, 100)])
+def test_fast_binning_long_tiles(n, img, rmax):
+    """Tiles with thousands of pairs (object-centric scenes): every tile of a small image holds most of the Gaussians, so
+    the per-tile sort takes the 1024-thread bitonic path — in shared memory up to 8192 pairs, chunked with in-place
+    global steps above (the 40k / 70k cases) — and must still equal the 64-bit key sort, exact depth ties included."""
+    from rasterizer import cuda as C
+
+    g = torch.Generator().manual_seed(n)
+    xys = (torch.rand(n, 2, generator=g) * img).cuda()
+    depths = (1.0 + 9.0 * torch.rand(n, generator=g)).cuda()
+    depths[::5] = 3.0                                   # many exact ties: Gaussian-index order decides
+    radii = torch.randint(rmax // 2, rmax, (n,), generator=g, dtype=torch.int32).cuda()
+    conics = torch.tensor([[1e-4, 0.0, 1e-4]]).repeat(n, 1).cuda()
+    opac = torch.full((n,), 0.8).cuda()
+    H = W = img
+    tiles_1d = (img + 15) // 16
+    tiles = C.count_tiles_tight(xys, radii, conics, opac, H, W, 16)
+    cum = torch.cumsum(tiles, 0, dtype=torch.int32)
+    M = int(cum[-1])
+    isect, gids = C.map_gaussian_to_intersects_tight(n, M, xys, depths, radii, conics, opac, cum, H, W, 16)
+    ks, vs = C.sort_intersects(isect, gids, tiles_1d * tiles_1d)
+    bins = C.get_tile_bin_edges(M, ks, (tiles_1d, tiles_1d, 1))
+    m, ids, bins2 = C.bin_gaussians_fast(xys, depths, radii, conics, opac, H, W, 16)
+    longest = int((bins[:, 1] - bins[:, 0]).max())
+    print(f"[long tiles] n={n} {img}x{img}: M={M}, longest tile {longest}")
+    assert longest > 1024
+    assert m == M and torch.equal(bins2, bins) and torch.equal(ids, vs)
+
+
 def test_sh_backward_multiview_equals_sum_of_views(oracle):
     """gsr_compute_sh_backward_multiview == sum over views of the single-view adjoint (and of the oracle's)."""
     from rasterizer import cuda as C
