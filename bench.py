@@ -398,6 +398,28 @@ def fused_leg(torch, s, scene_np, steps, warmup):
             "what": "render_gaussians(raw parameters) fwd+bwd, resident inputs; not the headline (reference-facing API) path"}
 
 
+def host_link_gbs(torch, pv):
+    """H2D / D2H rate of the e2e leg's own pinned image buffers (3 copies each, CUDA events) — outside every timed
+    region; reported next to `e2e` so that a box with a slow host link is recognisable in the record."""
+    try:
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        torch.cuda.synchronize()
+        e[0].record()
+        for _ in range(3):
+            pv.d_vimg[0].copy_(pv.h_vimg, non_blocking=True)
+        e[1].record()
+        dimg = pv.d_vimg[0]
+        for _ in range(3):
+            pv.h_img.copy_(dimg, non_blocking=True)
+        e[2].record()
+        torch.cuda.synchronize()
+        nbytes = 3 * pv.h_vimg.numel() * 4
+        return {"h2d": nbytes / (e[0].elapsed_time(e[1]) * 1e-3) / 1e9, "d2h": nbytes / (e[1].elapsed_time(e[2]) * 1e-3) / 1e9,
+                "what": "3 x 24.9 MB copies between the leg's pinned host buffers and HBM, outside the timed regions"}
+    except Exception as ex:  # diagnostic only
+        return {"error": str(ex)}
+
+
 def workload_text(name, scene_np):
     N, W, H = scene_np["means3d"].shape[0], scene_np["img_width"], scene_np["img_height"]
     return (f"{name}: {N} Gaussians, {W}x{H}, SH degree {scene_np['sh_degree']}, fwd+bwd, block_width "
@@ -745,6 +767,7 @@ def main():
         if world > 1:
             dist.destroy_process_group()
         return
+    host_link = host_link_gbs(torch, pv)  # diagnostic: what this box's PCIe path gives the leg's own pinned buffers
     e2e_ms = timed_loop(torch, dist, world, e2e_step, args.steps, args.warmup, finish=pv.finish)
     e2e_value = world * args.steps / (e2e_ms * 1e-3)
     _binning.check()  # every asynchronous call of the e2e leg stayed within its pair-buffer capacity (raises otherwise)
@@ -782,7 +805,7 @@ def main():
                                     "no explicit flush)"},
             "stages_ms": stages,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": pv.h2d,
-                    "d2h_bytes_per_step": pv.d2h,
+                    "d2h_bytes_per_step": pv.d2h, "host_link_gbs": host_link,
                     "api": "rasterizer.project_gaussians + spherical_harmonics + rasterize_gaussians + autograd backward",
                     "note": "training-operator e2e: the Gaussian parameters and their 236 N bytes of gradients stay resident "
                             "in HBM (as in training); per view the camera matrices + upstream image / alpha gradients come "
