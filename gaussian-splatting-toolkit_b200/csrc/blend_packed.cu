@@ -306,8 +306,14 @@ blend_packed_backward_kernel(int tiles_x, int img_w, int img_h, int block_width,
   }
 }
 
-// blend_packed_scan.cu: the Gaussian-parallel adjoint (default for 16x16 tiles), GSR_PACKED_BWD=pixel selects the kernel above
-int blend_packed_bwd_use_scan();
+// 16x16 tiles: blend_packed_tr.cu (two-phase transposing adjoint, default) or blend_packed_scan.cu (GSR_PACKED_BWD=scan);
+// GSR_PACKED_BWD=pixel selects the kernel above
+int blend_packed_bwd_mode();  // 0 = pixel, 1 = scan, 2 = tr
+int launch_blend_packed_backward_tr(dim3 grid, cudaStream_t st, int img_w, int img_h, int num_points,
+                                    const int *gaussian_ids_sorted, const int2 *tile_bins, const float4 *rec,
+                                    const float *background, const float *final_Ts, const int *final_idx,
+                                    const float *v_output, const float *v_output_depth, const float *v_output_alpha,
+                                    float *grad_rec);
 int launch_blend_packed_backward_scan(dim3 grid, cudaStream_t st, int img_w, int img_h, int num_points,
                                       const int *gaussian_ids_sorted, const int2 *tile_bins, const float4 *rec,
                                       const float *background, const float *final_Ts, const int *final_idx,
@@ -369,8 +375,14 @@ GSR_API int gsr_blend_packed_backward(unsigned img_height, unsigned img_width, u
   const unsigned threads = cdiv(block_width * block_width, 32) * 32;
   const float4 *rec = reinterpret_cast<const float4 *>(records);
   const int2 *bins = reinterpret_cast<const int2 *>(tile_bins);
-  if (block_width == 16 && blend_packed_bwd_use_scan()) {
+  const int mode = block_width == 16 ? blend_packed_bwd_mode() : 0;
+  if (mode != 0)
     GSR_REQUIRE((uintptr_t)grad_records % 16 == 0, GSR_ERR_INVALID_ARGUMENT, "blend_packed_backward: grad_records must be 16-byte aligned");
+  if (mode == 2)
+    return launch_blend_packed_backward_tr(grid, st, (int)img_width, (int)img_height, num_points, gaussian_ids_sorted, bins,
+                                           rec, background, final_Ts, final_idx, v_output, v_output_depth, v_output_alpha,
+                                           grad_records);
+  if (mode == 1) {
     return launch_blend_packed_backward_scan(grid, st, (int)img_width, (int)img_height, num_points, gaussian_ids_sorted, bins,
                                              rec, background, final_Ts, final_idx, v_output, v_output_depth, v_output_alpha,
                                              grad_records);

@@ -242,15 +242,7 @@ blend_packed_backward_scan_kernel(int tiles_x, int img_w, int img_h, int num_poi
   }
 }
 
-// GSR_PACKED_BWD = scan (default) | pixel
-int blend_packed_bwd_use_scan() {
-  static const int v = [] {
-    const char *e = getenv("GSR_PACKED_BWD");
-    return (e && e[0] == 'p') ? 0 : 1;
-  }();
-  return v;
-}
-
+// selected with GSR_PACKED_BWD=scan (blend_packed_tr.cu holds the switch and the default kernel)
 int launch_blend_packed_backward_scan(dim3 grid, cudaStream_t st, int img_w, int img_h, int num_points,
                                       const int *gaussian_ids_sorted, const int2 *tile_bins, const float4 *rec,
                                       const float *background, const float *final_Ts, const int *final_idx,
