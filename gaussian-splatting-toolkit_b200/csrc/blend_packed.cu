@@ -28,7 +28,8 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 // stage the record of Gaussian g into slot `slot` of ring buffer `buf`
-__device__ __forceinline__ void stage_packed(float4 (*s_rec)[3][BLEND_THREADS], int buf, int slot, int g, int n,
+template <int SLOTS>
+__device__ __forceinline__ void stage_packed(float4 (*s_rec)[3][SLOTS], int buf, int slot, int g, int n,
                                              const float4 *__restrict__ rec) {
   cp_async16(&s_rec[buf][0][slot], rec + g);
   cp_async16(&s_rec[buf][1][slot], rec + n + g);
@@ -42,8 +43,10 @@ blend_packed_forward_kernel(int tiles_x, int img_w, int img_h, int block_width, 
                             const float4 *__restrict__ rec, const float *__restrict__ background,
                             float *__restrict__ out_img, float *__restrict__ out_depth, float *__restrict__ final_Ts,
                             int *__restrict__ final_idx) {
-  __shared__ float4 s_rec[2][3][BLEND_THREADS];
-  __shared__ unsigned char s_list[BLEND_THREADS / 32][BLEND_THREADS];
+  // slot kNull of every plane holds a record that never contributes (opacity 0): the survivor lists are padded with it
+  constexpr int kNull = BLEND_THREADS, kUnroll = 4;
+  __shared__ float4 s_rec[2][3][BLEND_THREADS + 1];
+  __shared__ unsigned short s_list[BLEND_THREADS / 32][BLEND_THREADS + kUnroll + 2];
 
   const unsigned full = 0xffffffffu;
   const int tile_x = blockIdx.x, tile_y = blockIdx.y;
@@ -54,7 +57,7 @@ blend_packed_forward_kernel(int tiles_x, int img_w, int img_h, int block_width, 
   const int ipx = tile_x * block_width + lx, ipy = tile_y * block_width + ly;
   const bool inside = (ly < block_width) && (ipx < img_w) && (ipy < img_h);
   const float px = (float)ipx, py = (float)ipy;
-  bool done = !inside;
+  const bool done0 = !inside;
   const float fx0 = (float)__reduce_min_sync(full, inside ? ipx : 0x7fffffff);
   const float fx1 = (float)__reduce_max_sync(full, inside ? ipx : -0x7fffffff);
   const float fy0 = (float)__reduce_min_sync(full, inside ? ipy : 0x7fffffff);
@@ -65,6 +68,9 @@ blend_packed_forward_kernel(int tiles_x, int img_w, int img_h, int block_width, 
   float T = 1.f;
   int cur_idx = 0;
   float acc_r = 0.f, acc_g = 0.f, acc_b = 0.f, acc_d = 0.f;
+  // a finished pixel has slot_stop = -1; contributors need slot < slot_stop (see blend_fwd.cu)
+  int slot_stop = done0 ? -1 : 0x7fffffff;
+  if (tr < 6) s_rec[tr & 1][tr >> 1][kNull] = tr < 2 ? make_float4(0.f, 0.f, -1e30f, -1e30f) : make_float4(0.f, 0.f, 0.f, 0.f);
 
   // 2-stage cp.async ring: batch b lives in buffer b & 1; its copies were issued one iteration earlier
   if (num_batches > 0 && range.x + tr < range.y)
@@ -75,40 +81,52 @@ blend_packed_forward_kernel(int tiles_x, int img_w, int img_h, int block_width, 
     const int batch_start = range.x + nthreads * b;
     cp_async_wait_all();  // this thread's copies for batch b have landed ...
     // ... and the barrier publishes everyone's; it also tells that buffer buf ^ 1 (batch b-1) is no longer read
-    if (__syncthreads_count(done) >= nthreads) break;
+    if (__syncthreads_count(slot_stop < 0) >= nthreads) break;
     {
       const int nxt = batch_start + nthreads + tr;
       if (nxt < range.y) stage_packed(s_rec, buf ^ 1, tr, gaussian_ids_sorted[nxt], num_points, rec);
       cp_async_commit();
     }
-    if (__all_sync(full, done)) continue;
+    if (__all_sync(full, slot_stop < 0)) continue;
     const int batch_size = min(nthreads, range.y - batch_start);
-    const int n_list = compact_survivors(s_rec[buf][0], s_rec[buf][1], 0, batch_size, fx0, fx1, fy0, fy1, s_list[warp], lane);
-    for (int i = 0; i < n_list; ++i) {
-      const int t = s_list[warp][i];
-      const float4 q0 = s_rec[buf][0][t];
-      const float4 q1 = s_rec[buf][1][t];
-      const float dx = q0.x - px, dy = q0.y - py;
-      const float power = dx * (q1.x * dx + q1.y * dy) + q1.z * dy * dy;
-      const float alpha = fminf(0.999f, q1.w * exp2f(power));
-      const bool contrib = !done && !(power > 0.f || alpha < 1.f / 255.f);
-      if (__any_sync(full, contrib)) {
+    const unsigned short *lp = s_list[warp];
+    const int n_list = compact_survivors<unsigned short, kUnroll + 2>(s_rec[buf][0], s_rec[buf][1], 0, batch_size, fx0, fx1,
+                                                                      fy0, fy1, s_list[warp], lane, kNull);
+    // software-pipelined walk, kUnroll survivors per trip, one all-done vote per trip (blend_fwd.cu)
+    int slot = lp[0];
+    float2 c0 = *reinterpret_cast<const float2 *>(&s_rec[buf][0][slot]);
+    float4 q1 = s_rec[buf][1][slot];
+    float4 q2 = s_rec[buf][2][slot];
+    int slot_n = lp[1];
+    int last_slot = -1;
+    for (int i = 0; i < n_list; i += kUnroll) {
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const float2 n0 = *reinterpret_cast<const float2 *>(&s_rec[buf][0][slot_n]);
+        const float4 n1 = s_rec[buf][1][slot_n];
+        const float4 n2 = s_rec[buf][2][slot_n];
+        const int slot_nn = lp[i + u + 2];
+        const float dx = c0.x - px, dy = c0.y - py;
+        const float power = dx * (q1.x * dx + q1.y * dy) + q1.z * dy * dy;
+        const float alpha = fminf(0.999f, q1.w * exp2f(power));
+        const bool contrib = (slot < slot_stop) && !(power > 0.f || alpha < 1.f / 255.f);
         const float next_T = T * (1.f - alpha);
         const bool stop = contrib && (next_T <= 1e-4f);
-        done = done || stop;
+        if (stop) slot_stop = -1;
         if (contrib && !stop) {
-          const float4 q2 = s_rec[buf][2][t];
           const float vis = alpha * T;
           acc_r += q2.x * vis;
           acc_g += q2.y * vis;
           acc_b += q2.z * vis;
           if (DEPTH) acc_d += q2.w * vis;
           T = next_T;
-          cur_idx = batch_start + t;
+          last_slot = slot;
         }
-        if (__all_sync(full, done)) break;
+        slot = slot_n; c0 = n0; q1 = n1; q2 = n2; slot_n = slot_nn;
       }
+      if (__all_sync(full, slot_stop < 0)) break;
     }
+    if (last_slot >= 0) cur_idx = batch_start + last_slot;
   }
   if (inside) {
     const int pix = ipy * img_w + ipx;
