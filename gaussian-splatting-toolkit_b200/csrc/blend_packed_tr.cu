@@ -14,9 +14,10 @@ namespace {
 constexpr int kRowStride = 33;  // float2 elements per matrix row (32 pixels + 1 pad)
 constexpr int G = 16;           // rows (Gaussians) per group
 
+template <int BATCH>
 struct PkTrSmem {
-  float4 rec[2][3][BLEND_THREADS];
-  int gid[2][BLEND_THREADS];
+  float4 rec[2][3][BATCH];
+  int gid[2][BATCH];
   float2 wf[BLEND_THREADS / 32][G * kRowStride];
   float4 vout[BLEND_THREADS / 32][32];  // {v_out_r, v_out_g, v_out_b, v_out_depth}
   unsigned char list[BLEND_THREADS / 32][BLEND_THREADS + 8];
@@ -108,8 +109,10 @@ __device__ __forceinline__ void pkt_sum_rows(const RowGaussian &R, int rows, con
   }
 }
 
-template <bool DEPTH>
-__global__ void __launch_bounds__(BLEND_THREADS, 3)
+// BATCH = records per ring stage.  <256, 3>: 66.6 KB of shared memory, three CTAs / SM; <128, 4>: 53.3 KB and 64 registers,
+// four CTAs / SM (32 warps) at twice the number of batch barriers.
+template <bool DEPTH, int BATCH, int MIN_CTAS>
+__global__ void __launch_bounds__(BLEND_THREADS, MIN_CTAS)
 blend_packed_backward_tr_kernel(int tiles_x, int img_w, int img_h, int num_points,
                                 const int *__restrict__ gaussian_ids_sorted, const int2 *__restrict__ tile_bins,
                                 const float4 *__restrict__ rec, const float *__restrict__ background,
@@ -117,12 +120,12 @@ blend_packed_backward_tr_kernel(int tiles_x, int img_w, int img_h, int num_point
                                 const float *__restrict__ v_output, const float *__restrict__ v_output_depth,
                                 const float *__restrict__ v_output_alpha, float *__restrict__ grad_rec) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  PkTrSmem &S = *reinterpret_cast<PkTrSmem *>(smem_raw);
+  PkTrSmem<BATCH> &S = *reinterpret_cast<PkTrSmem<BATCH> *>(smem_raw);
 
   const unsigned full = 0xffffffffu;
   const int tile_x = blockIdx.x, tile_y = blockIdx.y;
   const int tile_id = tile_y * tiles_x + tile_x;
-  const int tr = threadIdx.x, nthreads = BLEND_THREADS, lane = tr & 31, warp = tr >> 5;
+  const int tr = threadIdx.x, nthreads = BATCH, lane = tr & 31, warp = tr >> 5;  // nthreads: records per batch
   int lx, ly;
   map_pixel(16, lx, ly);
   const int ipx = tile_x * 16 + lx, ipy = tile_y * 16 + ly;
@@ -155,7 +158,7 @@ blend_packed_backward_tr_kernel(int tiles_x, int img_w, int img_h, int num_point
   if (lane == 0) S.warp_max[warp] = warp_bin_final;
   __syncthreads();
   int cta_bin_final = -1;
-  for (int w = 0; w < (nthreads >> 5); ++w) cta_bin_final = max(cta_bin_final, S.warp_max[w]);
+  for (int w = 0; w < BLEND_THREADS / 32; ++w) cta_bin_final = max(cta_bin_final, S.warp_max[w]);
 
   const int end = min(range.y, cta_bin_final + 1);
   const int count = end - range.x;
@@ -169,7 +172,7 @@ blend_packed_backward_tr_kernel(int tiles_x, int img_w, int img_h, int num_point
     pkt_cp_async16(&S.rec[buf][1][tr], rec + num_points + gid);
     pkt_cp_async16(&S.rec[buf][2][tr], rec + 2 * (size_t)num_points + gid);
   };
-  if (end - 1 - tr >= range.x) stage(0, end - 1 - tr);
+  if (tr < BATCH && end - 1 - tr >= range.x) stage(0, end - 1 - tr);
   pkt_commit();
 
   RowGaussian R;
@@ -186,7 +189,7 @@ blend_packed_backward_tr_kernel(int tiles_x, int img_w, int img_h, int num_point
     __syncthreads();
     {
       const int nxt = batch_end - nthreads - tr;
-      if (nxt >= range.x) stage(buf ^ 1, nxt);
+      if (tr < BATCH && nxt >= range.x) stage(buf ^ 1, nxt);
       pkt_commit();
     }
     const int batch_size = min(nthreads, batch_end + 1 - range.x);
@@ -268,27 +271,36 @@ int blend_packed_bwd_mode() {
   return v;
 }
 
+template <bool DEPTH, int BATCH, int MIN_CTAS>
+static int launch_pkt(dim3 grid, cudaStream_t st, int img_w, int img_h, int num_points, const int *gaussian_ids_sorted,
+                      const int2 *tile_bins, const float4 *rec, const float *background, const float *final_Ts,
+                      const int *final_idx, const float *v_output, const float *v_output_depth, const float *v_output_alpha,
+                      float *grad_rec) {
+  static const cudaError_t attr = cudaFuncSetAttribute(blend_packed_backward_tr_kernel<DEPTH, BATCH, MIN_CTAS>,
+                                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PkTrSmem<BATCH>));
+  GSR_CUDA(attr);
+  blend_packed_backward_tr_kernel<DEPTH, BATCH, MIN_CTAS><<<grid, BLEND_THREADS, sizeof(PkTrSmem<BATCH>), st>>>(
+      (int)grid.x, img_w, img_h, num_points, gaussian_ids_sorted, tile_bins, rec, background, final_Ts, final_idx, v_output,
+      v_output_depth, v_output_alpha, grad_rec);
+  GSR_CHECK_LAUNCH("blend_packed_backward_tr_kernel");
+  return GSR_OK;
+}
+
 int launch_blend_packed_backward_tr(dim3 grid, cudaStream_t st, int img_w, int img_h, int num_points,
                                     const int *gaussian_ids_sorted, const int2 *tile_bins, const float4 *rec,
                                     const float *background, const float *final_Ts, const int *final_idx,
                                     const float *v_output, const float *v_output_depth, const float *v_output_alpha,
                                     float *grad_rec) {
-  static const cudaError_t a1 = cudaFuncSetAttribute(blend_packed_backward_tr_kernel<true>,
-                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PkTrSmem));
-  static const cudaError_t a2 = cudaFuncSetAttribute(blend_packed_backward_tr_kernel<false>,
-                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PkTrSmem));
-  GSR_CUDA(a1);
-  GSR_CUDA(a2);
-  if (v_output_depth)
-    blend_packed_backward_tr_kernel<true><<<grid, BLEND_THREADS, sizeof(PkTrSmem), st>>>(
-        (int)grid.x, img_w, img_h, num_points, gaussian_ids_sorted, tile_bins, rec, background, final_Ts, final_idx, v_output,
-        v_output_depth, v_output_alpha, grad_rec);
-  else
-    blend_packed_backward_tr_kernel<false><<<grid, BLEND_THREADS, sizeof(PkTrSmem), st>>>(
-        (int)grid.x, img_w, img_h, num_points, gaussian_ids_sorted, tile_bins, rec, background, final_Ts, final_idx, v_output,
-        nullptr, v_output_alpha, grad_rec);
-  GSR_CHECK_LAUNCH("blend_packed_backward_tr_kernel");
-  return GSR_OK;
+  // GSR_PACKED_TR_BATCH = 256 (default, three CTAs / SM) | 128 (four CTAs / SM: measured 20 us SLOWER at cfg2) — read once
+  static const int batch = [] {
+    const char *e = getenv("GSR_PACKED_TR_BATCH");
+    return (e && e[0] == '1') ? 128 : 256;
+  }();
+#define GSR_PKT_ARGS grid, st, img_w, img_h, num_points, gaussian_ids_sorted, tile_bins, rec, background, final_Ts, final_idx, \
+                     v_output, v_output_depth, v_output_alpha, grad_rec
+  if (batch == 256) return v_output_depth ? launch_pkt<true, 256, 3>(GSR_PKT_ARGS) : launch_pkt<false, 256, 3>(GSR_PKT_ARGS);
+  return v_output_depth ? launch_pkt<true, 128, 4>(GSR_PKT_ARGS) : launch_pkt<false, 128, 4>(GSR_PKT_ARGS);
+#undef GSR_PKT_ARGS
 }
 
 }  // namespace gsr
