@@ -665,7 +665,9 @@ def main():
     # backward kernels of the resident leg write straight into its segments, the autograd leg packs into it
     from rasterizer.view_parallel import GradientBucket
 
-    bucket = GradientBucket(N, s["sh_coeffs"].shape[1], device=s["means3d"].device) if world > 1 else None
+    bucket = (GradientBucket(N, s["sh_coeffs"].shape[1], device=s["means3d"].device,
+                             symmetric=os.environ.get("GSR_OWN_TAIL") == "1" and os.environ.get("GSR_NO_P2P") != "1")
+              if world > 1 else None)
     ar_events = []
     from rasterizer.view_parallel import GradientExchange, PeerColorGrads
 

@@ -312,15 +312,31 @@ struct ShViews {
 
 __global__ void __launch_bounds__(SH_THREADS)
 sh_backward_multiview_kernel(int n, int K, int deg_use, int num_views, const float *__restrict__ means3d,
-                             const ShViews views, float *__restrict__ v_coeffs, int vec_ok) {
+                             const ShViews views, float *__restrict__ v_coeffs, int vec_ok, int vc_vec_ok) {
   extern __shared__ float smem[];
   __shared__ float s_cam[SH_MAX_VIEWS * 3];
+  // the views' colour gradients of this block's 128 Gaussians: 384 contiguous floats per view.  They may live in PEER
+  // memory (NVLink): a thread-per-Gaussian read (three 4-byte loads at a 12-byte stride) fetches every remote sector three
+  // times, so the block copies them with coalesced 16-byte loads into shared memory first (round 2: the exchange tail at
+  // 8 GPUs was bound by exactly this kernel, 0.30 ms for 84 MB of peer data)
+  // (the staging area follows the output rows in the dynamic shared memory: [128][stride] floats, then [views][384])
   if (threadIdx.x < 3 * num_views) s_cam[threadIdx.x] = views.cam[threadIdx.x / 3][threadIdx.x % 3];
-  __syncthreads();
   const int row_len = 3 * K, stride = sh_row_stride(row_len);
   const int g0 = blockIdx.x * SH_THREADS;
   const int rows = min(SH_THREADS, n - g0);
   const int tid = threadIdx.x;
+  float(*s_vc)[3 * SH_THREADS] = reinterpret_cast<float(*)[3 * SH_THREADS]>(smem + SH_THREADS * stride);
+  {
+    const int nf = 3 * rows, nvec = vc_vec_ok ? (nf >> 2) : 0;
+    for (int idx = tid; idx < num_views * (3 * SH_THREADS / 4); idx += SH_THREADS) {
+      const int v = idx / (3 * SH_THREADS / 4), q = idx - v * (3 * SH_THREADS / 4);
+      if (q < nvec)
+        *reinterpret_cast<float4 *>(&s_vc[v][4 * q]) = *reinterpret_cast<const float4 *>(views.v_colors[v] + 3 * (size_t)g0 + 4 * q);
+    }
+    for (int v = 0; v < num_views; ++v)
+      for (int f = (nvec << 2) + tid; f < nf; f += SH_THREADS) s_vc[v][f] = views.v_colors[v][3 * (size_t)g0 + f];
+  }
+  __syncthreads();
   const int Ku = num_sh_bases(deg_use);
   if (tid < rows) {
     const int g = g0 + tid;
@@ -330,8 +346,7 @@ sh_backward_multiview_kernel(int n, int K, int deg_use, int num_views, const flo
       float Y[25];
       Y[0] = GSR_SH_C0;
       sh_basis(deg_use, mx - s_cam[3 * v], my - s_cam[3 * v + 1], mz - s_cam[3 * v + 2], Y);
-      const float *vc = views.v_colors[v] + 3 * (size_t)g;
-      const float v0 = vc[0], v1 = vc[1], v2 = vc[2];
+      const float v0 = s_vc[v][3 * tid], v1 = s_vc[v][3 * tid + 1], v2 = s_vc[v][3 * tid + 2];
 #pragma unroll
       for (int k = 0; k < 25; ++k) {
         if (k < K) {
@@ -396,10 +411,20 @@ GSR_API int gsr_compute_sh_backward_multiview_ptrs(int num_points, int degree, i
     views.cam[v] = cam_views_host[v];
   }
   const int K = num_sh_bases(degree);
-  const size_t smem = (size_t)SH_THREADS * sh_row_stride(3 * K) * sizeof(float);
+  const size_t smem = ((size_t)SH_THREADS * sh_row_stride(3 * K) + (size_t)num_views * 3 * SH_THREADS) * sizeof(float);
+  if (smem > 48 * 1024) {
+    static size_t configured = 0;  // opt in to more than 48 KB of dynamic shared memory (many views at degree 4)
+    if (smem > configured) {
+      GSR_CUDA(cudaFuncSetAttribute(sh_backward_multiview_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = smem;
+    }
+  }
   const int vec_ok = ((uintptr_t)v_coeffs % 16 == 0) ? 1 : 0;
+  int vc_vec_ok = 1;
+  for (int v = 0; v < num_views; ++v)
+    if ((uintptr_t)views.v_colors[v] % 16 != 0) vc_vec_ok = 0;
   sh_backward_multiview_kernel<<<cdiv(num_points, SH_THREADS), SH_THREADS, smem, (cudaStream_t)stream>>>(
-      num_points, K, degrees_to_use, num_views, means3d, views, v_coeffs, vec_ok);
+      num_points, K, degrees_to_use, num_views, means3d, views, v_coeffs, vec_ok, vc_vec_ok);
   GSR_CHECK_LAUNCH("sh_backward_multiview_kernel");
   return GSR_OK;
 }

@@ -135,6 +135,23 @@ def compute_sh_backward_multiview(degree: int, degrees_to_use: int, means3d: Ten
     return v_coeffs
 
 
+def peer_all_reduce_phase(phase: str, rank: int, bufs, num_floats: int) -> None:
+    """One kernel of the two-kernel all-reduce over NVLink peer memory (gsr_peer_reduce_scatter / gsr_peer_all_gather).
+    `bufs`: one CUDA float32 tensor per rank — rank w's buffer as mapped into this process (symmetric memory) — each with at
+    least `num_floats` elements.  The caller synchronises the ranks (device-side barriers) around the two phases."""
+    import ctypes
+
+    bufs = list(bufs)
+    for i, b in enumerate(bufs):
+        _check_input(b, f"bufs[{i}]", torch.float32)
+        if b.numel() < num_floats:
+            raise RuntimeError("peer_all_reduce_phase: buffer smaller than num_floats")
+    fn = {"reduce_scatter": "gsr_peer_reduce_scatter", "all_gather": "gsr_peer_all_gather"}[phase]
+    ptrs = (ctypes.c_void_p * len(bufs))(*[b.data_ptr() for b in bufs])
+    with _Guard(bufs[rank]) as st:
+        _lib.check(getattr(_lib.load(), fn)(len(bufs), int(rank), ptrs, int(num_floats), st), fn)
+
+
 def compute_cov2d_bounds(num_pts: int, covs2d: Tensor) -> Tuple[Tensor, Tensor]:
     _check_input(covs2d, "covs2d", torch.float32)
     conics = torch.empty((num_pts, covs2d.size(1)), dtype=torch.float32, device=covs2d.device)

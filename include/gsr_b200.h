@@ -94,6 +94,15 @@ GSR_API int gsr_compute_sh_backward_multiview_ptrs(int num_points, int degree, i
                                                    const float *const *v_colors_views_host, float *v_coeffs,
                                                    void *stream);
 
+/* All-reduce (sum) of a replicated FP32 buffer over NVLink peer memory, in two kernels (multi-GPU plumbing of SURVEY §8(e);
+ * the reference's counterpart is torch DDP's bucketed all-reduce, pipelines/base_pipeline.py:202-207).  bufs_host[w] is
+ * rank w's buffer as mapped into THIS process (symmetric memory), all of num_floats floats and 16-byte aligned.
+ * reduce_scatter: slice `rank` of this rank's buffer <- sum over ranks of that slice (fixed order: identical replicas);
+ * all_gather: the other slices of this rank's buffer <- the owners' reduced slices.  The caller puts a barrier over all
+ * ranks before, between and after the two calls (rasterizer/view_parallel.py). */
+GSR_API int gsr_peer_reduce_scatter(int world, int rank, float *const *bufs_host, long long num_floats, void *stream);
+GSR_API int gsr_peer_all_gather(int world, int rank, float *const *bufs_host, long long num_floats, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * EWA projection — replaces project_gaussians_forward / project_gaussians_backward
  * (bindings.h:35-55, bindings.cu:105-216, kernels forward.cu:13-90, backward.cu:305-453)

@@ -483,7 +483,40 @@ def _exchange_worker(rank, world, port, results):
         spherical_harmonics_view_parallel(3, means, cam, c3, peer=peer).backward(v_rgb)
         torch.cuda.synchronize()
         err_ag += float((c3.grad - summed).norm() / summed.norm())
-    results[rank] = (err, err_p2p, err_ag)
+    # (e) GradientExchange with a SYMMETRIC bucket: SH adjoint with peer loads on a side stream + the package's own
+    #     reduce-scatter / all-gather kernels over peer memory for the other 11 N floats (no NCCL call), three rounds in a row
+    #     with different values (barriers / in-place slices), odd N (slice and segment padding)
+    from rasterizer.view_parallel import GradientExchange
+
+    err_own = -1.0
+    if peer is not None:
+        for n_own in (N, 12_345):
+            peer_n = peer if n_own == N else PeerColorGrads.try_create(n_own, device=torch.device("cuda", rank))
+            sym = GradientBucket(n_own, K, device=torch.device("cuda", rank), symmetric=True)
+            if sym.hdl is None or peer_n is None:
+                continue
+            ex = GradientExchange(sym, means[:n_own].contiguous(), 3, peer_n)
+            ref_b = GradientBucket(n_own, K, device="cuda")
+            for rnd in range(3):
+                scale = float(rnd + 1)
+                ref_b["v_coeffs"].copy_(C.compute_sh_backward(n_own, 3, 3, (means[:n_own] - cam[None]).contiguous(),
+                                                              (v_rgb[:n_own] * scale).contiguous()))
+                for k, v in rest.items():
+                    ref_b[k].copy_(v[:n_own] * scale)
+                    sym[k].copy_(v[:n_own] * scale)
+                ref_b.all_reduce()
+                ex.start_sh((v_rgb[:n_own] * scale).contiguous(), cam, 3)
+                ex.finish()
+                torch.cuda.synchronize()
+                got = torch.cat([sym[k].reshape(n_own, -1) for k in ("v_coeffs", "v_mean3d", "v_scale", "v_quat", "v_opacity")], 1)
+                want = torch.cat([ref_b[k].reshape(n_own, -1) for k in ("v_coeffs", "v_mean3d", "v_scale", "v_quat", "v_opacity")], 1)
+                err_own = max(err_own, float((got - want).norm() / want.norm()))
+                # the replicas of the own all-reduce are bit-identical (fixed summation order)
+                tail = sym.flat[sym.tail_start:].clone()
+                other = tail.clone()
+                dist.broadcast(other, src=0)
+                assert torch.equal(tail, other)
+    results[rank] = (err, err_p2p, err_ag, err_own)
     dist.destroy_process_group()
 
 
@@ -499,6 +532,7 @@ def test_exchange_gradients_matches_plain_allreduce_2gpu():
     assert all(results[r][0] < 1e-6 for r in range(2))
     assert all(results[r][1] < 1e-6 for r in range(2))   # -1 = symmetric memory unavailable on this box
     assert all(results[r][2] < 1e-6 for r in range(2))   # autograd form (spherical_harmonics_view_parallel)
+    assert all(results[r][3] < 1e-6 for r in range(2))   # GradientExchange, symmetric bucket, own peer all-reduce
 
 
 def test_gaussian_rasterizer_facade_matches_operators(oracle):
