@@ -103,8 +103,38 @@ def _inspect(block: bool) -> None:
             f"repeat the iteration (or use set_binning_mode('sync')).")
 
 
+_capture_slots: List[Tuple[torch.Tensor, Tuple, int]] = []  # pinned {M, overflow} slots written by graph replays
+_capture_slots_free: List[torch.Tensor] = []
+
+
+def prepare_capture_slots(n: int = 8) -> None:
+    """Pin `n` slots BEFORE a capture starts (pinning is a synchronising allocation and must not happen inside one)."""
+    while len(_capture_slots_free) < n:
+        _capture_slots_free.append(torch.zeros(4, dtype=torch.int32).pin_memory())
+
+
+def check_captured(synchronize: bool = True) -> None:
+    """After replaying graphs captured over rasterize_gaussians: raise BinningOverflow if the LAST replay of any of them
+    produced more (Gaussian, tile) pairs than the capacity baked into the graph (the capacity of the signature is raised;
+    re-capture and repeat).  Reads pinned memory written by the replays, so it synchronises the device first."""
+    if synchronize and _capture_slots:
+        torch.cuda.synchronize()
+    for slot, key, cap in _capture_slots:
+        m, over = int(slot[0]), int(slot[1])
+        sig = _signatures.get(key)
+        if sig is not None:
+            sig.max_seen = max(sig.max_seen, m)
+            if over:
+                sig.capacity = max(sig.capacity, int(1.5 * m) + 65536)
+        if over:
+            raise BinningOverflow(f"a replayed CUDA graph produced {m} (Gaussian, tile) pairs but its buffers hold {cap}: "
+                                  f"re-capture the step (the capacity has been raised) and repeat the iteration")
+
+
 def poll() -> None:
     """Non-blocking: inspect the asynchronous calls that have finished; raises BinningOverflow if one overflowed."""
+    if torch.cuda.is_current_stream_capturing():
+        return
     _inspect(block=False)
 
 
@@ -117,6 +147,7 @@ def reset() -> None:
     """Forget learned capacities and outstanding tickets (tests)."""
     _signatures.clear()
     _pending.clear()
+    _capture_slots.clear()
 
 
 def bin_gaussians(xys, depths, radii, conics, opacity, img_height, img_width, block_width):
@@ -127,6 +158,21 @@ def bin_gaussians(xys, depths, radii, conics, opacity, img_height, img_width, bl
         return _C.bin_gaussians_fast(xys, depths, radii, conics, op, img_height, img_width, block_width)
     dev = xys.device
     key = (dev.index, xys.size(0), img_height, img_width, block_width)
+    if torch.cuda.is_current_stream_capturing():
+        # CUDA-graph capture (rasterizer.graphs): no host-side bookkeeping may run — the capacity must have been learned by
+        # eager warm-up calls, and {M, overflow} of every REPLAY lands in a pinned slot owned by the capture
+        sig = _signatures.get(key)
+        if sig is None:
+            raise RuntimeError("rasterize_gaussians under CUDA-graph capture: run the step eagerly first (asynchronous "
+                               "binning learns its pair-buffer capacity from the first call of a signature)")
+        if not _capture_slots_free:
+            raise RuntimeError("rasterize_gaussians under CUDA-graph capture: call rasterizer.binning.prepare_capture_slots() "
+                               "before the capture (pinning host memory inside a capture is not allowed)")
+        slot = _capture_slots_free.pop()
+        _capture_slots.append((slot, key, sig.capacity))
+        ids, bins, _meta = _C.bin_gaussians_device(xys, depths, radii, conics, op, img_height, img_width, block_width,
+                                                   sig.capacity, meta_pinned=slot)
+        return None, ids, bins
     _inspect(block=False)
     sig = _signatures.get(key)
     if sig is None:

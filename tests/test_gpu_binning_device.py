@@ -117,6 +117,84 @@ def test_async_binning_mode_matches_sync_and_reports_overflow():
         binning.reset()
 
 
+def test_graph_capture_of_public_api_view_matches_eager():
+    """rasterizer.graphs.capture_step: forward + backward of a view through the public autograd API, captured once and
+    replayed with NEW camera / upstream-gradient contents in the static input tensors, equals the eager result; the
+    pair-buffer overflow of a replay is reported by graphs.check()."""
+    import rasterizer
+    from rasterizer import binning, graphs
+    from rasterizer.sh import spherical_harmonics
+    from rasterizer.synthetic import look_at_viewmat, make_scene, scene_to_torch
+
+    H, W, bw = 200, 320, 16
+    scenes = [scene_to_torch(make_scene(30_000, W, H, 0.01, 0.08, margin=1.1, seed=11, viewmat=look_at_viewmat(yaw_deg=y)), "cuda")
+              for y in (0.0, 7.0)]
+    s0 = scenes[0]
+    params = {k: s0[k].clone().requires_grad_(True) for k in ("means3d", "scales", "quats", "sh_coeffs")}
+    opac = s0["opacities"].reshape(-1, 1).clone().requires_grad_(True)
+    viewmat, projmat, cam = s0["viewmat"].clone(), s0["projmat"].clone(), s0["cam_pos"].clone()
+    v_img, v_alpha = s0["v_out_img"].clone(), s0["v_out_alpha"].clone()
+    leaves = list(params.values()) + [opac]
+
+    def view():
+        for p in leaves:
+            p.grad = None
+        xys, depths, radii, conics, comp, nth, cov3d = rasterizer.project_gaussians(
+            params["means3d"], params["scales"], 1.0, params["quats"], viewmat, projmat, s0["fx"], s0["fy"], s0["cx"], s0["cy"],
+            H, W, bw, 0.01)
+        rgbs = torch.clamp(spherical_harmonics(3, params["means3d"].detach() - cam[None], params["sh_coeffs"]) + 0.5, min=0.0)
+        img, alpha = rasterizer.rasterize_gaussians(xys, depths, radii, conics, nth, rgbs, opac, H, W, bw,
+                                                    background=s0["background"], return_alpha=True)
+        torch.autograd.backward([img, alpha], [v_img, v_alpha])
+        return img, alpha, [p.grad for p in leaves]
+
+    def load(s, scale):
+        viewmat.copy_(s["viewmat"]); projmat.copy_(s["projmat"]); cam.copy_(s["cam_pos"])
+        v_img.copy_(s["v_out_img"] * scale); v_alpha.copy_(s["v_out_alpha"] * scale)
+
+    binning.reset()
+    rasterizer.set_binning_mode("sync")
+    eager = []
+    # autograd ties a leaf's AccumulateGrad node to the stream on which the leaf is first used: the eager reference runs on
+    # the stream the capture will use, otherwise the captured backward would synchronise with the default stream
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for s, scale in zip(scenes, (1.0, -2.0)):
+            load(s, scale)
+            img, alpha, grads = view()
+            eager.append((img.clone(), alpha.clone(), [g.clone() for g in grads]))
+    torch.cuda.synchronize()
+    try:
+        load(scenes[0], 1.0)
+        step = graphs.capture_step(view, stream=side)
+        for (s, scale), want in zip(zip(scenes, (1.0, -2.0)), eager):
+            load(s, scale)
+            img, alpha, grads = step.replay()
+            torch.cuda.synchronize()
+            graphs.check()
+            assert torch.equal(img, want[0]) and torch.equal(alpha, want[1])
+            for g, w in zip(grads, want[2]):
+                err = float((g - w).norm() / w.norm())
+                assert err < 2e-6, err           # atomics order only
+        # a replay that needs more pairs than the capacity baked into the graph is flagged
+        for slot, key, cap in binning._capture_slots:
+            assert int(slot[1]) == 0 and 0 < int(slot[0]) <= cap
+        with torch.no_grad():
+            saved = opac.detach().clone()
+            params["scales"].mul_(4.0)           # 16x the footprint: far more (Gaussian, tile) pairs
+        step.replay()
+        with pytest.raises(rasterizer.BinningOverflow):
+            graphs.check()
+        with torch.no_grad():
+            params["scales"].div_(4.0)
+            opac.copy_(saved)
+    finally:
+        rasterizer.set_binning_mode("sync")
+        binning.reset()
+        binning._capture_slots.clear()
+
+
 def test_long_tiles_take_the_global_radix_path_and_match_key_sort():
     """More than 4096 pairs in one tile (the in-shared-memory sort's limit): the slow path must give the same lists as
     the reference orchestration (64-bit key sort)."""
