@@ -861,6 +861,13 @@ def main():
             if g_value > e2e_value:
                 e2e_value, e2e_ms, e2e_mode = g_value, g_ms, "cuda_graph"
             e2e_eager["graphed_value"] = g_value
+        # drop the captured graphs now (they hold captured NCCL work at N > 1: a process group must not be torn down under them)
+        pv.graphed = False
+        pv.graph_fwd = pv.graph_bwd = pv.graph_out = None
+        import gc
+
+        gc.collect()
+        torch.cuda.synchronize()
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -933,8 +940,16 @@ def main():
             v, desc, cores, _ = cpu_leg(scene_np, 25.0)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
         print(json.dumps(line))
+        sys.stdout.flush()
     if world > 1:
+        # the line is out: a process-group teardown that hangs (it did once with live CUDA graphs holding captured NCCL
+        # work, before they were released explicitly above) must not hold the box
+        wd = threading.Timer(45.0, lambda: os._exit(0))
+        wd.daemon = True
+        wd.start()
+        dist.barrier()
         dist.destroy_process_group()
+        wd.cancel()
 
 
 if __name__ == "__main__":
