@@ -42,6 +42,16 @@ def _scenes():
     }
 
 
+def _needles():
+    """Adversarial for the conservative culling tests: per-axis scales log-uniform over three decades, so many
+    Gaussians are long thin slanted needles whose quadratic form is a difference of terms ~1e5 that cancel to ~10.  (Not in
+    _scenes(): on such ill-conditioned covariances the FP32 projection itself differs between --use_fast_math and the IEEE
+    oracle by more than 1e-4 — compensation, conics — so only GPU-vs-GPU statements are made on it.)"""
+    from rasterizer.synthetic import make_scene
+
+    return make_scene(5000, 256, 192, 0.0008, 0.8, margin=1.0, seed=9)
+
+
 def _check_view(ours, ref, has_backward=True, int_slack=2e-4, grad_norm_rel=1e-4, grad_frac_bad=5e-4, amb=None):
     """ours: dict of torch tensors; ref: dict of numpy arrays (oracle or reference ext).
     Gradient bounds: normwise <= 1e-4 (the north-star tolerance; observed on B200: 4e-7 .. 5.9e-5, the largest on the
@@ -285,7 +295,7 @@ def test_cov2d_bounds_and_cumsum(oracle):
     assert m0 == 0 and cum0.numel() == 0
 
 
-@pytest.mark.parametrize("name", ["cfg1_10k_256", "dense_3k_160x160_opaque", "ragged_4k_200x120_bw12_rot"])
+@pytest.mark.parametrize("name", ["cfg1_10k_256", "dense_3k_160x160_opaque", "ragged_4k_200x120_bw12_rot", "needles_5k_256x192"])
 def test_tight_binning_is_exact(oracle, name):
     """Exact tile culling: the kept (Gaussian, tile) pairs are a subset of the reference's bounding-box list, and
     the image / final_Ts are BITWISE the same as with the reference list (dropped pairs are `continue`d on every
@@ -294,7 +304,7 @@ def test_tight_binning_is_exact(oracle, name):
     from rasterizer import cuda as C
     from rasterizer.synthetic import scene_to_torch
 
-    scene = _scenes()[name]()
+    scene = _needles() if name.startswith("needles") else _scenes()[name]()
     s = scene_to_torch(scene, "cuda")
     a = run_view_bindings(C, s, sort_impl="gsr", binning="reference")
     b = run_view_bindings(C, s, sort_impl="gsr", binning="tight")
@@ -310,7 +320,11 @@ def test_tight_binning_is_exact(oracle, name):
     pb = (kb >> 32) * (1 << 31) + b["gaussian_ids_sorted"].long()
     assert bool(torch.isin(pb, pa).all())
     for k in ("v_xy", "v_conic", "v_colors", "v_opacity", "v_coeffs", "v_mean3d", "v_scale", "v_quat"):
-        assert_float_parity(b[k], a[k], k, max_norm_rel=1e-5, max_frac_bad=1e-3)
+        # needles: the projection adjoint of ill-conditioned covariances amplifies the atomic-order noise of v_conic
+        loose = name.startswith("needles") and k in ("v_mean3d", "v_scale", "v_quat")
+        assert_float_parity(b[k], a[k], k, max_norm_rel=1e-3 if loose else 1e-5, max_frac_bad=2e-2 if loose else 1e-3)
+    if name.startswith("needles"):
+        return
     ref = oracle.render_view(scene, scene["v_out_img"], scene["v_out_alpha"])
     clean = ref["ambiguous"] == 0
     assert_float_parity(b["out_img"], ref["out_img"], "out_img", mask=np.broadcast_to(clean[..., None], ref["out_img"].shape), max_frac_bad=1e-5)
