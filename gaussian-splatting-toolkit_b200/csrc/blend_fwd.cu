@@ -19,9 +19,16 @@
 //     the staged conic.
 #include "blend_common.cuh"
 
+#ifndef GSR_FWD_UNROLL
+#define GSR_FWD_UNROLL 4  // survivors per trip of the walk (cfg2 on B200: 4 -> 0.391 ms, 8 -> 0.400, 2 -> 0.422)
+#endif
+#ifndef GSR_FWD_MIN_CTAS
+#define GSR_FWD_MIN_CTAS 4  // 64 registers; 5 CTAs / SM (48 registers, rematerialised pixel coordinates): 0.413 ms
+#endif
+
 namespace gsr {
 
-__global__ void __launch_bounds__(BLEND_THREADS, 4)
+__global__ void __launch_bounds__(BLEND_THREADS, GSR_FWD_MIN_CTAS)
 blend_forward_kernel(int tiles_x, int img_w, int img_h, int block_width,
                      const int *__restrict__ gaussian_ids_sorted, const int2 *__restrict__ tile_bins,
                      const float2 *__restrict__ xys, const float *__restrict__ conics,
@@ -29,7 +36,7 @@ blend_forward_kernel(int tiles_x, int img_w, int img_h, int block_width,
                      const float *__restrict__ background, float *__restrict__ out_img,
                      float *__restrict__ final_Ts, int *__restrict__ final_idx) {
   // slot kNull of every plane holds a record that never contributes (opacity 0): the survivor lists are padded with it
-  constexpr int kNull = BLEND_THREADS, kUnroll = 4;
+  constexpr int kNull = BLEND_THREADS, kUnroll = GSR_FWD_UNROLL;
   __shared__ float4 s_rec[2][3][BLEND_THREADS + 1];
   __shared__ unsigned short s_list[BLEND_THREADS / 32][BLEND_THREADS + kUnroll + 2];
 
