@@ -734,13 +734,17 @@ def main():
     from rasterizer.view_parallel import GradientBucket
 
     bucket = (GradientBucket(N, s["sh_coeffs"].shape[1], device=s["means3d"].device,
-                             symmetric=os.environ.get("GSR_OWN_TAIL") == "1" and os.environ.get("GSR_NO_P2P") != "1")
+                             symmetric=os.environ.get("GSR_OWN_TAIL") in ("1", "push") and os.environ.get("GSR_NO_P2P") != "1")
               if world > 1 else None)
     ar_events = []
     from rasterizer.view_parallel import GradientExchange, PeerColorGrads
 
     peer = PeerColorGrads.try_create(N, device=s["means3d"].device) if (world > 1 and os.environ.get("GSR_NO_P2P") != "1") else None
     exchange = GradientExchange(bucket, s["means3d"], {1: 0, 4: 1, 9: 2, 16: 3, 25: 4}[s["sh_coeffs"].shape[1]], peer) if world > 1 else None
+    if world > 1 and os.environ.get("GSR_OWN_TAIL") == "push" and bucket.hdl is not None:
+        from rasterizer.view_parallel import PushGradientExchange
+
+        exchange = PushGradientExchange(bucket, s["means3d"], {1: 0, 4: 1, 9: 2, 16: 3, 25: 4}[s["sh_coeffs"].shape[1]])
 
     rv = ResidentView(s, bucket, exchange)
     recording = {"on": False}

@@ -92,6 +92,61 @@ peer_all_gather_kernel(PeerBufs bufs, int world, int rank, long long n) {
   if (blockIdx.x == 0 && threadIdx.x < hi - t0) dst[t0 + threadIdx.x] = src[t0 + threadIdx.x];
 }
 
+// ---- push-based variants: remote STORES (posted: no NVLink round trip per access), reductions from local memory ----------
+//   peer_push_kernel              dst[w][0 .. n_w) <- src[w * src_stride .. )   for every rank w (blockIdx.y); src_stride = 0
+//                                 broadcasts one source, src_stride = L scatters slice w of the source to rank w
+//   peer_reduce_broadcast_kernel  acc = sum over slots (fixed order) of this rank's LOCAL staging slots; the total is
+//                                 stored into every rank's destination (the reduced slice lands in all replicas)
+__global__ void __launch_bounds__(256)
+peer_push_kernel(PeerBufs dsts, const float *__restrict__ src, long long src_stride, long long n_per_dst, long long n_total) {
+  const int w = blockIdx.y;
+  const long long off = (long long)w * src_stride;
+  // scatter mode: the last slices may be shorter / empty
+  const long long n = src_stride > 0 ? max(0ll, min(n_per_dst, n_total - off)) : n_per_dst;
+  if (n <= 0) return;
+  const float *s = src + off;
+  float *d = dsts.buf[w];
+  const long long nvec = n >> 2;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += 4 * stride) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i + u * stride < nvec) v[u] = *reinterpret_cast<const float4 *>(s + 4 * (i + u * stride));
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i + u * stride < nvec) *reinterpret_cast<float4 *>(d + 4 * (i + u * stride)) = v[u];
+  }
+  const long long t0 = nvec << 2;
+  if (blockIdx.x == 0 && threadIdx.x < n - t0) d[t0 + threadIdx.x] = s[t0 + threadIdx.x];
+}
+
+template <int WMAX>
+__global__ void __launch_bounds__(256)
+peer_reduce_broadcast_kernel(PeerBufs dsts, int world, const float *__restrict__ slots, long long slot_stride, long long n) {
+  const long long nvec = n >> 2;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    float4 v[WMAX];
+#pragma unroll
+    for (int w = 0; w < WMAX; ++w)
+      if (w < world) v[w] = *reinterpret_cast<const float4 *>(slots + (long long)w * slot_stride + 4 * i);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int w = 0; w < WMAX; ++w)  // fixed order: bit-identical replicas
+      if (w < world) { a.x += v[w].x; a.y += v[w].y; a.z += v[w].z; a.w += v[w].w; }
+#pragma unroll
+    for (int w = 0; w < WMAX; ++w)
+      if (w < world) *reinterpret_cast<float4 *>(dsts.buf[w] + 4 * i) = a;
+  }
+  const long long t0 = nvec << 2;
+  if (blockIdx.x == 0 && threadIdx.x < n - t0) {
+    float a = 0.f;
+    for (int w = 0; w < world; ++w) a += slots[(long long)w * slot_stride + t0 + threadIdx.x];
+    for (int w = 0; w < world; ++w) dsts.buf[w][t0 + threadIdx.x] = a;
+  }
+}
+
 static int fill_bufs(PeerBufs &b, int world, int rank, float *const *bufs_host, const char *what) {
   GSR_REQUIRE(world >= 1 && world <= PEER_MAX_RANKS, GSR_ERR_UNSUPPORTED, "%s: world %d not in [1,%d]", what, world, PEER_MAX_RANKS);
   GSR_REQUIRE(rank >= 0 && rank < world, GSR_ERR_INVALID_ARGUMENT, "%s: rank %d not in [0,%d)", what, rank, world);
@@ -137,6 +192,40 @@ GSR_API int gsr_peer_all_gather(int world, int rank, float *const *bufs_host, lo
   const int bx = (int)std::min<long long>(std::max(148, 8 * 148 / (world - 1)), std::max<long long>(1, (L / 16 + 255) / 256));
   peer_all_gather_kernel<<<dim3(bx, world - 1, 1), 256, 0, (cudaStream_t)stream>>>(b, world, rank, num_floats);
   GSR_CHECK_LAUNCH("peer_all_gather_kernel");
+  return GSR_OK;
+}
+
+GSR_API int gsr_peer_push(int world, float *const *dsts_host, const float *src, long long src_stride, long long n_per_dst,
+                          long long n_total, void *stream) {
+  using namespace gsr;
+  PeerBufs b;
+  const int rc = fill_bufs(b, world, 0, dsts_host, "peer_push");
+  if (rc != GSR_OK) return rc;
+  GSR_REQUIRE(src != nullptr && (uintptr_t)src % 16 == 0 && src_stride >= 0 && src_stride % 4 == 0 && n_per_dst >= 0,
+              GSR_ERR_INVALID_ARGUMENT, "peer_push: bad source / stride / size");
+  if (n_per_dst == 0) return GSR_OK;
+  const int bx = (int)std::min<long long>(std::max(64, 8 * 148 / world), std::max<long long>(1, (n_per_dst / 16 + 255) / 256));
+  peer_push_kernel<<<dim3(bx, world, 1), 256, 0, (cudaStream_t)stream>>>(b, src, src_stride, n_per_dst, n_total);
+  GSR_CHECK_LAUNCH("peer_push_kernel");
+  return GSR_OK;
+}
+
+GSR_API int gsr_peer_reduce_broadcast(int world, float *const *dsts_host, const float *slots, long long slot_stride,
+                                      long long num_floats, void *stream) {
+  using namespace gsr;
+  PeerBufs b;
+  const int rc = fill_bufs(b, world, 0, dsts_host, "peer_reduce_broadcast");
+  if (rc != GSR_OK) return rc;
+  GSR_REQUIRE(slots != nullptr && (uintptr_t)slots % 16 == 0 && slot_stride % 4 == 0 && num_floats >= 0,
+              GSR_ERR_INVALID_ARGUMENT, "peer_reduce_broadcast: bad slots / stride / size");
+  if (num_floats == 0) return GSR_OK;
+  const int blocks = (int)std::min<long long>(8 * 148, std::max<long long>(1, (num_floats / 4 + 255) / 256));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (world <= 2) peer_reduce_broadcast_kernel<2><<<blocks, 256, 0, st>>>(b, world, slots, slot_stride, num_floats);
+  else if (world <= 4) peer_reduce_broadcast_kernel<4><<<blocks, 256, 0, st>>>(b, world, slots, slot_stride, num_floats);
+  else if (world <= 8) peer_reduce_broadcast_kernel<8><<<blocks, 256, 0, st>>>(b, world, slots, slot_stride, num_floats);
+  else peer_reduce_broadcast_kernel<16><<<blocks, 256, 0, st>>>(b, world, slots, slot_stride, num_floats);
+  GSR_CHECK_LAUNCH("peer_reduce_broadcast_kernel");
   return GSR_OK;
 }
 }

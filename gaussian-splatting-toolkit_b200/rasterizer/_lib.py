@@ -33,6 +33,8 @@ SIGNATURES = {
     "gsr_compute_sh_backward_multiview_ptrs": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p]),
     "gsr_peer_reduce_scatter": (_i, [_i, _i, _p, C.c_longlong, _p]),
     "gsr_peer_all_gather": (_i, [_i, _i, _p, C.c_longlong, _p]),
+    "gsr_peer_push": (_i, [_i, _p, _p, C.c_longlong, C.c_longlong, C.c_longlong, _p]),
+    "gsr_peer_reduce_broadcast": (_i, [_i, _p, _p, C.c_longlong, C.c_longlong, _p]),
     "gsr_project_gaussians_forward": (_i, [_i, _p, _p, _f, _p, _p, _p, _f, _f, _f, _f, _u, _u, _u, _f,
                                            _p, _p, _p, _p, _p, _p, _p, _p]),
     "gsr_project_gaussians_backward": (_i, [_i, _p, _p, _f, _p, _p, _p, _f, _f, _f, _f, _u, _u, _p, _p, _p,

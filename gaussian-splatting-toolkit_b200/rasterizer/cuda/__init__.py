@@ -160,6 +160,33 @@ def peer_all_reduce_phase(phase: str, rank: int, bufs, num_floats: int) -> None:
         _lib.check(getattr(_lib.load(), fn)(len(bufs), int(rank), ptrs, int(num_floats), st), fn)
 
 
+def peer_push(dsts, src: Tensor, src_stride: int, n_per_dst: int, n_total: int = 0) -> None:
+    """gsr_peer_push: dsts[w][0 .. n_w) <- src[w * src_stride ..) for every rank w (remote stores into symmetric memory).
+    src_stride = 0 broadcasts `n_per_dst` floats of `src` to every destination."""
+    import ctypes
+
+    dsts = list(dsts)
+    _check_input(src, "src", torch.float32)
+    for i, d in enumerate(dsts):
+        _check_input(d, f"dsts[{i}]", torch.float32)
+    ptrs = (ctypes.c_void_p * len(dsts))(*[d.data_ptr() for d in dsts])
+    with _Guard(src) as st:
+        _lib.check(_lib.load().gsr_peer_push(len(dsts), ptrs, _ptr(src), int(src_stride), int(n_per_dst), int(n_total), st),
+                   "peer_push")
+
+
+def peer_reduce_broadcast(dsts, slots: Tensor, slot_stride: int, num_floats: int) -> None:
+    """gsr_peer_reduce_broadcast: every dsts[w][0 .. num_floats) <- sum over the len(dsts) local slots of `slots`."""
+    import ctypes
+
+    dsts = list(dsts)
+    _check_input(slots, "slots", torch.float32)
+    ptrs = (ctypes.c_void_p * len(dsts))(*[d.data_ptr() for d in dsts])
+    with _Guard(slots) as st:
+        _lib.check(_lib.load().gsr_peer_reduce_broadcast(len(dsts), ptrs, _ptr(slots), int(slot_stride), int(num_floats), st),
+                   "peer_reduce_broadcast")
+
+
 def compute_cov2d_bounds(num_pts: int, covs2d: Tensor) -> Tuple[Tensor, Tensor]:
     _check_input(covs2d, "covs2d", torch.float32)
     conics = torch.empty((num_pts, covs2d.size(1)), dtype=torch.float32, device=covs2d.device)

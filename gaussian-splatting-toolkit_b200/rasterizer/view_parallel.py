@@ -339,6 +339,107 @@ class GradientExchange:
             bucket.flat.div_(dist.get_world_size(self.group))
 
 
+class PushGradientExchange:
+    """GradientExchange with PUSHED data (opt-in, NVLink-connected GPUs): everything that crosses NVLink is a remote STORE
+    into a peer's symmetric staging buffer — posted, no round trip per access — and every reduction reads local memory.
+
+        start_sh   side stream: push this rank's colour gradients + camera centre into slot `rank` of every rank's staging
+                   buffer; barrier; multi-view SH adjoint over the W LOCAL slots -> bucket["v_coeffs"]
+        finish     main stream: push slice w of this rank's 11 N non-SH floats into slot `rank` of rank w's staging buffer;
+                   barrier; sum the W local slots of this rank's slice (fixed order: replicas bit-identical) and store the
+                   total into slice `rank` of EVERY rank's bucket; join the side stream; barrier ("all gathered" + "all
+                   consumed")
+
+    Needs a symmetric bucket (GradientBucket(symmetric=True)).  Same interface as GradientExchange."""
+
+    def __init__(self, bucket: GradientBucket, means3d: torch.Tensor, degree: int, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        if bucket.hdl is None:
+            raise RuntimeError("PushGradientExchange needs GradientBucket(symmetric=True)")
+        self.bucket, self.means3d, self.degree, self.group = bucket, means3d, degree, group
+        W, r, N = bucket.hdl.world_size, bucket.hdl.rank, bucket.num_points
+        self.world, self.rank = W, r
+        self.rgb_floats = 3 * N
+        self.cam_off = (3 * N + 3) // 4 * 4            # camera centre behind the colour gradients, 16-byte aligned
+        S = self.cam_off + 4                           # floats per colour slot
+        L = ((bucket.tail_len + W - 1) // W + 3) // 4 * 4   # floats per slice of the non-SH tail
+        self.S, self.L = S, L
+        self.n_mine = max(0, min(L, bucket.tail_len - r * L))
+        dev = means3d.device
+        self.stage = symm_mem.empty(W * S + W * L, dtype=torch.float32, device=dev)
+        self.stage.zero_()
+        self.hdl = symm_mem.rendezvous(self.stage, group if group is not None else dist.group.WORLD)
+        # destinations on every rank w: MY colour slot, MY camera slot, MY tail slot; and slice `rank` of w's bucket tail
+        self.dst_rgb = [self.hdl.get_buffer(w, (S,), torch.float32, r * S) for w in range(W)]
+        self.dst_cam = [self.hdl.get_buffer(w, (4,), torch.float32, r * S + self.cam_off) for w in range(W)]
+        self.dst_tail = [self.hdl.get_buffer(w, (L,), torch.float32, W * S + r * L) for w in range(W)]
+        self.dst_slice = [bucket.peer_tails[w][r * L:] for w in range(W)] if self.n_mine > 0 else None
+        # local views of the W slots
+        self.loc_rgb = [self.stage[w * S: w * S + 3 * N].view(N, 3) for w in range(W)]
+        self.loc_cam = [self.stage[w * S + self.cam_off: w * S + self.cam_off + 3] for w in range(W)]
+        self.loc_tail = self.stage[W * S:]
+        self.cam4 = torch.zeros(4, dtype=torch.float32, device=dev)
+        self.side = torch.cuda.Stream(dev)
+        self.peer = self  # bench.py looks at `.peer is not None` for the breakdown
+        self.timing = False
+        self._ev_side, self._ev_main = [], []
+
+    def _ev(self):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def breakdown_ms(self) -> Dict[str, float]:
+        out = {}
+        if self._ev_side:
+            n = len(self._ev_side)
+            out["side.push_rgb_and_barrier"] = sum(a.elapsed_time(b) for a, b, _ in self._ev_side) / n
+            out["side.sh_adjoint_multiview_local_slots"] = sum(b.elapsed_time(c) for _, b, c in self._ev_side) / n
+        if self._ev_main:
+            n = len(self._ev_main)
+            out["main.push_slices_barrier_reduce_broadcast_11N"] = sum(a.elapsed_time(b) for a, b, _ in self._ev_main) / n
+            out["main.join_side_and_barrier"] = sum(b.elapsed_time(c) for _, b, c in self._ev_main) / n
+        return out
+
+    def start_sh(self, v_rgb_sh: torch.Tensor, cam_pos: torch.Tensor, degrees_to_use: int) -> None:
+        from . import cuda as _C
+
+        cur = torch.cuda.current_stream()
+        self.side.wait_stream(cur)
+        with torch.cuda.stream(self.side):
+            e0 = self._ev() if self.timing else None
+            v = v_rgb_sh.contiguous()
+            _C.peer_push(self.dst_rgb, v.view(-1), 0, self.rgb_floats)
+            v.record_stream(self.side)
+            self.cam4[:3].copy_(cam_pos.reshape(3))
+            _C.peer_push(self.dst_cam, self.cam4, 0, 4)
+            self.hdl.barrier(channel=0)
+            e1 = self._ev() if self.timing else None
+            _C.compute_sh_backward_multiview(self.degree, degrees_to_use, self.means3d, self.loc_cam, self.loc_rgb,
+                                             out=self.bucket["v_coeffs"])
+            if self.timing:
+                self._ev_side.append((e0, e1, self._ev()))
+
+    def finish(self, average: bool = False) -> None:
+        from . import cuda as _C
+
+        bucket = self.bucket
+        e0 = self._ev() if self.timing else None
+        tail = bucket.flat[bucket.tail_start:]
+        _C.peer_push(self.dst_tail, tail, self.L, self.L, bucket.tail_len)
+        self.hdl.barrier(channel=1)
+        if self.n_mine > 0:
+            _C.peer_reduce_broadcast(self.dst_slice, self.loc_tail, self.L, self.n_mine)
+        e1 = self._ev() if self.timing else None
+        torch.cuda.current_stream().wait_stream(self.side)
+        self.hdl.barrier(channel=2)
+        if self.timing:
+            self._ev_main.append((e0, e1, self._ev()))
+        if average:
+            bucket.flat.div_(self.world)
+
+
 def bind_process_to_gpu_numa(device_index: int) -> Optional[list]:
     """Pin the calling process to the CPUs NVML reports as local to GPU `device_index` (its NUMA node), so that the
     pinned host buffers it allocates afterwards (first touch) and its H2D / D2H traffic stay on the GPU's own socket —

@@ -102,6 +102,15 @@ GSR_API int gsr_compute_sh_backward_multiview_ptrs(int num_points, int degree, i
  * ranks before, between and after the two calls (rasterizer/view_parallel.py). */
 GSR_API int gsr_peer_reduce_scatter(int world, int rank, float *const *bufs_host, long long num_floats, void *stream);
 GSR_API int gsr_peer_all_gather(int world, int rank, float *const *bufs_host, long long num_floats, void *stream);
+/* Push-based forms (remote stores are posted; reductions read local memory).  peer_push: for every rank w,
+ * dsts_host[w][0 .. n_w) <- src[w * src_stride ..): src_stride = 0 broadcasts n_per_dst floats, src_stride > 0 scatters
+ * slice w (n_w = min(n_per_dst, n_total - w * src_stride)).  peer_reduce_broadcast: sums the `world` local staging slots
+ * (slot w at slots + w * slot_stride, fixed order) and stores the total into dsts_host[w] of every rank.  Pointers 16-byte
+ * aligned, strides multiples of 4 floats; barriers between the steps are the caller's (rasterizer/view_parallel.py). */
+GSR_API int gsr_peer_push(int world, float *const *dsts_host, const float *src, long long src_stride, long long n_per_dst,
+                          long long n_total, void *stream);
+GSR_API int gsr_peer_reduce_broadcast(int world, float *const *dsts_host, const float *slots, long long slot_stride,
+                                      long long num_floats, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * EWA projection — replaces project_gaussians_forward / project_gaussians_backward

@@ -509,27 +509,30 @@ def _exchange_worker(rank, world, port, results):
             sym = GradientBucket(n_own, K, device=torch.device("cuda", rank), symmetric=True)
             if sym.hdl is None or peer_n is None:
                 continue
-            ex = GradientExchange(sym, means[:n_own].contiguous(), 3, peer_n)
             ref_b = GradientBucket(n_own, K, device="cuda")
-            for rnd in range(3):
-                scale = float(rnd + 1)
-                ref_b["v_coeffs"].copy_(C.compute_sh_backward(n_own, 3, 3, (means[:n_own] - cam[None]).contiguous(),
-                                                              (v_rgb[:n_own] * scale).contiguous()))
-                for k, v in rest.items():
-                    ref_b[k].copy_(v[:n_own] * scale)
-                    sym[k].copy_(v[:n_own] * scale)
-                ref_b.all_reduce()
-                ex.start_sh((v_rgb[:n_own] * scale).contiguous(), cam, 3)
-                ex.finish()
-                torch.cuda.synchronize()
-                got = torch.cat([sym[k].reshape(n_own, -1) for k in ("v_coeffs", "v_mean3d", "v_scale", "v_quat", "v_opacity")], 1)
-                want = torch.cat([ref_b[k].reshape(n_own, -1) for k in ("v_coeffs", "v_mean3d", "v_scale", "v_quat", "v_opacity")], 1)
-                err_own = max(err_own, float((got - want).norm() / want.norm()))
-                # the replicas of the own all-reduce are bit-identical (fixed summation order)
-                tail = sym.flat[sym.tail_start:].clone()
-                other = tail.clone()
-                dist.broadcast(other, src=0)
-                assert torch.equal(tail, other)
+            from rasterizer.view_parallel import PushGradientExchange
+
+            for ex in (GradientExchange(sym, means[:n_own].contiguous(), 3, peer_n),
+                       PushGradientExchange(sym, means[:n_own].contiguous(), 3)):   # load-based, then push-based
+              for rnd in range(3):
+                  scale = float(rnd + 1)
+                  ref_b["v_coeffs"].copy_(C.compute_sh_backward(n_own, 3, 3, (means[:n_own] - cam[None]).contiguous(),
+                                                                (v_rgb[:n_own] * scale).contiguous()))
+                  for k, v in rest.items():
+                      ref_b[k].copy_(v[:n_own] * scale)
+                      sym[k].copy_(v[:n_own] * scale)
+                  ref_b.all_reduce()
+                  ex.start_sh((v_rgb[:n_own] * scale).contiguous(), cam, 3)
+                  ex.finish()
+                  torch.cuda.synchronize()
+                  got = torch.cat([sym[k].reshape(n_own, -1) for k in ("v_coeffs", "v_mean3d", "v_scale", "v_quat", "v_opacity")], 1)
+                  want = torch.cat([ref_b[k].reshape(n_own, -1) for k in ("v_coeffs", "v_mean3d", "v_scale", "v_quat", "v_opacity")], 1)
+                  err_own = max(err_own, float((got - want).norm() / want.norm()))
+                  # the replicas of the own all-reduce are bit-identical (fixed summation order)
+                  tail = sym.flat[sym.tail_start:].clone()
+                  other = tail.clone()
+                  dist.broadcast(other, src=0)
+                  assert torch.equal(tail, other)
     results[rank] = (err, err_p2p, err_ag, err_own)
     dist.destroy_process_group()
 
