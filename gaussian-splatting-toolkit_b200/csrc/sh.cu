@@ -9,6 +9,8 @@
 // and shared memory with fully coalesced 128-bit accesses, and each thread then reads / writes its own
 // row in shared memory with an odd row stride (bank-conflict free).  The backward writes every one of
 // the K*3 outputs itself (zeros above degrees_to_use), so no separate zero-fill pass is needed.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace gsr {
@@ -257,6 +259,86 @@ sh_forward_vec_kernel(int n, int deg_use, const float *__restrict__ viewdirs, co
   }
 }
 
+// ---- the same forward with TMA bulk copies ---------------------------------------------------------------------------
+// One `cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes` per coefficient row (3K floats = 192 B at degree 3,
+// 16-byte aligned on both sides) from each of the 128 threads, into the same padded rows; completion is counted in bytes
+// on an mbarrier armed by thread 0 (`arrive.expect_tx`), which all threads wait on with `try_wait.parity` after they have
+// evaluated the basis.  No register or LSU slot carries data (SASS: UBLKCP.S.G + SYNCS.ARRIVE.TRANS64 / PHASECHK.TRYWAIT;
+// the copy instruction takes uniform operands, so the compiler elects the lanes of a warp one after the other).
+// Measured at cfg2 on B200 (ncu, per launch): 36.9 us against 33.0 us for the LDGSTS variant above — 128 bulk copies of
+// 192 B per CTA cost more TMA requests than 12 coalesced 16-byte copies per thread — and the same 0.060 ms stage inside
+// the view, so it is OPT-IN (GSR_SH_TMA=1); one bulk copy of the whole contiguous 24 KB block would need unpadded rows,
+// whose row-per-thread 128-bit reads are four-way bank conflicted.
+template <int K>
+__global__ void __launch_bounds__(SH_THREADS)
+sh_forward_tma_kernel(int n, int deg_use, const float *__restrict__ viewdirs, const float *__restrict__ coeffs,
+                      float *__restrict__ colors) {
+  constexpr int RL = 3 * K, ST = (RL % 8 == 4) ? RL : RL + 4;  // = 4 (mod 8) words
+  constexpr unsigned ROW_BYTES = RL * sizeof(float);
+  __shared__ __align__(128) float s[SH_THREADS * ST];
+  __shared__ __align__(8) unsigned long long mbar;
+  const int tid = threadIdx.x;
+  const int g0 = blockIdx.x * SH_THREADS;
+  const int rows = min(SH_THREADS, n - g0);
+  const unsigned mbar_addr = (unsigned)__cvta_generic_to_shared(&mbar);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(mbar_addr) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(mbar_addr), "r"(rows * ROW_BYTES) : "memory");
+  }
+  __syncthreads();
+  if (tid < rows) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(s + tid * ST);
+    const float *src = coeffs + (size_t)(g0 + tid) * RL;
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
+                 "l"(src), "r"(ROW_BYTES), "r"(mbar_addr)
+                 : "memory");
+  }
+  float Y[25];
+  const int g = g0 + tid;
+  if (tid < rows) sh_basis(deg_use, viewdirs[3 * (size_t)g], viewdirs[3 * (size_t)g + 1], viewdirs[3 * (size_t)g + 2], Y);
+  {
+    unsigned done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}\n"
+          : "=r"(done)
+          : "r"(mbar_addr)
+          : "memory");
+    }
+  }
+  if (tid < rows) {
+    float c[RL];
+#pragma unroll
+    for (int q = 0; q < RL / 4; ++q) {
+      const float4 v = *reinterpret_cast<const float4 *>(s + tid * ST + 4 * q);
+      c[4 * q] = v.x; c[4 * q + 1] = v.y; c[4 * q + 2] = v.z; c[4 * q + 3] = v.w;
+    }
+    float out[3];
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      float acc = GSR_SH_C0 * c[ch];
+      if (K >= 4 && deg_use >= 1) acc += Y[1] * c[3 + ch] + Y[2] * c[6 + ch] + Y[3] * c[9 + ch];
+      if (K >= 9 && deg_use >= 2) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 4; k < 9; ++k) t += Y[k] * c[(3 * k + ch) % RL];
+        acc += t;
+      }
+      if (K >= 16 && deg_use >= 3) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 9; k < 16; ++k) t += Y[k] * c[(3 * k + ch) % RL];
+        acc += t;
+      }
+      out[ch] = acc;
+    }
+    colors[3 * (size_t)g] = out[0];
+    colors[3 * (size_t)g + 1] = out[1];
+    colors[3 * (size_t)g + 2] = out[2];
+  }
+}
+
 template <int K>
 __global__ void __launch_bounds__(SH_THREADS)
 sh_backward_vec_kernel(int n, int deg_use, const float *__restrict__ viewdirs, const float *__restrict__ v_colors,
@@ -449,7 +531,14 @@ GSR_API int gsr_compute_sh_forward(int num_points, int degree, int degrees_to_us
   const size_t smem = (size_t)SH_THREADS * sh_row_stride(3 * K) * sizeof(float);
   // every CTA's block starts at g0*3K floats: 16-byte aligned iff the base is and 128*3K*4 % 16 == 0 (always)
   const int vec_ok = ((uintptr_t)coeffs % 16 == 0) ? 1 : 0;
-  if (vec_ok && K == 16)
+  static const bool use_tma = [] {
+    const char *e = getenv("GSR_SH_TMA");
+    return e && e[0] == '1';
+  }();
+  if (vec_ok && K == 16 && use_tma)
+    sh_forward_tma_kernel<16><<<cdiv(num_points, SH_THREADS), SH_THREADS, 0, (cudaStream_t)stream>>>(
+        num_points, degrees_to_use, viewdirs, coeffs, colors);
+  else if (vec_ok && K == 16)
     sh_forward_vec_kernel<16><<<cdiv(num_points, SH_THREADS), SH_THREADS, 0, (cudaStream_t)stream>>>(
         num_points, degrees_to_use, viewdirs, coeffs, colors);
   else if (vec_ok && K == 4)

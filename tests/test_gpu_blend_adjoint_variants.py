@@ -50,3 +50,31 @@ def test_adjoint_variants_match_pixel_parallel(tmp_path, variant):
             err = np.linalg.norm(a - b) / np.linalg.norm(b)
             print(f"[adjoint variants] {variant} scene {name} {k}: normwise rel {err:.2e}")
             assert err < 5e-6, (variant, name, k, err)
+
+
+_SH_SCRIPT = r"""
+import sys, os, numpy as np, torch
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "gaussian-splatting-toolkit_b200"))
+from rasterizer import cuda as C
+g = torch.Generator().manual_seed(3)
+out = {{}}
+for n in (1, 127, 128, 100_003):
+    dirs = torch.randn(n, 3, generator=g).cuda()
+    coeffs = torch.randn(n, 16, 3, generator=g).cuda()
+    for use in (0, 2, 3):
+        out[f"{{n}}_{{use}}"] = C.compute_sh_forward(n, 3, use, dirs, coeffs).cpu().numpy()
+np.savez({path!r}, **out)
+"""
+
+
+def test_sh_forward_tma_variant_is_bit_identical(tmp_path):
+    """GSR_SH_TMA=1: the SH forward staged with TMA bulk copies (cp.async.bulk + mbarrier) gives bit-identical colours to the
+    default cp.async variant — same arithmetic, only the staging differs; row counts that are not a multiple of the block."""
+    res = {}
+    for flag in ("0", "1"):
+        path = str(tmp_path / f"sh_{flag}.npz")
+        env = dict(os.environ, GSR_SH_TMA=flag)
+        subprocess.run([sys.executable, "-c", _SH_SCRIPT.format(root=ROOT, path=path)], check=True, env=env)
+        res[flag] = np.load(path)
+    for k in res["0"].files:
+        assert np.array_equal(res["0"][k], res["1"][k]), k
