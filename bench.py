@@ -849,7 +849,10 @@ def main():
     # the same step with the view captured by rasterizer.graphs (public API): per step the same pinned-host copies in and
     # out, two graph launches instead of ~40 Python-dispatched calls — the eager path is host-bound on slow hosts
     e2e_mode = "eager"
-    if os.environ.get("GSR_E2E_GRAPH", "1") != "0":
+    # default: on for a single process; at N > 1 the captured step contains the NCCL all-reduce and the symmetric-memory
+    # barriers — measured working at 2 and 8 GPUs (profiles/r02/bench_v13_n8.json: 2063 against 1937 views/s eager), but a
+    # teardown under live graphs hung once during development, so multi-rank runs replay graphs only with GSR_E2E_GRAPH=1
+    if os.environ.get("GSR_E2E_GRAPH", "1" if world == 1 else "0") != "0":
         ok = pv.capture()
         if world > 1:  # every rank must take the same path (the captured step contains collectives)
             flag = torch.tensor([1 if ok else 0], device="cuda")
