@@ -56,28 +56,17 @@ inline int num_sms() {
 constexpr int BD_THREADS = 256;
 typedef unsigned long long u64;
 
-// tiles kept for Gaussian g: calls f(tile_id) for each; returns the count.  `mask` caches the decision for boxes of
-// at most 64 tiles (bit k = k-th tile of the bounding box, row-major).
+// The tiles kept for a Gaussian (exact tile culling, tile_cull.cuh) inside its bounding box [x0, x1) x [y0, y1): calls
+// f(tile_id) for each and returns the count.  For boxes of at most 64 tiles the decision is also returned as a mask
+// (bit k = k-th tile of the box, row-major), which the fill pass walks instead of evaluating the ellipse again.
 template <typename F>
-__device__ __forceinline__ int for_each_kept_tile(float2 ctr, int r, float ca, float cb, float cc, float opac, int tiles_x,
-                                                  int tiles_y, int block_width, u64 &mask, bool have_mask, F f) {
-  int x0, y0, x1, y1;
-  tile_bbox(ctr.x, ctr.y, (float)r, tiles_x, tiles_y, block_width, x0, y0, x1, y1);
+__device__ __forceinline__ int cull_tiles(float2 ctr, int r, float ca, float cb, float cc, float opac, int x0, int y0, int x1,
+                                          int y1, int tiles_x, int block_width, u64 &mask, F f) {
   const int bw_tiles = x1 - x0, area = bw_tiles * (y1 - y0);
-  if (area <= 0) return 0;
-  int count = 0;
-  if (have_mask && area <= 64) {
-    u64 m = mask;
-    while (m) {
-      const int k = __ffsll((long long)m) - 1;
-      m &= m - 1;
-      f((y0 + k / bw_tiles) * tiles_x + x0 + k % bw_tiles);
-      ++count;
-    }
-    return count;
-  }
+  mask = 0ull;
   const CullEllipse e = make_cull_ellipse(ca, cb, cc, opac, (float)(r + block_width));
   if (e.empty) return 0;
+  int count = 0;
   u64 mk = 0ull;
   for (int i = y0; i < y1; ++i) {
     int j0, j1;
@@ -91,18 +80,83 @@ __device__ __forceinline__ int for_each_kept_tile(float2 ctr, int r, float ca, f
   return count;
 }
 
+// Walk of a cached mask: tile of bit k = (y0 * tiles_x + x0) + k + (k / bw_tiles) * (tiles_x - bw_tiles).
+// k / bw_tiles without an integer division per pair (25 of the 50 instructions of the loop it replaces):
+// (k * magic) >> 16 is exact for k < 64 and every divisor up to 64 for any magic in [ceil(65536 / d), ceil(65536 / d) + 16]
+// — the approximate reciprocal of fast-math cannot leave that interval
+// (tests/test_abi.py::test_tile_mask_division_magic_is_exact).
+template <typename F>
+__device__ __forceinline__ void walk_tile_mask(u64 mask, int x0, int y0, int bw_tiles, int tiles_x, F f) {
+  const unsigned magic = (unsigned)(65536.f / (float)bw_tiles) + 1u;
+  const int base = y0 * tiles_x + x0, skip = tiles_x - bw_tiles;
+#pragma unroll 1
+  for (int h = 0; h < 2; ++h) {
+    unsigned w = h ? (unsigned)(mask >> 32) : (unsigned)mask;
+    const int k0 = 32 * h;
+    while (w) {
+      const unsigned low = w & (0u - w);
+      const int k = k0 + 31 - __clz((int)low);
+      w ^= low;
+      f(base + k + (int)(((unsigned)k * magic) >> 16) * skip);
+    }
+  }
+}
+
+// count pass of one Gaussian
+template <typename F>
+__device__ __forceinline__ u64 count_one(int g, const float2 *__restrict__ xys, const int *__restrict__ radii,
+                                         const float *__restrict__ conics, const float *__restrict__ opacities, int tiles_x,
+                                         int tiles_y, int block_width, F f) {
+  const int r = radii[g];
+  const float2 ctr = xys[g];
+  const float ca = conics[3 * (size_t)g], cb = conics[3 * (size_t)g + 1], cc = conics[3 * (size_t)g + 2];
+  const float opac = opacities[g];
+  u64 mask = 0ull;
+  if (r > 0) {
+    int x0, y0, x1, y1;
+    tile_bbox(ctr.x, ctr.y, (float)r, tiles_x, tiles_y, block_width, x0, y0, x1, y1);
+    if ((x1 - x0) * (y1 - y0) > 0) cull_tiles(ctr, r, ca, cb, cc, opac, x0, y0, x1, y1, tiles_x, block_width, mask, f);
+  }
+  return mask;
+}
+
+// fill pass of one Gaussian: the cached mask is walked; the conic and the opacity are read only for the rare boxes of
+// more than 64 tiles, whose decision is evaluated again.  (Measured and dropped: forcing radius / mask / centre / depth
+// to be requested together with ld.relaxed.gpu loads — the compiler sinks plain loads behind the branches, three
+// dependent round trips — made both passes SLOWER in the steady state, +9 us count / +8 us fill at cfg2, +0.18 ms at
+// cfg4: the L1-bypassing loads cost more than the shorter chain saves, gpurun_out/r2_run49_*.)
+template <typename F>
+__device__ __forceinline__ void fill_one(int g, const float2 *__restrict__ xys, const float *__restrict__ depths,
+                                         const int *__restrict__ radii, const float *__restrict__ conics,
+                                         const float *__restrict__ opacities, const u64 *__restrict__ masks, int tiles_x,
+                                         int tiles_y, int block_width, F f /* f(tile, key) */) {
+  const int r = radii[g];
+  const u64 mask = masks[g];
+  const float2 ctr = xys[g];
+  // the low 32 bits of the reference key are the IEEE bits of the depth (forward.cu:116); the id breaks ties in index order
+  const u64 key = ((u64)(unsigned)__float_as_int(depths[g]) << 32) | (u64)(unsigned)g;
+  if (r <= 0) return;
+  int x0, y0, x1, y1;
+  tile_bbox(ctr.x, ctr.y, (float)r, tiles_x, tiles_y, block_width, x0, y0, x1, y1);
+  const int area = (x1 - x0) * (y1 - y0);
+  if (area <= 0) return;
+  if (area <= 64) {
+    walk_tile_mask(mask, x0, y0, x1 - x0, tiles_x, [&](int tile) { f(tile, key); });
+  } else {
+    u64 unused;
+    cull_tiles(ctr, r, conics[3 * (size_t)g], conics[3 * (size_t)g + 1], conics[3 * (size_t)g + 2], opacities[g], x0, y0, x1,
+               y1, tiles_x, block_width, unused, [&](int tile) { f(tile, key); });
+  }
+}
+
 __global__ void __launch_bounds__(BD_THREADS)
 bin_count_kernel(int n, const float2 *__restrict__ xys, const int *__restrict__ radii, const float *__restrict__ conics,
                  const float *__restrict__ opacities, int tiles_x, int tiles_y, int block_width,
                  u64 *__restrict__ masks, unsigned *__restrict__ tile_count) {
   const int g = blockIdx.x * BD_THREADS + threadIdx.x;
   if (g >= n) return;
-  const int r = radii[g];
-  u64 mask = 0ull;
-  if (r > 0)
-    for_each_kept_tile(xys[g], r, conics[3 * (size_t)g], conics[3 * (size_t)g + 1], conics[3 * (size_t)g + 2], opacities[g],
-                       tiles_x, tiles_y, block_width, mask, false, [&](int tile) { atomicAdd(tile_count + tile, 1u); });
-  masks[g] = mask;
+  masks[g] = count_one(g, xys, radii, conics, opacities, tiles_x, tiles_y, block_width,
+                              [&](int tile) { atomicAdd(tile_count + tile, 1u); });
 }
 
 constexpr int SORT_WARP_SMALL = 512;  // tiles up to this size: tile_sort_warp_kernel<false> over all tiles
@@ -158,12 +212,29 @@ tile_scan_kernel(int num_tiles, const unsigned *__restrict__ tile_count, int cap
     for (int i = 0; i < PER; ++i) {
       const int tile = c0 + tid * PER + i;
       const unsigned long long nxt = run + v[i];
+      int len = 0;
       if (tile < num_tiles) {
         const int b = (int)min(run, cap), e = (int)min(nxt, cap);
         tile_bins[tile] = (e > b) ? make_int2(b, e) : make_int2(0, 0);  // empty tiles are (0, 0), like the reference's zeros
         cursors[tile] = (unsigned)min(run, 0xffffffffull);
-        if (e - b > SORT_WARP_MAX) lng[atomicAdd(&s_nlong, 1)] = tile;
-        else if (e - b > SORT_WARP_SMALL) mid[atomicAdd(&s_nmid, 1)] = tile;
+        len = e - b;
+      }
+      // list appends: one shared-memory atomic per warp and list instead of one per tile on the same counter (at cfg4
+      // nearly all 32 400 tiles are `mid` tiles)
+      const bool is_long = len > SORT_WARP_MAX, is_mid = !is_long && len > SORT_WARP_SMALL;
+      const unsigned m_mid = __ballot_sync(0xffffffffu, is_mid), m_long = __ballot_sync(0xffffffffu, is_long);
+      const unsigned below = (1u << lane) - 1u;
+      if (m_mid) {
+        int at = 0;
+        if (lane == 0) at = atomicAdd(&s_nmid, __popc(m_mid));
+        at = __shfl_sync(0xffffffffu, at, 0);
+        if (is_mid) mid[at + __popc(m_mid & below)] = tile;
+      }
+      if (m_long) {
+        int at = 0;
+        if (lane == 0) at = atomicAdd(&s_nlong, __popc(m_long));
+        at = __shfl_sync(0xffffffffu, at, 0);
+        if (is_long) lng[at + __popc(m_long & below)] = tile;
       }
       run = nxt;
     }
@@ -190,16 +261,10 @@ bin_fill_kernel(int n, const float2 *__restrict__ xys, const float *__restrict__
                 u64 *__restrict__ keys) {
   const int g = blockIdx.x * BD_THREADS + threadIdx.x;
   if (g >= n) return;
-  const int r = radii[g];
-  if (r <= 0) return;
-  u64 mask = masks[g];
-  // the low 32 bits of the reference key are the IEEE bits of the depth (forward.cu:116); the id breaks ties in index order
-  const u64 key = ((u64)(unsigned)__float_as_int(depths[g]) << 32) | (u64)(unsigned)g;
-  for_each_kept_tile(xys[g], r, conics[3 * (size_t)g], conics[3 * (size_t)g + 1], conics[3 * (size_t)g + 2], opacities[g],
-                     tiles_x, tiles_y, block_width, mask, true, [&](int tile) {
-                       const unsigned pos = atomicAdd(cursors + tile, 1u);
-                       if (pos < (unsigned)capacity) keys[pos] = key;
-                     });
+  fill_one(g, xys, depths, radii, conics, opacities, masks, tiles_x, tiles_y, block_width, [&](int tile, u64 key) {
+    const unsigned pos = atomicAdd(cursors + tile, 1u);
+    if (pos < (unsigned)capacity) keys[pos] = key;
+  });
 }
 
 // ---- block-privatised counting / filling (no global atomics) --------------------------------------------------------
@@ -222,14 +287,9 @@ bin_count_blocks_kernel(int n, int per_block, const float2 *__restrict__ xys, co
   for (int i = threadIdx.x; i < words; i += BLK_THREADS) s_hist[i] = 0u;
   __syncthreads();
   const int g0 = blockIdx.x * per_block, g1 = min(n, g0 + per_block);
-  for (int g = g0 + threadIdx.x; g < g1; g += BLK_THREADS) {
-    const int r = radii[g];
-    u64 mask = 0ull;
-    if (r > 0)
-      for_each_kept_tile(xys[g], r, conics[3 * (size_t)g], conics[3 * (size_t)g + 1], conics[3 * (size_t)g + 2], opacities[g],
-                         tiles_x, tiles_y, block_width, mask, false, [&](int tile) { smem_count_inc(s_hist, tile); });
-    masks[g] = mask;
-  }
+  for (int g = g0 + threadIdx.x; g < g1; g += BLK_THREADS)
+    masks[g] = count_one(g, xys, radii, conics, opacities, tiles_x, tiles_y, block_width,
+                                [&](int tile) { smem_count_inc(s_hist, tile); });
   __syncthreads();
   unsigned *row = base + (size_t)blockIdx.x * num_tiles;
   for (int t = threadIdx.x; t < num_tiles; t += BLK_THREADS) row[t] = (s_hist[t >> 1] >> ((t & 1) * 16)) & 0xffffu;
@@ -285,17 +345,11 @@ bin_fill_blocks_kernel(int n, int per_block, const float2 *__restrict__ xys, con
   for (int i = threadIdx.x; i < num_tiles; i += BLK_THREADS) s_cur[i] = tile_start[i] + row[i];
   __syncthreads();
   const int g0 = blockIdx.x * per_block, g1 = min(n, g0 + per_block);
-  for (int g = g0 + threadIdx.x; g < g1; g += BLK_THREADS) {
-    const int r = radii[g];
-    if (r <= 0) continue;
-    u64 mask = masks[g];
-    const u64 key = ((u64)(unsigned)__float_as_int(depths[g]) << 32) | (u64)(unsigned)g;
-    for_each_kept_tile(xys[g], r, conics[3 * (size_t)g], conics[3 * (size_t)g + 1], conics[3 * (size_t)g + 2], opacities[g],
-                       tiles_x, tiles_y, block_width, mask, true, [&](int tile) {
-                         const unsigned pos = atomicAdd(&s_cur[tile], 1u);
-                         if (pos < (unsigned)capacity) keys[pos] = key;
-                       });
-  }
+  for (int g = g0 + threadIdx.x; g < g1; g += BLK_THREADS)
+    fill_one(g, xys, depths, radii, conics, opacities, masks, tiles_x, tiles_y, block_width, [&](int tile, u64 key) {
+      const unsigned pos = atomicAdd(&s_cur[tile], 1u);
+      if (pos < (unsigned)capacity) keys[pos] = key;
+    });
 }
 
 // ---- per-tile sort, one warp per tile, keys in registers --------------------------------------------------------------
@@ -555,12 +609,14 @@ struct BinLayout {  // carved from the caller's workspace
   int per_block, num_blocks;  // Gaussians per block / blocks of the shared-memory-histogram kernels (0 = global atomics)
 };
 
-// Gaussians per block: about two blocks per SM, a multiple of the block size, at most 65535 (16-bit counters)
+// Gaussians per block: two blocks per SM (2 x 148), a multiple of the warp size, at most 65535 (16-bit counters).
+// (Rounding up to a multiple of the block size — 3379 -> 4096 at cfg2 — left 245 blocks for 296 slots: a third of the SMs
+// ran one block while the others ran two, ncu "0.8 full waves", SMs active 74 % of the kernel.)
 inline void block_partition(int num_points, int num_tiles, int &per_block, int &num_blocks) {
   per_block = num_blocks = 0;
   if (num_tiles > SMEM_HIST_MAX_TILES || num_points <= 0) return;
   long long per = ((long long)num_points + 295) / 296;
-  per = ((per + 1023) / 1024) * 1024;
+  per = ((per + 31) / 32) * 32;
   if (per < 2048) per = 2048;
   if (per > 65280) per = 65280;
   per_block = (int)per;

@@ -38,6 +38,7 @@ struct TrSmem {
   float2 wf[BLEND_THREADS / 32][G * kRowStride];
   float4 vout[BLEND_THREADS / 32][32];
   unsigned char list[BLEND_THREADS / 32][BLEND_THREADS + 8];  // + 8: the pipelined phase 1 reads up to two entries ahead
+  alignas(8) unsigned char mask[2][BLEND_THREADS];  // MASKS: per staged record, the warp blocks it can reach (block_mask_16)
   int warp_max[BLEND_THREADS / 32];
 };
 
@@ -128,16 +129,20 @@ __device__ __forceinline__ void sum_rows(const RowGaussian &R, int rows, const f
   }
 }
 
-template <int G, int MIN_CTAS>
-__global__ void __launch_bounds__(BLEND_THREADS, MIN_CTAS)
-blend_backward_tr_kernel(int tiles_x, int img_w, int img_h, const int *__restrict__ gaussian_ids_sorted,
-                         const int2 *__restrict__ tile_bins, const float2 *__restrict__ xys,
-                         const float *__restrict__ conics, const float *__restrict__ colors,
-                         const float *__restrict__ opacities, const float *__restrict__ background,
-                         const float *__restrict__ final_Ts, const int *__restrict__ final_idx,
-                         const float *__restrict__ v_output, const float *__restrict__ v_output_alpha,
-                         float *__restrict__ v_xy, float *__restrict__ v_conic, float *__restrict__ v_colors,
-                         float *__restrict__ v_opacity) {
+#define GSR_TR_PARAMS                                                                                                   \
+  int tiles_x, int img_w, int img_h, const int *__restrict__ gaussian_ids_sorted, const int2 *__restrict__ tile_bins,   \
+      const float2 *__restrict__ xys, const float *__restrict__ conics, const float *__restrict__ colors,               \
+      const float *__restrict__ opacities, const float *__restrict__ background, const float *__restrict__ final_Ts,    \
+      const int *__restrict__ final_idx, const float *__restrict__ v_output, const float *__restrict__ v_output_alpha,  \
+      float *__restrict__ v_xy, float *__restrict__ v_conic, float *__restrict__ v_colors, float *__restrict__ v_opacity
+#define GSR_TR_ARGS                                                                                                     \
+  tiles_x, img_w, img_h, gaussian_ids_sorted, tile_bins, xys, conics, colors, opacities, background, final_Ts,          \
+      final_idx, v_output, v_output_alpha, v_xy, v_conic, v_colors, v_opacity
+
+// MASKS: the staging thread evaluates its record against the eight warp blocks once (block_mask_16, blend_common.cuh)
+// instead of every warp testing every record (compact_survivors)
+template <int G, bool MASKS>
+__device__ __forceinline__ void blend_backward_tr_body(GSR_TR_PARAMS) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TrSmem<G> &S = *reinterpret_cast<TrSmem<G> *>(smem_raw);
 
@@ -152,6 +157,7 @@ blend_backward_tr_kernel(int tiles_x, int img_w, int img_h, const int *__restric
   const float px = (float)ipx, py = (float)ipy;
   const int pix = inside ? (ipy * img_w + ipx) : 0;
   const float x0 = (float)(tile_x * 16 + ((warp & 1) << 3)), y0 = (float)(tile_y * 16 + ((warp >> 1) << 2));
+  const float tile_x0 = (float)(tile_x * 16), tile_y0 = (float)(tile_y * 16);
 
   const float fx0 = (float)__reduce_min_sync(full, inside ? ipx : 0x7fffffff);
   const float fx1 = (float)__reduce_max_sync(full, inside ? ipx : -0x7fffffff);
@@ -202,6 +208,7 @@ blend_backward_tr_kernel(int tiles_x, int img_w, int img_h, const int *__restric
       S.rec[buf][0][tr] = rec.r0;
       S.rec[buf][1][tr] = rec.r1;
       S.rec[buf][2][tr] = rec.r2;
+      if (MASKS) S.mask[buf][tr] = (unsigned char)block_mask_16(rec.r0, rec.r1, tile_x0, tile_y0);
     }
     __syncthreads();
     {
@@ -211,8 +218,9 @@ blend_backward_tr_kernel(int tiles_x, int img_w, int img_h, const int *__restric
     const int batch_size = min(nthreads, batch_end + 1 - range.x);
     const int t_begin = max(0, batch_end - warp_bin_final);  // slots before it are behind every pixel's last contributor
     if (t_begin >= batch_size) continue;
-    const int n_list = compact_survivors(S.rec[buf][0], S.rec[buf][1], t_begin, batch_size, fx0, fx1, fy0, fy1,
-                                         S.list[warp], lane);
+    const int n_list = MASKS ? compact_from_masks(S.mask[buf], warp, t_begin, batch_size, S.list[warp], lane)
+                             : compact_survivors(S.rec[buf][0], S.rec[buf][1], t_begin, batch_size, fx0, fx1, fy0, fy1,
+                                                 S.list[warp], lane);
     const unsigned char *list = S.list[warp];
     const int slot_min = batch_end - bin_final;  // slot t holds sorted index batch_end - t <= bin_final  <=>  t >= slot_min
     int li = 0;
@@ -273,11 +281,34 @@ blend_backward_tr_kernel(int tiles_x, int img_w, int img_h, const int *__restric
   }
 }
 
+// the default: block masks from the staging threads
+template <int G, int MIN_CTAS>
+__global__ void __launch_bounds__(BLEND_THREADS, MIN_CTAS) blend_backward_tr_kernel(GSR_TR_PARAMS) {
+  blend_backward_tr_body<G, true>(GSR_TR_ARGS);
+}
+
+// GSR_BLOCK_MASK=0: per-warp tests
+template <int G, int MIN_CTAS>
+__global__ void __launch_bounds__(BLEND_THREADS, MIN_CTAS) blend_backward_tr_warptest_kernel(GSR_TR_PARAMS) {
+  blend_backward_tr_body<G, false>(GSR_TR_ARGS);
+}
+
 template <int G, int MIN_CTAS>
 int launch_tr(dim3 grid, cudaStream_t st, int img_w, int img_h, const int *gaussian_ids_sorted, const int2 *tile_bins,
               const float2 *xys, const float *conics, const float *colors, const float *opacities,
               const float *background, const float *final_Ts, const int *final_idx, const float *v_output,
               const float *v_output_alpha, float *v_xy, float *v_conic, float *v_colors, float *v_opacity) {
+  if (!blend_block_masks()) {
+    static const cudaError_t attr0 =
+        cudaFuncSetAttribute(blend_backward_tr_warptest_kernel<G, MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(TrSmem<G>));
+    GSR_CUDA(attr0);
+    blend_backward_tr_warptest_kernel<G, MIN_CTAS><<<grid, BLEND_THREADS, sizeof(TrSmem<G>), st>>>(
+        (int)grid.x, img_w, img_h, gaussian_ids_sorted, tile_bins, xys, conics, colors, opacities, background, final_Ts,
+        final_idx, v_output, v_output_alpha, v_xy, v_conic, v_colors, v_opacity);
+    GSR_CHECK_LAUNCH("blend_backward_tr_warptest_kernel");
+    return GSR_OK;
+  }
   static const cudaError_t attr = cudaFuncSetAttribute(blend_backward_tr_kernel<G, MIN_CTAS>,
                                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TrSmem<G>));
   GSR_CUDA(attr);

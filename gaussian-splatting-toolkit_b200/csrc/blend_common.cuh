@@ -1,5 +1,7 @@
 // blend_common.cuh — pieces shared by the 3-channel blend kernels (forward and adjoint).
 #pragma once
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace gsr {
@@ -115,6 +117,92 @@ __device__ __forceinline__ int compact_survivors(const float4 *__restrict__ rec0
   if (PAD > 0 && lane < PAD) list[n + lane] = (ListT)pad_slot;
   __syncwarp();
   return n;
+}
+
+// ---- CTA-cooperative form of the same two tests for 16x16 tiles -----------------------------------------------------
+// With compact_survivors every one of the 8 warps tests every staged record (8 x 107 warp-instructions per 32 records:
+// 19 % of the forward's and 11 % of the adjoint's instructions, profiles/r02/ncu_blend_v9.txt).  Here the thread that
+// STAGES a record evaluates it once, from its registers, against all eight 8x4 pixel blocks of the tile (warp w owns
+// block column w & 1, block row w >> 1) and stores the 8-bit result next to the record; a warp then only gathers its
+// bit (compact_from_masks).  Block rectangles are taken unclipped by the image (a superset of the clipped ones), the
+// tests and their margins are those of compact_survivors: box test, then per pixel row the maximum of the exponent
+// over the block's x segment against -log2(255 o); anything not provably below the threshold is kept (NaNs, A >= 0).
+// Written with margins (>= 0 keeps) combined by min and read off the sign bit: the predicate form of the same logic
+// compiles to ~130 instructions of predicate spilling (P2R / LOP3) on top of the ~300 of arithmetic.
+__device__ __forceinline__ unsigned block_mask_16(const float4 c, const float4 q, float tile_x0, float tile_y0) {
+  // NaN anywhere (non-positive-definite conic, NaN opacity) or inf - inf: keep every block (fmin / fmax drop NaNs)
+  const float probe = (c.x + c.y) + (c.z + c.w) + (q.x + q.y) + (q.z + q.w);
+  const bool weird = !(probe == probe);
+  const bool any_shape = !(q.x < 0.f);  // not concave in dx: only the box test applies
+  const float thr = -1.001f * __log2f(255.f * q.w) - 0.01f;
+  const float k = -0.5f * q.y / q.x;
+  const float lo0 = tile_x0 - c.x, hi0 = lo0 + 7.f, lo1 = lo0 + 8.f, hi1 = lo0 + 15.f;
+  const float dy0 = tile_y0 - c.y;
+  // box test:  !(x + ext < x_min || x - ext > x_max)  <=>  ext - max(x_min - x, x - x_max) >= 0
+  const float box_l = c.z - fmaxf(lo0, -hi0), box_r = c.z - fmaxf(lo1, -hi1);
+  unsigned reject = 0u;
+#pragma unroll
+  for (int g = 3; g >= 0; --g) {
+    const float ylo = dy0 + (float)(4 * g);
+    const float box_y = c.w - fmaxf(ylo, -(ylo + 3.f));
+    float pm0 = -3.0e38f, pm1 = -3.0e38f;  // max of the exponent over the block's rows and its x segment
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float dy = dy0 + (float)(4 * g + i);
+      const float v = k * dy, bdy = q.y * dy, cdy = q.z * dy * dy;
+      const float dx0 = fminf(fmaxf(v, lo0), hi0), dx1 = fminf(fmaxf(v, lo1), hi1);
+      pm0 = fmaxf(pm0, dx0 * (q.x * dx0 + bdy) + cdy);
+      pm1 = fmaxf(pm1, dx1 * (q.x * dx1 + bdy) + cdy);
+    }
+    const float row0 = any_shape ? 1.f : pm0 - thr, row1 = any_shape ? 1.f : pm1 - thr;  // !(pm < thr)
+    const float m1 = fminf(fminf(box_y, box_r), row1), m0 = fminf(fminf(box_y, box_l), row0);
+    reject = (reject << 1) | (__float_as_uint(m1) >> 31);  // bit 2 g + 1
+    reject = (reject << 1) | (__float_as_uint(m0) >> 31);  // bit 2 g
+  }
+  return weird ? 0xffu : (~reject & 0xffu);
+}
+
+// Per-warp list of the staged records [t_begin, t_end) whose block mask has this warp's bit (ascending slot numbers,
+// padded like compact_survivors).  Returns the number kept (warp-uniform).  `masks` holds BLEND_THREADS bytes, 8-byte
+// aligned; bytes at or beyond t_end may be stale (they are masked off).  Lane l owns slots 8 l .. 8 l + 7: one 8-byte
+// load, the warp's bit of the eight bytes gathered with a multiply, an exclusive prefix over the lanes and a short
+// store loop — ~75 instructions per (warp, batch) instead of 8 ballot rounds.
+template <typename ListT = unsigned char, int PAD = 0>
+__device__ __forceinline__ int compact_from_masks(const unsigned char *__restrict__ masks, int warp, int t_begin, int t_end,
+                                                  ListT *__restrict__ list, int lane, int pad_slot = 0) {
+  const uint2 m = reinterpret_cast<const uint2 *>(masks)[lane];
+  const unsigned lo = (m.x >> warp) & 0x01010101u, hi = (m.y >> warp) & 0x01010101u;
+  // bits 0, 8, 16, 24 -> bits 24..27 of the product (all partial products land on distinct bits: no carries)
+  unsigned f = ((lo * 0x01020408u) >> 24) | (((hi * 0x01020408u) >> 24) << 4);
+  const int s0 = 8 * lane;
+  const int nb = min(max(t_begin - s0, 0), 8), ne = min(max(t_end - s0, 0), 8);
+  f &= ((1u << ne) - 1u) & ~((1u << nb) - 1u);
+  const int cnt = __popc(f);
+  int incl = cnt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int up = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += up;
+  }
+  const int n = __shfl_sync(0xffffffffu, incl, 31);
+  ListT *dst = list + (incl - cnt);
+  while (f) {
+    const unsigned low = f & (0u - f);
+    *dst++ = (ListT)(s0 + 31 - __clz((int)low));
+    f ^= low;
+  }
+  if (PAD > 0 && lane < PAD) list[n + lane] = (ListT)pad_slot;
+  __syncwarp();
+  return n;
+}
+
+// GSR_BLOCK_MASK = 0 keeps the per-warp tests (compact_survivors) in the 16x16 kernels; read once
+inline bool blend_block_masks() {
+  static const bool v = [] {
+    const char *e = getenv("GSR_BLOCK_MASK");
+    return !(e && e[0] == '0');
+  }();
+  return v;
 }
 
 }  // namespace gsr

@@ -28,17 +28,21 @@
 
 namespace gsr {
 
-__global__ void __launch_bounds__(BLEND_THREADS, GSR_FWD_MIN_CTAS)
-blend_forward_kernel(int tiles_x, int img_w, int img_h, int block_width,
-                     const int *__restrict__ gaussian_ids_sorted, const int2 *__restrict__ tile_bins,
-                     const float2 *__restrict__ xys, const float *__restrict__ conics,
-                     const float *__restrict__ colors, const float *__restrict__ opacities,
-                     const float *__restrict__ background, float *__restrict__ out_img,
-                     float *__restrict__ final_Ts, int *__restrict__ final_idx) {
+// MASKS (16x16 tiles only): the staging thread evaluates its record against the eight warp blocks once (block_mask_16)
+// instead of every warp testing every record (compact_survivors) — see blend_common.cuh
+template <bool MASKS>
+__device__ __forceinline__ void blend_forward_body(int tiles_x, int img_w, int img_h, int block_width,
+                                                   const int *__restrict__ gaussian_ids_sorted,
+                                                   const int2 *__restrict__ tile_bins, const float2 *__restrict__ xys,
+                                                   const float *__restrict__ conics, const float *__restrict__ colors,
+                                                   const float *__restrict__ opacities,
+                                                   const float *__restrict__ background, float *__restrict__ out_img,
+                                                   float *__restrict__ final_Ts, int *__restrict__ final_idx) {
   // slot kNull of every plane holds a record that never contributes (opacity 0): the survivor lists are padded with it
   constexpr int kNull = BLEND_THREADS, kUnroll = GSR_FWD_UNROLL;
   __shared__ float4 s_rec[2][3][BLEND_THREADS + 1];
   __shared__ unsigned short s_list[BLEND_THREADS / 32][BLEND_THREADS + kUnroll + 2];
+  __shared__ __align__(8) unsigned char s_mask[2][MASKS ? BLEND_THREADS : 8];
 
   const unsigned full = 0xffffffffu;
   const int tile_x = blockIdx.x, tile_y = blockIdx.y;
@@ -59,6 +63,7 @@ blend_forward_kernel(int tiles_x, int img_w, int img_h, int block_width,
 
   const int2 range = tile_bins[tile_id];
   const int num_batches = (range.y - range.x + nthreads - 1) / nthreads;
+  const float tile_x0 = (float)(tile_x * 16), tile_y0 = (float)(tile_y * 16);  // MASKS: block_width == 16
 
   float T = 1.f;
   int cur_idx = 0;
@@ -79,6 +84,7 @@ blend_forward_kernel(int tiles_x, int img_w, int img_h, int block_width,
       s_rec[buf][0][tr] = rec.r0;
       s_rec[buf][1][tr] = rec.r1;
       s_rec[buf][2][tr] = rec.r2;
+      if (MASKS) s_mask[buf][tr] = (unsigned char)block_mask_16(rec.r0, rec.r1, tile_x0, tile_y0);
     }
     // one barrier per batch: publishes buffer `buf` and counts finished pixels (forward.cu:327-329)
     if (__syncthreads_count(slot_stop < 0) >= nthreads) break;
@@ -90,8 +96,10 @@ blend_forward_kernel(int tiles_x, int img_w, int img_h, int block_width,
 
     const int batch_size = min(nthreads, range.y - batch_start);
     const unsigned short *lp = s_list[warp];
-    const int n_list = compact_survivors<unsigned short, kUnroll + 2>(s_rec[buf][0], s_rec[buf][1], 0, batch_size, fx0, fx1,
-                                                                      fy0, fy1, s_list[warp], lane, kNull);
+    const int n_list =
+        MASKS ? compact_from_masks<unsigned short, kUnroll + 2>(s_mask[buf], warp, 0, batch_size, s_list[warp], lane, kNull)
+              : compact_survivors<unsigned short, kUnroll + 2>(s_rec[buf][0], s_rec[buf][1], 0, batch_size, fx0, fx1, fy0,
+                                                               fy1, s_list[warp], lane, kNull);
     // Software-pipelined walk, kUnroll survivors per trip (the list is padded with the null record, so there is no
     // remainder loop); the next record is loaded while this one is evaluated, and the all-pixels-done vote is taken
     // once per trip — visits after the last pixel has finished change nothing (no lane contributes).
@@ -140,6 +148,25 @@ blend_forward_kernel(int tiles_x, int img_w, int img_h, int block_width,
   }
 }
 
+#define GSR_FWD_PARAMS                                                                                                  \
+  int tiles_x, int img_w, int img_h, int block_width, const int *__restrict__ gaussian_ids_sorted,                      \
+      const int2 *__restrict__ tile_bins, const float2 *__restrict__ xys, const float *__restrict__ conics,             \
+      const float *__restrict__ colors, const float *__restrict__ opacities, const float *__restrict__ background,      \
+      float *__restrict__ out_img, float *__restrict__ final_Ts, int *__restrict__ final_idx
+#define GSR_FWD_ARGS                                                                                                    \
+  tiles_x, img_w, img_h, block_width, gaussian_ids_sorted, tile_bins, xys, conics, colors, opacities, background,       \
+      out_img, final_Ts, final_idx
+
+// 16x16 tiles (the default): block masks from the staging threads
+__global__ void __launch_bounds__(BLEND_THREADS, GSR_FWD_MIN_CTAS) blend_forward_kernel(GSR_FWD_PARAMS) {
+  blend_forward_body<true>(GSR_FWD_ARGS);
+}
+
+// any block width (and 16x16 with GSR_BLOCK_MASK=0): per-warp tests
+__global__ void __launch_bounds__(BLEND_THREADS, GSR_FWD_MIN_CTAS) blend_forward_warptest_kernel(GSR_FWD_PARAMS) {
+  blend_forward_body<false>(GSR_FWD_ARGS);
+}
+
 }  // namespace gsr
 
 extern "C" GSR_API int gsr_rasterize_forward(unsigned img_height, unsigned img_width, unsigned block_width,
@@ -160,10 +187,18 @@ extern "C" GSR_API int gsr_rasterize_forward(unsigned img_height, unsigned img_w
               "rasterize_forward: xys / tile_bins must be 8-byte aligned");
   const dim3 grid(cdiv(img_width, block_width), cdiv(img_height, block_width), 1);
   const unsigned threads = cdiv(block_width * block_width, 32) * 32;
-  blend_forward_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(
-      (int)grid.x, (int)img_width, (int)img_height, (int)block_width, gaussian_ids_sorted,
-      reinterpret_cast<const int2 *>(tile_bins), reinterpret_cast<const float2 *>(xys), conics, colors, opacities,
-      background, out_img, final_Ts, final_idx);
-  GSR_CHECK_LAUNCH("blend_forward_kernel");
+  if (block_width == 16 && blend_block_masks()) {
+    blend_forward_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(
+        (int)grid.x, (int)img_width, (int)img_height, (int)block_width, gaussian_ids_sorted,
+        reinterpret_cast<const int2 *>(tile_bins), reinterpret_cast<const float2 *>(xys), conics, colors, opacities,
+        background, out_img, final_Ts, final_idx);
+    GSR_CHECK_LAUNCH("blend_forward_kernel");
+  } else {
+    blend_forward_warptest_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(
+        (int)grid.x, (int)img_width, (int)img_height, (int)block_width, gaussian_ids_sorted,
+        reinterpret_cast<const int2 *>(tile_bins), reinterpret_cast<const float2 *>(xys), conics, colors, opacities,
+        background, out_img, final_Ts, final_idx);
+    GSR_CHECK_LAUNCH("blend_forward_warptest_kernel");
+  }
   return GSR_OK;
 }

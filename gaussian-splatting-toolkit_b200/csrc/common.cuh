@@ -12,6 +12,11 @@
 
 namespace gsr {
 
+// tan(fov / 2) as the reference forms it: `0.5 * img_size.x / fx` evaluated in DOUBLE and rounded once (forward.cu:71-72).
+// Computed on the host and passed to the kernels: on the device the two double divisions were ~45 dependent FP64
+// instructions per Gaussian (DFMA / DMUL / slow-path CALL) in an otherwise FP32 streaming kernel.
+inline float tan_half_fov(unsigned img_size, float focal) { return (float)(0.5 * (double)img_size / (double)focal); }
+
 // thread-local error message (api.cu)
 void set_error(const char *fmt, ...);
 // process-wide count of own kernel launches (api.cu; read with gsr_launch_count())

@@ -90,7 +90,8 @@ fused_preprocess_forward_kernel(int n, int K, int deg_use, const float *__restri
                                 const float *__restrict__ opacities_raw, const float *__restrict__ features_dc,
                                 const float *__restrict__ features_rest, const float *__restrict__ viewmat,
                                 const float *__restrict__ projmat, float glob_scale, float fx, float fy, float cx,
-                                float cy, int img_w, int img_h, int tiles_x, int tiles_y, int block_width,
+                                float cy, float tan_fovx, float tan_fovy, int img_w, int img_h, int tiles_x,
+                                int tiles_y, int block_width,
                                 float clip_thresh, float4 *__restrict__ rec0, float4 *__restrict__ rec1,
                                 float4 *__restrict__ rec2, float *__restrict__ xys, float *__restrict__ depths,
                                 int *__restrict__ radii, float *__restrict__ conics, float *__restrict__ opac_act,
@@ -115,8 +116,8 @@ fused_preprocess_forward_kernel(int n, int K, int deg_use, const float *__restri
   const float4 q = reinterpret_cast<const float4 *>(quats_raw)[g];
   float opac = 1.f / (1.f + __expf(-opacities_raw[g]));
 
-  const ProjFwd p = project_one(px, py, pz, s0, s1, s2, q.x, q.y, q.z, q.w, cam.V, cam.PM, fx, fy, cx, cy, img_w,
-                                img_h, tiles_x, tiles_y, block_width, clip_thresh);
+  const ProjFwd p = project_one(px, py, pz, s0, s1, s2, q.x, q.y, q.z, q.w, cam.V, cam.PM, fx, fy, cx, cy, tan_fovx,
+                                tan_fovy, img_w, img_h, tiles_x, tiles_y, block_width, clip_thresh);
   // rasterize_mode == "antialiased": opacities = sigmoid(raw) * compensation (vanilla_gs.py:813-816)
   if (compensation != nullptr) {
     compensation[g] = p.comp;
@@ -286,7 +287,8 @@ GSR_API int gsr_fused_preprocess_forward(int num_points, int sh_degree, int degr
   float4 *rec = reinterpret_cast<float4 *>(records);
   fused_preprocess_forward_kernel<<<cdiv(num_points, FU_THREADS), FU_THREADS, smem, (cudaStream_t)stream>>>(
       num_points, K, degrees_to_use, means3d, scales_raw, quats_raw, opacities_raw, features_dc, features_rest, viewmat,
-      projmat, glob_scale, fx, fy, cx, cy, (int)img_width, (int)img_height, (int)cdiv(img_width, block_width),
+      projmat, glob_scale, fx, fy, cx, cy, tan_half_fov(img_width, fx), tan_half_fov(img_height, fy), (int)img_width,
+      (int)img_height, (int)cdiv(img_width, block_width),
       (int)cdiv(img_height, block_width), (int)block_width, clip_thresh, rec, rec + num_points, rec + 2 * (size_t)num_points,
       xys, depths, radii, conics, opacities, clamp_mask, compensation, vec_ok);
   GSR_CHECK_LAUNCH("fused_preprocess_forward_kernel");

@@ -25,11 +25,11 @@ __global__ void __launch_bounds__(PROJ_THREADS)
 project_forward_kernel(int n, const float *__restrict__ means3d, const float *__restrict__ scales,
                        float glob_scale, const float *__restrict__ quats,
                        const float *__restrict__ viewmat, const float *__restrict__ projmat, float fx,
-                       float fy, float cx, float cy, int img_w, int img_h, int tiles_x, int tiles_y,
-                       int block_width, float clip_thresh, float *__restrict__ cov3d,
+                       float fy, float cx, float cy, float tan_fovx, float tan_fovy, int img_w, int img_h,
+                       int tiles_x, int tiles_y, int block_width, float clip_thresh, float *__restrict__ cov3d,
                        float *__restrict__ xys, float *__restrict__ depths, int *__restrict__ radii,
                        float *__restrict__ conics, float *__restrict__ compensation,
-                       int *__restrict__ num_tiles_hit) {
+                       int *__restrict__ num_tiles_hit, int quats_vec) {
   __shared__ CamParams cam;
   if (threadIdx.x < 12) cam.V[threadIdx.x] = viewmat[threadIdx.x];
   if (threadIdx.x >= 32 && threadIdx.x < 48) cam.PM[threadIdx.x - 32] = projmat[threadIdx.x - 32];
@@ -43,7 +43,17 @@ project_forward_kernel(int n, const float *__restrict__ means3d, const float *__
   float o_x = 0.f, o_y = 0.f, o_depth = 0.f, o_comp = 0.f;
   int o_radius = 0, o_tiles = 0;
 
+  // every input of the Gaussian is requested before the first use (one exposed round trip to HBM instead of two: the
+  // quaternion and the scales used to be loaded behind the near-plane branch)
   const float px = means3d[3 * (size_t)idx], py = means3d[3 * (size_t)idx + 1], pz = means3d[3 * (size_t)idx + 2];
+  float4 q;
+  if (quats_vec) {
+    q = reinterpret_cast<const float4 *>(quats)[idx];
+  } else {
+    q = make_float4(quats[4 * (size_t)idx], quats[4 * (size_t)idx + 1], quats[4 * (size_t)idx + 2],
+                    quats[4 * (size_t)idx + 3]);
+  }
+  const float sc0 = scales[3 * (size_t)idx], sc1 = scales[3 * (size_t)idx + 1], sc2 = scales[3 * (size_t)idx + 2];
   // clip_near_plane (helpers.cuh:210-219)
   const float vx = V[0] * px + V[1] * py + V[2] * pz + V[3];
   const float vy = V[4] * px + V[5] * py + V[6] * pz + V[7];
@@ -53,10 +63,8 @@ project_forward_kernel(int n, const float *__restrict__ means3d, const float *__
 
     // scale_rot_to_cov3d (forward.cu:445-464): M = R * S, Sigma = M * M^T
     float R[9];
-    quat_to_rotmat(quats[4 * (size_t)idx], quats[4 * (size_t)idx + 1], quats[4 * (size_t)idx + 2],
-                   quats[4 * (size_t)idx + 3], R);
-    const float s0 = glob_scale * scales[3 * (size_t)idx], s1 = glob_scale * scales[3 * (size_t)idx + 1],
-                s2 = glob_scale * scales[3 * (size_t)idx + 2];
+    quat_to_rotmat(q.x, q.y, q.z, q.w, R);
+    const float s0 = glob_scale * sc0, s1 = glob_scale * sc1, s2 = glob_scale * sc2;
     float M[9] = {R[0] * s0, R[1] * s1, R[2] * s2, R[3] * s0, R[4] * s1, R[5] * s2, R[6] * s0, R[7] * s1, R[8] * s2};
     o_cov3d[0] = M[0] * M[0] + M[1] * M[1] + M[2] * M[2];
     o_cov3d[1] = M[0] * M[3] + M[1] * M[4] + M[2] * M[5];
@@ -66,8 +74,7 @@ project_forward_kernel(int n, const float *__restrict__ means3d, const float *__
     o_cov3d[5] = M[6] * M[6] + M[7] * M[7] + M[8] * M[8];
 
     // project_cov3d_ewa (forward.cu:398-442)
-    // the reference evaluates `0.5 * img_size.x / fx` in DOUBLE (forward.cu:71-72) and rounds once
-    const float tan_fovx = (float)(0.5 * (double)img_w / (double)fx), tan_fovy = (float)(0.5 * (double)img_h / (double)fy);
+    // tan_fov: `0.5 * img_size.x / fx` in DOUBLE, rounded once, like the reference (host side: tan_half_fov)
     const float lim_x = 1.3f * tan_fovx, lim_y = 1.3f * tan_fovy;
     const float tz = vz;
     const float tx = tz * fminf(lim_x, fmaxf(-lim_x, vx / tz));
@@ -314,9 +321,9 @@ GSR_API int gsr_project_gaussians_forward(int num_points, const float *means3d, 
   GSR_REQUIRE((uintptr_t)xys % 8 == 0, GSR_ERR_INVALID_ARGUMENT, "project_gaussians_forward: xys must be 8-byte aligned");
   const int tiles_x = cdiv(img_width, block_width), tiles_y = cdiv(img_height, block_width);
   project_forward_kernel<<<cdiv(num_points, PROJ_THREADS), PROJ_THREADS, 0, (cudaStream_t)stream>>>(
-      num_points, means3d, scales, glob_scale, quats, viewmat, projmat, fx, fy, cx, cy, (int)img_width,
-      (int)img_height, tiles_x, tiles_y, (int)block_width, clip_thresh, cov3d, xys, depths, radii, conics,
-      compensation, num_tiles_hit);
+      num_points, means3d, scales, glob_scale, quats, viewmat, projmat, fx, fy, cx, cy, tan_half_fov(img_width, fx),
+      tan_half_fov(img_height, fy), (int)img_width, (int)img_height, tiles_x, tiles_y, (int)block_width, clip_thresh, cov3d,
+      xys, depths, radii, conics, compensation, num_tiles_hit, (uintptr_t)quats % 16 == 0 ? 1 : 0);
   GSR_CHECK_LAUNCH("project_forward_kernel");
   return GSR_OK;
 }

@@ -17,8 +17,9 @@ struct ProjFwd {
 // s0,s1,s2 = glob_scale * (activated) scales; V = viewmat (12 floats), PM = projmat (16 floats)
 __device__ __forceinline__ ProjFwd project_one(float px, float py, float pz, float s0, float s1, float s2, float qw,
                                                float qx, float qy, float qz, const float *V, const float *PM, float fx,
-                                               float fy, float cx, float cy, int img_w, int img_h, int tiles_x,
-                                               int tiles_y, int block_width, float clip_thresh) {
+                                               float fy, float cx, float cy, float tan_fovx, float tan_fovy, int img_w,
+                                               int img_h, int tiles_x, int tiles_y, int block_width,
+                                               float clip_thresh) {
   float o_cov3d[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   float o_conic[3] = {0.f, 0.f, 0.f};
   float o_x = 0.f, o_y = 0.f, o_depth = 0.f, o_comp = 0.f;
@@ -43,8 +44,7 @@ __device__ __forceinline__ ProjFwd project_one(float px, float py, float pz, flo
     o_cov3d[5] = M[6] * M[6] + M[7] * M[7] + M[8] * M[8];
 
     // project_cov3d_ewa (forward.cu:398-442)
-    // the reference evaluates `0.5 * img_size.x / fx` in DOUBLE (forward.cu:71-72) and rounds once
-    const float tan_fovx = (float)(0.5 * (double)img_w / (double)fx), tan_fovy = (float)(0.5 * (double)img_h / (double)fy);
+    // tan_fov: `0.5 * img_size.x / fx` in DOUBLE, rounded once, like the reference (host side: tan_half_fov)
     const float lim_x = 1.3f * tan_fovx, lim_y = 1.3f * tan_fovy;
     const float tz = vz;
     const float tx = tz * fminf(lim_x, fmaxf(-lim_x, vx / tz));

@@ -132,3 +132,14 @@ def test_python_error_behaviour_on_cpu():
     with pytest.warns(DeprecationWarning):
         with pytest.raises(RuntimeError):
             rasterizer.SphericalHarmonics.apply(0, torch.zeros(4, 3), torch.zeros(4, 1, 3))
+
+
+def test_tile_mask_division_magic_is_exact():
+    """binning_device.cu walks the cached 64-bit tile mask of a bounding box without an integer division: row of bit k
+    = (k * magic) >> 16 with magic = trunc(65536 / d) + 1 from a fast-math FP32 reciprocal (d = box width in tiles, at
+    most 64; k < 64).  Every magic the approximate division can produce must give exactly k // d."""
+    for d in range(1, 65):
+        x = 65536.0 / d
+        for magic in {int(x * (1 - 2.0 ** -20)) + 1, int(x) + 1, int(x * (1 + 2.0 ** -20)) + 1}:
+            for k in range(64):
+                assert (k * magic) >> 16 == k // d, (d, magic, k)
