@@ -276,7 +276,10 @@ __device__ __forceinline__ unsigned smem_count_inc(unsigned *s_hist, int tile) {
   return (tile & 1) ? (old >> 16) : (old & 0xffffu);
 }
 
-constexpr int BLK_THREADS = 1024;  // few, fat blocks: one shared-memory histogram per block, full occupancy per SM
+#ifndef GSR_BLK_THREADS
+#define GSR_BLK_THREADS 1024
+#endif
+constexpr int BLK_THREADS = GSR_BLK_THREADS;  // few, fat blocks: one shared-memory histogram per block, full occupancy per SM
 
 __global__ void __launch_bounds__(BLK_THREADS)
 bin_count_blocks_kernel(int n, int per_block, const float2 *__restrict__ xys, const int *__restrict__ radii,
@@ -404,7 +407,10 @@ __device__ __forceinline__ void warp_sort_tile(const u64 *__restrict__ seg, int 
   }
 }
 
-constexpr int SORT_WARPS = 4;        // warps (= tiles) per CTA of tile_sort_warp_kernel
+#ifndef GSR_SORT_WARPS
+#define GSR_SORT_WARPS 4
+#endif
+constexpr int SORT_WARPS = GSR_SORT_WARPS;  // warps (= tiles) per CTA of tile_sort_warp_kernel
 
 // BIG = false: every tile with 1..512 pairs (E <= 16, ~90 registers), one warp per tile; BIG = true: the tiles of the
 // `mid` list (513..1024 pairs, E = 32, ~170 registers), a fixed grid striding over the list — two kernels so that the
@@ -615,9 +621,10 @@ struct BinLayout {  // carved from the caller's workspace
 inline void block_partition(int num_points, int num_tiles, int &per_block, int &num_blocks) {
   per_block = num_blocks = 0;
   if (num_tiles > SMEM_HIST_MAX_TILES || num_points <= 0) return;
-  long long per = ((long long)num_points + 295) / 296;
+  constexpr long long kBlocks = 148ll * (2048 / BLK_THREADS);
+  long long per = ((long long)num_points + kBlocks - 1) / kBlocks;
   per = ((per + 31) / 32) * 32;
-  if (per < 2048) per = 2048;
+  if (per < 2 * BLK_THREADS) per = 2 * BLK_THREADS;
   if (per > 65280) per = 65280;
   per_block = (int)per;
   num_blocks = (int)(((long long)num_points + per - 1) / per);

@@ -26,6 +26,12 @@
 
 #include "blend_common.cuh"
 
+#ifndef GSR_TR_UNROLL
+#define GSR_TR_UNROLL 2  // visits per trip of the phase-1 walk
+#endif
+#define GSR_PRAGMA_(x) _Pragma(#x)
+#define GSR_PRAGMA_UNROLL(n) GSR_PRAGMA_(unroll n)
+
 namespace gsr {
 
 namespace {
@@ -241,7 +247,7 @@ __device__ __forceinline__ void blend_backward_tr_body(GSR_TR_PARAMS) {
       float4 q1 = S.rec[buf][1][slot];
       float4 q2 = S.rec[buf][2][slot];
       int slot_n = lp[1];  // the list is padded: reading one or two entries past its end is harmless
-#pragma unroll 2
+GSR_PRAGMA_UNROLL(GSR_TR_UNROLL)
       for (int k = 0; k < take; ++k) {
         const float2 n0 = *reinterpret_cast<const float2 *>(&S.rec[buf][0][slot_n]);
         const float4 n1 = S.rec[buf][1][slot_n];

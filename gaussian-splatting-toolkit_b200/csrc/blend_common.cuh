@@ -78,7 +78,9 @@ __device__ __forceinline__ void map_pixel(int block_width, int &lx, int &ly) {
 // Anything not provably below the threshold is kept (NaNs, A >= 0): comparisons are written so NaN keeps.
 // PAD > 0: the PAD entries after the last survivor are set to `pad_slot` (a record that never contributes), so that a
 // consumer may unroll / read ahead past the end of the list without a remainder loop.
-template <typename ListT = unsigned char, int PAD = 0>
+// SHIFT: the list holds slot << SHIFT (SHIFT = 4: the byte offset of the slot's float4 in a record plane, which saves
+// the consumer one address instruction per visit).
+template <typename ListT = unsigned char, int PAD = 0, int SHIFT = 0>
 __device__ __forceinline__ int compact_survivors(const float4 *__restrict__ rec0, const float4 *__restrict__ rec1,
                                                  int t_begin, int t_end, float fx0, float fx1, float fy0, float fy1,
                                                  ListT *__restrict__ list, int lane, int pad_slot = 0) {
@@ -111,10 +113,10 @@ __device__ __forceinline__ int compact_survivors(const float4 *__restrict__ rec0
       }
     }
     const unsigned m = __ballot_sync(0xffffffffu, hit);
-    if (hit) list[n + __popc(m & lt_mask)] = (ListT)t;
+    if (hit) list[n + __popc(m & lt_mask)] = (ListT)(t << SHIFT);
     n += __popc(m);
   }
-  if (PAD > 0 && lane < PAD) list[n + lane] = (ListT)pad_slot;
+  if (PAD > 0 && lane < PAD) list[n + lane] = (ListT)(pad_slot << SHIFT);
   __syncwarp();
   return n;
 }
@@ -167,7 +169,7 @@ __device__ __forceinline__ unsigned block_mask_16(const float4 c, const float4 q
 // aligned; bytes at or beyond t_end may be stale (they are masked off).  Lane l owns slots 8 l .. 8 l + 7: one 8-byte
 // load, the warp's bit of the eight bytes gathered with a multiply, an exclusive prefix over the lanes and a short
 // store loop — ~75 instructions per (warp, batch) instead of 8 ballot rounds.
-template <typename ListT = unsigned char, int PAD = 0>
+template <typename ListT = unsigned char, int PAD = 0, int SHIFT = 0>
 __device__ __forceinline__ int compact_from_masks(const unsigned char *__restrict__ masks, int warp, int t_begin, int t_end,
                                                   ListT *__restrict__ list, int lane, int pad_slot = 0) {
   const uint2 m = reinterpret_cast<const uint2 *>(masks)[lane];
@@ -188,10 +190,10 @@ __device__ __forceinline__ int compact_from_masks(const unsigned char *__restric
   ListT *dst = list + (incl - cnt);
   while (f) {
     const unsigned low = f & (0u - f);
-    *dst++ = (ListT)(s0 + 31 - __clz((int)low));
+    *dst++ = (ListT)((s0 + 31 - __clz((int)low)) << SHIFT);
     f ^= low;
   }
-  if (PAD > 0 && lane < PAD) list[n + lane] = (ListT)pad_slot;
+  if (PAD > 0 && lane < PAD) list[n + lane] = (ListT)(pad_slot << SHIFT);
   __syncwarp();
   return n;
 }

@@ -29,9 +29,9 @@ np.savez({path!r}, **out)
 """
 
 
-def _run(bwd, tmp_path):
-    path = str(tmp_path / f"{bwd}.npz")
-    env = dict(os.environ, GSR_BWD_KERNEL=bwd)
+def _run(bwd, tmp_path, **extra_env):
+    path = str(tmp_path / ("_".join([bwd] + [f"{k}{v}" for k, v in extra_env.items()]) + ".npz"))
+    env = dict(os.environ, GSR_BWD_KERNEL=bwd, **extra_env)
     subprocess.run([sys.executable, "-c", _SCRIPT.format(root=ROOT, path=path)], check=True, env=env)
     return np.load(path)
 
@@ -50,6 +50,23 @@ def test_adjoint_variants_match_pixel_parallel(tmp_path, variant):
             err = np.linalg.norm(a - b) / np.linalg.norm(b)
             print(f"[adjoint variants] {variant} scene {name} {k}: normwise rel {err:.2e}")
             assert err < 5e-6, (variant, name, k, err)
+
+
+def test_block_masks_match_per_warp_tests(tmp_path):
+    """The 16x16 kernels evaluate the warp-block reach of a staged record once, in the staging thread (block_mask_16,
+    default), instead of once per warp (GSR_BLOCK_MASK=0, compact_survivors).  Both are conservative supersets of the
+    pairs that pass the per-pixel alpha test, so the forward outputs must be BITWISE identical and the gradients equal
+    up to the order of the FP32 atomics.  Scene "b" has Gaussians larger than a tile, "c" one partial tile row."""
+    ref = _run("tr", tmp_path, GSR_BLOCK_MASK="0")
+    got = _run("tr", tmp_path, GSR_BLOCK_MASK="1")
+    for name in ("a", "b", "c"):
+        for k in ("out_img", "final_Ts", "final_idx"):
+            assert np.array_equal(got[f"{name}_{k}"], ref[f"{name}_{k}"]), (name, k)
+        for k in ("v_xy", "v_conic", "v_colors", "v_opacity"):
+            a, b = got[f"{name}_{k}"].astype(np.float64), ref[f"{name}_{k}"].astype(np.float64)
+            err = np.linalg.norm(a - b) / np.linalg.norm(b)
+            print(f"[block masks] scene {name} {k}: normwise rel {err:.2e}")
+            assert err < 5e-6, (name, k, err)
 
 
 _SH_SCRIPT = r"""
