@@ -33,6 +33,8 @@
 // be captured in a CUDA graph; if M exceeds the caller's capacity, meta[1] is set (the lists are truncated).
 // Compared with round 1 (depth sort of N + emit + stable sort of M pairs by tile with cub::DeviceRadixSort + bin edges)
 // this moves 8 M bytes of keys once instead of ~50 M and drops both library sorts.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "radix_sort.cuh"
 #include "tile_cull.cuh"
@@ -68,9 +70,10 @@ __device__ __forceinline__ int cull_tiles(float2 ctr, int r, float ca, float cb,
   if (e.empty) return 0;
   int count = 0;
   u64 mk = 0ull;
+  const float inv_bw = 1.f / (float)block_width;
   for (int i = y0; i < y1; ++i) {
     int j0, j1;
-    cull_row_range(e, ctr.x, ctr.y, i, x0, x1, block_width, j0, j1);
+    cull_row_range(e, ctr.x, ctr.y, i, x0, x1, block_width, inv_bw, j0, j1);
     for (int j = j0; j < j1; ++j) f(i * tiles_x + j);
     const int cnt = j1 - j0;
     if (cnt > 0 && area <= 64) mk |= ((cnt >= 64) ? ~0ull : ((1ull << cnt) - 1ull)) << ((i - y0) * bw_tiles + (j0 - x0));
@@ -281,21 +284,27 @@ __device__ __forceinline__ unsigned smem_count_inc(unsigned *s_hist, int tile) {
 #endif
 constexpr int BLK_THREADS = GSR_BLK_THREADS;  // few, fat blocks: one shared-memory histogram per block, full occupancy per SM
 
+// WIDE: one 32-bit counter per tile (an increment is LEA + ATOMS instead of the ~8 instructions of the packed form) —
+// used when two blocks per SM still fit (4 T bytes each); the packed 16-bit counters otherwise
+template <bool WIDE>
 __global__ void __launch_bounds__(BLK_THREADS)
 bin_count_blocks_kernel(int n, int per_block, const float2 *__restrict__ xys, const int *__restrict__ radii,
                         const float *__restrict__ conics, const float *__restrict__ opacities, int tiles_x, int tiles_y,
                         int block_width, u64 *__restrict__ masks, unsigned *__restrict__ base /*[B][T]*/) {
   extern __shared__ unsigned s_hist[];
-  const int num_tiles = tiles_x * tiles_y, words = (num_tiles + 1) >> 1;
+  const int num_tiles = tiles_x * tiles_y, words = WIDE ? num_tiles : (num_tiles + 1) >> 1;
   for (int i = threadIdx.x; i < words; i += BLK_THREADS) s_hist[i] = 0u;
   __syncthreads();
   const int g0 = blockIdx.x * per_block, g1 = min(n, g0 + per_block);
   for (int g = g0 + threadIdx.x; g < g1; g += BLK_THREADS)
-    masks[g] = count_one(g, xys, radii, conics, opacities, tiles_x, tiles_y, block_width,
-                                [&](int tile) { smem_count_inc(s_hist, tile); });
+    masks[g] = count_one(g, xys, radii, conics, opacities, tiles_x, tiles_y, block_width, [&](int tile) {
+      if (WIDE) atomicAdd(s_hist + tile, 1u);
+      else smem_count_inc(s_hist, tile);
+    });
   __syncthreads();
   unsigned *row = base + (size_t)blockIdx.x * num_tiles;
-  for (int t = threadIdx.x; t < num_tiles; t += BLK_THREADS) row[t] = (s_hist[t >> 1] >> ((t & 1) * 16)) & 0xffffu;
+  for (int t = threadIdx.x; t < num_tiles; t += BLK_THREADS)
+    row[t] = WIDE ? s_hist[t] : (s_hist[t >> 1] >> ((t & 1) * 16)) & 0xffffu;
 }
 
 // exclusive prefix of every column of base [B][T] over the blocks, in place; column totals -> tile_count.
@@ -659,12 +668,22 @@ int run_count(int num_points, const float *xys, const int32_t *radii, const floa
               int32_t *meta, cudaStream_t st) {
   const int num_tiles = tiles_x * tiles_y;
   if (L.num_blocks > 0) {
-    const size_t smem = sizeof(unsigned) * (size_t)((num_tiles + 1) >> 1);
-    if (smem > 48 * 1024)
-      GSR_CUDA(cudaFuncSetAttribute(bin_count_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    bin_count_blocks_kernel<<<L.num_blocks, BLK_THREADS, smem, st>>>(
-        num_points, L.per_block, reinterpret_cast<const float2 *>(xys), radii, conics, opacities, tiles_x, tiles_y,
-        (int)block_width, L.masks, L.base);
+    static const bool allow_wide = [] { const char *e = getenv("GSR_COUNT_WIDE"); return !(e && e[0] == '0'); }();
+    const bool wide = allow_wide && sizeof(unsigned) * (size_t)num_tiles <= 100 * 1024;
+    const size_t smem = wide ? sizeof(unsigned) * (size_t)num_tiles : sizeof(unsigned) * (size_t)((num_tiles + 1) >> 1);
+    if (wide) {
+      if (smem > 48 * 1024)
+        GSR_CUDA(cudaFuncSetAttribute(bin_count_blocks_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      bin_count_blocks_kernel<true><<<L.num_blocks, BLK_THREADS, smem, st>>>(
+          num_points, L.per_block, reinterpret_cast<const float2 *>(xys), radii, conics, opacities, tiles_x, tiles_y,
+          (int)block_width, L.masks, L.base);
+    } else {
+      if (smem > 48 * 1024)
+        GSR_CUDA(cudaFuncSetAttribute(bin_count_blocks_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      bin_count_blocks_kernel<false><<<L.num_blocks, BLK_THREADS, smem, st>>>(
+          num_points, L.per_block, reinterpret_cast<const float2 *>(xys), radii, conics, opacities, tiles_x, tiles_y,
+          (int)block_width, L.masks, L.base);
+    }
     GSR_CHECK_LAUNCH("bin_count_blocks_kernel");
     bin_colscan_kernel<<<cdiv(num_tiles, 32), 1024, 0, st>>>(L.num_blocks, num_tiles, L.base, L.tile_count);
     GSR_CHECK_LAUNCH("bin_colscan_kernel");

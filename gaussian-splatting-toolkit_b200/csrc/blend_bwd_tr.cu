@@ -22,6 +22,10 @@
 // at max(final_idx) are those of blend_bwd.cu (tried and dropped: staging two batches ahead so that tiles of <= 512 pairs
 // need no barrier after the prologue — same time, the warps of a CTA finish unevenly either way); rows left over at the end of a staged batch stay in the matrix and the
 // group is completed from the next batch, so only the last group of a (warp, tile) is partially filled.
+// Measured and dropped (round 2, gpurun_out/r2_run50 / r2_run51): 16-bit lists holding byte offsets as in the forward
+// (two address instructions less per visit, 72 instead of 76 per trip of two) — 0.694 -> 0.763 ms, with AND without the
+// shift: the wider lists take the CTA from 63.6 to 65.7 KB of shared memory and the kernel loses more than the
+// instructions save; 8 / 32 rows per group 0.793 / 0.729 ms; phase-1 unroll 1 / 4: 0.730 / 0.693 ms (2 = 0.694).
 #include <stdlib.h>
 
 #include "blend_common.cuh"

@@ -43,8 +43,10 @@ __device__ __forceinline__ CullEllipse make_cull_ellipse(float a, float b, float
 }
 
 // Tiles [j0, j1) of tile row `i` (clipped to the bounding box [x0, x1)) that the ellipse can reach; j0 >= j1 if none.
+// inv_bw = 1.f / (float)block_width, hoisted out of the caller's row loop (the compiler does not hoist the MUFU.RCP of
+// the fast-math division out of a divergent loop)
 __device__ __forceinline__ void cull_row_range(const CullEllipse &e, float mx, float my, int i, int x0, int x1,
-                                               int block_width, int &j0, int &j1) {
+                                               int block_width, float inv_bw, int &j0, int &j1) {
   if (e.never_cull) {
     j0 = x0;
     j1 = x1;
@@ -61,11 +63,16 @@ __device__ __forceinline__ void cull_row_range(const CullEllipse &e, float mx, f
   const float L = (-e.b * dyl - sqrtf(fmaxf(e.a * e.thr - e.det * dyl * dyl, 0.f))) * e.inv_a;
   const float R = (-e.b * dyr + sqrtf(fmaxf(e.a * e.thr - e.det * dyr * dyr, 0.f))) * e.inv_a;
   // tile j spans x in [j bw, j bw + bw - 1]
-  const int lo_j = (int)ceilf((mx + L - (bw - 1.f)) / bw);
-  const int hi_j = (int)floorf((mx + R) / bw);
+  const int lo_j = (int)ceilf((mx + L - (bw - 1.f)) * inv_bw);
+  const int hi_j = (int)floorf((mx + R) * inv_bw);
   j0 = max(x0, lo_j);
   j1 = min(x1, hi_j + 1);
   if (j1 < j0) j1 = j0;
+}
+
+__device__ __forceinline__ void cull_row_range(const CullEllipse &e, float mx, float my, int i, int x0, int x1,
+                                               int block_width, int &j0, int &j1) {
+  cull_row_range(e, mx, my, i, x0, x1, block_width, 1.f / (float)block_width, j0, j1);
 }
 
 }  // namespace gsr
