@@ -33,6 +33,9 @@
 #ifndef GSR_TR_UNROLL
 #define GSR_TR_UNROLL 2  // visits per trip of the phase-1 walk
 #endif
+#ifndef GSR_TR_RING
+#define GSR_TR_RING 1  // buffers of the staged-record ring (see TrSmem)
+#endif
 #define GSR_PRAGMA_(x) _Pragma(#x)
 #define GSR_PRAGMA_UNROLL(n) GSR_PRAGMA_(unroll n)
 
@@ -42,13 +45,18 @@ namespace {
 
 constexpr int kRowStride = 33;  // float2 elements per matrix row (32 pixels + 1 pad)
 
+// Shared memory per CTA decides the L1 / shared-memory split of the SM, and the L1 size decides how many of the
+// scattered record gathers can be in flight: forcing the largest carveout (28 KB of L1) takes this kernel from 0.692 to
+// 0.759 ms and the forward from 0.369 to 0.428 ms (gpurun_out/r2_run52_*).  A SINGLE-buffered record ring (one more
+// barrier per batch; the next batch still waits in registers) brings the CTA from 63.6 to 51.3 KB, the carveout from
+// 196 to 164 KB, and the kernel to 0.677 ms.
 template <int G>
 struct TrSmem {
-  float4 rec[2][3][BLEND_THREADS];
+  float4 rec[GSR_TR_RING][3][BLEND_THREADS];
   float2 wf[BLEND_THREADS / 32][G * kRowStride];
   float4 vout[BLEND_THREADS / 32][32];
   unsigned char list[BLEND_THREADS / 32][BLEND_THREADS + 8];  // + 8: the pipelined phase 1 reads up to two entries ahead
-  alignas(8) unsigned char mask[2][BLEND_THREADS];  // MASKS: per staged record, the warp blocks it can reach (block_mask_16)
+  alignas(8) unsigned char mask[GSR_TR_RING][BLEND_THREADS];  // MASKS: per staged record, the warp blocks it can reach (block_mask_16)
   int warp_max[BLEND_THREADS / 32];
 };
 
@@ -212,7 +220,8 @@ __device__ __forceinline__ void blend_backward_tr_body(GSR_TR_PARAMS) {
   const int my_row = lane & (G - 1);
 
   for (int b = 0; b < num_batches; ++b) {
-    const int buf = b & 1;
+    const int buf = GSR_TR_RING == 2 ? (b & 1) : 0;
+    if (GSR_TR_RING == 1 && b > 0) __syncthreads();  // every warp is done with the previous batch
     const int batch_end = end - 1 - nthreads * b;  // sorted index held by slot 0; slot t holds batch_end - t
     if (batch_end - tr >= range.x) {
       S.rec[buf][0][tr] = rec.r0;
@@ -322,6 +331,13 @@ int launch_tr(dim3 grid, cudaStream_t st, int img_w, int img_h, const int *gauss
   static const cudaError_t attr = cudaFuncSetAttribute(blend_backward_tr_kernel<G, MIN_CTAS>,
                                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TrSmem<G>));
   GSR_CUDA(attr);
+  static const cudaError_t carve = [] {
+    const char *e = getenv("GSR_TR_CARVEOUT");  // percent of the maximum shared-memory carveout; unset = driver default
+    return (e && e[0]) ? cudaFuncSetAttribute(blend_backward_tr_kernel<G, MIN_CTAS>,
+                                              cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e))
+                       : cudaSuccess;
+  }();
+  GSR_CUDA(carve);
   blend_backward_tr_kernel<G, MIN_CTAS><<<grid, BLEND_THREADS, sizeof(TrSmem<G>), st>>>(
       (int)grid.x, img_w, img_h, gaussian_ids_sorted, tile_bins, xys, conics, colors, opacities, background, final_Ts,
       final_idx, v_output, v_output_alpha, v_xy, v_conic, v_colors, v_opacity);

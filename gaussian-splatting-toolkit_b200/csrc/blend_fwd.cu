@@ -26,6 +26,10 @@
 #define GSR_FWD_MIN_CTAS 4  // 64 registers; 5 CTAs / SM (48 registers, rematerialised pixel coordinates): 0.413 ms
 #endif
 
+#ifndef GSR_FWD_RING
+#define GSR_FWD_RING 2  // buffers of the staged-record ring
+#endif
+
 namespace gsr {
 
 // MASKS (16x16 tiles only): the staging thread evaluates its record against the eight warp blocks once (block_mask_16)
@@ -42,9 +46,9 @@ __device__ __forceinline__ void blend_forward_body(int tiles_x, int img_w, int i
                                                    float *__restrict__ final_Ts, int *__restrict__ final_idx) {
   // slot kNull of every plane holds a record that never contributes (opacity 0): the survivor lists are padded with it
   constexpr int kNull = BLEND_THREADS, kUnroll = GSR_FWD_UNROLL;
-  __shared__ float4 s_rec[2][3][BLEND_THREADS + 1];
+  __shared__ float4 s_rec[GSR_FWD_RING][3][BLEND_THREADS + 1];
   __shared__ unsigned short s_list[BLEND_THREADS / 32][BLEND_THREADS + kUnroll + 2];
-  __shared__ __align__(8) unsigned char s_mask[2][MASKS ? BLEND_THREADS : 8];
+  __shared__ __align__(8) unsigned char s_mask[GSR_FWD_RING][MASKS ? BLEND_THREADS : 8];
 
   const unsigned full = 0xffffffffu;
   const int tile_x = blockIdx.x, tile_y = blockIdx.y;
@@ -73,14 +77,16 @@ __device__ __forceinline__ void blend_forward_body(int tiles_x, int img_w, int i
   // a finished pixel has slot_stop = -1; contributors need slot < slot_stop (one ISETP instead of a flag round trip)
   int slot_stop = done ? -1 : 0x7fffffff;
 
-  if (tr < 6) s_rec[tr & 1][tr >> 1][kNull] = tr < 2 ? make_float4(0.f, 0.f, -1e30f, -1e30f) : make_float4(0.f, 0.f, 0.f, 0.f);
+  if (tr < 6 && (tr & 1) < GSR_FWD_RING)
+    s_rec[tr & 1][tr >> 1][kNull] = tr < 2 ? make_float4(0.f, 0.f, -1e30f, -1e30f) : make_float4(0.f, 0.f, 0.f, 0.f);
 
   BlendRecord rec;
   if (num_batches > 0 && range.x + tr < range.y)
     rec = gather_record(gaussian_ids_sorted[range.x + tr], xys, conics, colors, opacities);
 
   for (int b = 0; b < num_batches; ++b) {
-    const int buf = b & 1;
+    const int buf = GSR_FWD_RING == 2 ? (b & 1) : 0;
+    if (GSR_FWD_RING == 1 && b > 0) __syncthreads();  // every warp is done with the previous batch
     const int batch_start = range.x + nthreads * b;
     if (batch_start + tr < range.y) {
       s_rec[buf][0][tr] = rec.r0;
@@ -195,6 +201,12 @@ extern "C" GSR_API int gsr_rasterize_forward(unsigned img_height, unsigned img_w
               "rasterize_forward: xys / tile_bins must be 8-byte aligned");
   const dim3 grid(cdiv(img_width, block_width), cdiv(img_height, block_width), 1);
   const unsigned threads = cdiv(block_width * block_width, 32) * 32;
+  static const cudaError_t carve = [] {
+    const char *e = getenv("GSR_FWD_CARVEOUT");  // percent of the maximum shared-memory carveout; unset = driver default
+    return (e && e[0]) ? cudaFuncSetAttribute(blend_forward_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e))
+                       : cudaSuccess;
+  }();
+  GSR_CUDA(carve);
   if (block_width == 16 && blend_block_masks()) {
     blend_forward_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(
         (int)grid.x, (int)img_width, (int)img_height, (int)block_width, gaussian_ids_sorted,
