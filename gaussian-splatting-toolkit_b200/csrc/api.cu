@@ -1,7 +1,10 @@
 // api.cu — library identification + thread-local error reporting of the C ABI (include/gsr_b200.h).
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <atomic>
+
+#include <nvtx3/nvToolsExt.h>
 
 #include "common.cuh"
 
@@ -14,7 +17,25 @@ void set_error(const char *fmt, ...) {
   va_end(ap);
 }
 static std::atomic<unsigned long long> g_launches{0};
-void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+// GSR_NVTX=1: NVTX ranges over the entry points, one marker per kernel launch (header-only NVTX 3: no-ops unless a tool
+// is attached to the process)
+static bool nvtx_on() {
+  static const bool v = [] {
+    const char *e = getenv("GSR_NVTX");
+    return e && e[0] == '1';
+  }();
+  return v;
+}
+void count_launch(const char *kernel_name) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (kernel_name && nvtx_on()) nvtxMarkA(kernel_name);
+}
+TraceScope::TraceScope(const char *name) : on(nvtx_on()) {
+  if (on) nvtxRangePushA(name);
+}
+TraceScope::~TraceScope() {
+  if (on) nvtxRangePop();
+}
 }  // namespace gsr
 
 extern "C" {

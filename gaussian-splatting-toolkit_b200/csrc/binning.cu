@@ -117,6 +117,7 @@ GSR_API int gsr_cumsum_tiles_hit(int num_points, const int32_t *num_tiles_hit, i
                                  int32_t *total_host_pinned, void *workspace, size_t workspace_bytes,
                                  void *stream) {
   using namespace gsr;
+  GSR_TRACE_SCOPE("gsr_cumsum_tiles_hit");
   GSR_REQUIRE(num_points >= 0, GSR_ERR_INVALID_ARGUMENT, "cumsum_tiles_hit: num_points < 0");
   if (num_points == 0) {
     if (total_host_pinned) *total_host_pinned = 0;
@@ -142,6 +143,7 @@ GSR_API int gsr_map_gaussian_to_intersects(int num_points, int num_intersects, c
                                            unsigned block_width, int64_t *isect_ids, int32_t *gaussian_ids,
                                            void *stream) {
   using namespace gsr;
+  GSR_TRACE_SCOPE("gsr_map_gaussian_to_intersects");
   GSR_REQUIRE(num_points >= 0 && num_intersects >= 0, GSR_ERR_INVALID_ARGUMENT, "map_gaussian_to_intersects: negative size");
   GSR_REQUIRE(block_width > 1 && block_width <= 16, GSR_ERR_INVALID_ARGUMENT,
               "block_width must be between 2 and 16 (got %u)", block_width);
@@ -160,6 +162,7 @@ GSR_API int gsr_count_tiles_tight(int num_points, const float *xys, const int32_
                                   const float *opacities, unsigned img_height, unsigned img_width,
                                   unsigned block_width, int32_t *tiles_touched, void *stream) {
   using namespace gsr;
+  GSR_TRACE_SCOPE("gsr_count_tiles_tight");
   GSR_REQUIRE(num_points >= 0, GSR_ERR_INVALID_ARGUMENT, "count_tiles_tight: num_points < 0");
   GSR_REQUIRE(block_width > 1 && block_width <= 16, GSR_ERR_INVALID_ARGUMENT,
               "block_width must be between 2 and 16 (got %u)", block_width);
@@ -180,6 +183,7 @@ GSR_API int gsr_map_gaussian_to_intersects_tight(int num_points, int num_interse
                                                  unsigned img_height, unsigned img_width, unsigned block_width,
                                                  int64_t *isect_ids, int32_t *gaussian_ids, void *stream) {
   using namespace gsr;
+  GSR_TRACE_SCOPE("gsr_map_gaussian_to_intersects_tight");
   GSR_REQUIRE(num_points >= 0 && num_intersects >= 0, GSR_ERR_INVALID_ARGUMENT, "map_gaussian_to_intersects_tight: negative size");
   GSR_REQUIRE(block_width > 1 && block_width <= 16, GSR_ERR_INVALID_ARGUMENT,
               "block_width must be between 2 and 16 (got %u)", block_width);
@@ -206,6 +210,7 @@ GSR_API int gsr_sort_intersects(int num_intersects, int num_tiles, const int64_t
                                 int32_t *gaussian_ids_sorted, void *workspace, size_t workspace_bytes,
                                 void *stream) {
   using namespace gsr;
+  GSR_TRACE_SCOPE("gsr_sort_intersects");
   GSR_REQUIRE(num_intersects >= 0 && num_tiles > 0, GSR_ERR_INVALID_ARGUMENT, "sort_intersects: bad sizes");
   if (num_intersects == 0) return GSR_OK;
   GSR_REQUIRE(isect_ids && gaussian_ids && isect_ids_sorted && gaussian_ids_sorted && workspace,
@@ -233,6 +238,7 @@ GSR_API int gsr_sort_intersects(int num_intersects, int num_tiles, const int64_t
 GSR_API int gsr_get_tile_bin_edges(int num_intersects, const int64_t *isect_ids_sorted, int num_tiles,
                                    int32_t *tile_bins, void *stream) {
   using namespace gsr;
+  GSR_TRACE_SCOPE("gsr_get_tile_bin_edges");
   GSR_REQUIRE(num_intersects >= 0 && num_tiles >= 0, GSR_ERR_INVALID_ARGUMENT, "get_tile_bin_edges: negative size");
   if (num_tiles == 0) return GSR_OK;
   GSR_REQUIRE(tile_bins, GSR_ERR_INVALID_ARGUMENT, "get_tile_bin_edges: null pointer");

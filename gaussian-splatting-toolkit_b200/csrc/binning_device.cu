@@ -757,6 +757,7 @@ GSR_API int gsr_bin_gaussians_device(int num_points, const float *xys, const flo
                                      int32_t *gaussian_ids_sorted, int32_t *tile_bins, int32_t *meta,
                                      int32_t *meta_host_pinned, void *workspace, size_t workspace_bytes, void *stream) {
   using namespace gsr;
+  GSR_TRACE_SCOPE("gsr_bin_gaussians_device");
   GSR_REQUIRE(num_points >= 0 && capacity >= 0, GSR_ERR_INVALID_ARGUMENT, "bin_gaussians_device: negative size");
   GSR_REQUIRE(block_width > 1 && block_width <= 16, GSR_ERR_INVALID_ARGUMENT,
               "block_width must be between 2 and 16 (got %u)", block_width);
@@ -793,6 +794,7 @@ GSR_API int gsr_bin_count(int num_points, const float *xys, const int32_t *radii
                           int32_t *tile_bins, int32_t *meta, int32_t *meta_host_pinned, void *count_workspace,
                           size_t workspace_bytes, void *stream) {
   using namespace gsr;
+  GSR_TRACE_SCOPE("gsr_bin_count");
   GSR_REQUIRE(num_points >= 0, GSR_ERR_INVALID_ARGUMENT, "bin_count: num_points < 0");
   GSR_REQUIRE(block_width > 1 && block_width <= 16, GSR_ERR_INVALID_ARGUMENT,
               "block_width must be between 2 and 16 (got %u)", block_width);
@@ -825,6 +827,7 @@ GSR_API int gsr_bin_fill_sort(int num_points, int num_intersects, const float *x
                               void *count_workspace, int32_t *gaussian_ids_sorted, void *fill_workspace,
                               size_t fill_workspace_bytes, void *stream) {
   using namespace gsr;
+  GSR_TRACE_SCOPE("gsr_bin_fill_sort");
   GSR_REQUIRE(num_points >= 0 && num_intersects >= 0, GSR_ERR_INVALID_ARGUMENT, "bin_fill_sort: negative size");
   GSR_REQUIRE(block_width > 1 && block_width <= 16, GSR_ERR_INVALID_ARGUMENT,
               "block_width must be between 2 and 16 (got %u)", block_width);

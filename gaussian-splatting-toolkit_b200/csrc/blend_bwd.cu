@@ -231,6 +231,7 @@ extern "C" GSR_API int gsr_rasterize_backward(unsigned img_height, unsigned img_
                                               const float *v_output_alpha, float *v_xy, float *v_conic,
                                               float *v_colors, float *v_opacity, void *stream) {
   using namespace gsr;
+  GSR_TRACE_SCOPE("gsr_rasterize_backward");
   GSR_REQUIRE(block_width > 1 && block_width <= 16, GSR_ERR_INVALID_ARGUMENT,
               "block_width must be between 2 and 16 (got %u)", block_width);
   GSR_REQUIRE(img_height > 0 && img_width > 0 && num_points >= 0, GSR_ERR_INVALID_ARGUMENT, "rasterize_backward: bad sizes");

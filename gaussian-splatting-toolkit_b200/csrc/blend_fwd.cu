@@ -190,6 +190,7 @@ extern "C" GSR_API int gsr_rasterize_forward(unsigned img_height, unsigned img_w
                                              const float *background, float *out_img, float *final_Ts,
                                              int32_t *final_idx, void *stream) {
   using namespace gsr;
+  GSR_TRACE_SCOPE("gsr_rasterize_forward");
   (void)num_points;
   GSR_REQUIRE(block_width > 1 && block_width <= 16, GSR_ERR_INVALID_ARGUMENT,
               "block_width must be between 2 and 16 (got %u)", block_width);

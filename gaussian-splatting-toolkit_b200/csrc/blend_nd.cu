@@ -196,6 +196,7 @@ GSR_API int gsr_nd_rasterize_forward(unsigned img_height, unsigned img_width, un
                                      const float *colors, const float *opacities, const float *background,
                                      float *out_img, float *final_Ts, int32_t *final_idx, void *stream) {
   using namespace gsr;
+  GSR_TRACE_SCOPE("gsr_nd_rasterize_forward");
   (void)num_points;
   GSR_REQUIRE(block_width > 1 && block_width <= 16, GSR_ERR_INVALID_ARGUMENT,
               "block_width must be between 2 and 16 (got %u)", block_width);
@@ -224,6 +225,7 @@ GSR_API int gsr_nd_rasterize_backward(unsigned img_height, unsigned img_width, u
                                       const float *v_output_alpha, float *v_xy, float *v_conic,
                                       float *v_colors, float *v_opacity, void *stream) {
   using namespace gsr;
+  GSR_TRACE_SCOPE("gsr_nd_rasterize_backward");
   GSR_REQUIRE(block_width > 1 && block_width <= 16, GSR_ERR_INVALID_ARGUMENT,
               "block_width must be between 2 and 16 (got %u)", block_width);
   GSR_REQUIRE(channels >= 1 && channels <= GSR_MAX_CHANNELS, GSR_ERR_UNSUPPORTED,

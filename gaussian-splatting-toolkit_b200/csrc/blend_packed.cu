@@ -347,6 +347,7 @@ GSR_API int gsr_blend_packed_forward(unsigned img_height, unsigned img_width, un
                                      const float *records, const float *background, float *out_img,
                                      float *out_depth /*nullable*/, float *final_Ts, int32_t *final_idx, void *stream) {
   using namespace gsr;
+  GSR_TRACE_SCOPE("gsr_blend_packed_forward");
   GSR_REQUIRE(block_width > 1 && block_width <= 16, GSR_ERR_INVALID_ARGUMENT,
               "block_width must be between 2 and 16 (got %u)", block_width);
   GSR_REQUIRE(img_height > 0 && img_width > 0 && num_points >= 0, GSR_ERR_INVALID_ARGUMENT, "blend_packed_forward: bad sizes");
@@ -378,6 +379,7 @@ GSR_API int gsr_blend_packed_backward(unsigned img_height, unsigned img_width, u
                                       const float *v_output_depth /*nullable*/, const float *v_output_alpha,
                                       float *grad_records, void *stream) {
   using namespace gsr;
+  GSR_TRACE_SCOPE("gsr_blend_packed_backward");
   GSR_REQUIRE(block_width > 1 && block_width <= 16, GSR_ERR_INVALID_ARGUMENT,
               "block_width must be between 2 and 16 (got %u)", block_width);
   GSR_REQUIRE(img_height > 0 && img_width > 0 && num_points >= 0, GSR_ERR_INVALID_ARGUMENT, "blend_packed_backward: bad sizes");

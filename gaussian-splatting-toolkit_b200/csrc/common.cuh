@@ -19,8 +19,17 @@ inline float tan_half_fov(unsigned img_size, float focal) { return (float)(0.5 *
 
 // thread-local error message (api.cu)
 void set_error(const char *fmt, ...);
-// process-wide count of own kernel launches (api.cu; read with gsr_launch_count())
-void count_launch();
+// process-wide count of own kernel launches (api.cu; read with gsr_launch_count()); with GSR_NVTX=1 every launch also
+// leaves an NVTX marker carrying the kernel's name
+void count_launch(const char *kernel_name = nullptr);
+// NVTX range over a C-ABI entry point (api.cu; active only with GSR_NVTX=1 — one relaxed load otherwise): the ranges and
+// markers show up in `ncu --nvtx` / Nsight Systems captures of a process that uses the library
+struct TraceScope {
+  explicit TraceScope(const char *name);
+  ~TraceScope();
+  bool on;
+};
+#define GSR_TRACE_SCOPE(name) gsr::TraceScope _gsr_trace_scope(name)
 
 #define GSR_REQUIRE(cond, code, ...)  \
   do {                                \
@@ -46,7 +55,7 @@ void count_launch();
       gsr::set_error("launch of %s failed: %s", name, cudaGetErrorString(_e));          \
       return GSR_ERR_CUDA;                                                              \
     }                                                                                   \
-    gsr::count_launch();                                                                \
+    gsr::count_launch(name);                                                            \
   } while (0)
 
 static inline unsigned cdiv(unsigned a, unsigned b) { return (a + b - 1) / b; }

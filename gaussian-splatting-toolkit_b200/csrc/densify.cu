@@ -256,6 +256,7 @@ GSR_API int gsr_densify_stats_update(int num_points, const float *xys_grad, int 
                                      float max_dim, int first, float *xys_grad_norm, float *vis_counts,
                                      float *max_2Dsize, void *stream) {
   using namespace gsr;
+  GSR_TRACE_SCOPE("gsr_densify_stats_update");
   GSR_REQUIRE(num_points >= 0 && xys_grad_stride >= 2 && max_dim > 0.f, GSR_ERR_INVALID_ARGUMENT,
               "densify_stats_update: bad sizes (N=%d, stride=%d, max_dim=%g)", num_points, xys_grad_stride, max_dim);
   if (num_points == 0) return GSR_OK;
@@ -283,6 +284,7 @@ GSR_API int gsr_densify_plan(int num_points, const float *scales_raw, const floa
                              float cull_scale_thresh, int use_cull_screen, float cull_screen_size, uint8_t *flags,
                              int32_t *ranks, int32_t *counts, void *workspace, size_t workspace_bytes, void *stream) {
   using namespace gsr;
+  GSR_TRACE_SCOPE("gsr_densify_plan");
   GSR_REQUIRE(num_points >= 1, GSR_ERR_INVALID_ARGUMENT, "densify_plan: num_points must be >= 1 (got %d)", num_points);
   GSR_REQUIRE(scales_raw && opacities_raw && flags && ranks && counts && workspace, GSR_ERR_INVALID_ARGUMENT,
               "densify_plan: null pointer");
@@ -326,6 +328,7 @@ GSR_API int gsr_densify_apply(int num_points, int n_split_samples, const int32_t
                               float *const *dst_host, const int32_t *widths_host, const int32_t *kinds_host,
                               uint32_t *map, void *stream) {
   using namespace gsr;
+  GSR_TRACE_SCOPE("gsr_densify_apply");
   GSR_REQUIRE(num_points >= 1 && n_split_samples >= 1, GSR_ERR_INVALID_ARGUMENT, "densify_apply: bad sizes");
   GSR_REQUIRE(counts_host && flags && ranks && src_host && dst_host && widths_host && kinds_host,
               GSR_ERR_INVALID_ARGUMENT, "densify_apply: null pointer");

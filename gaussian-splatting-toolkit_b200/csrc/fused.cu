@@ -268,6 +268,7 @@ GSR_API int gsr_fused_preprocess_forward(int num_points, int sh_degree, int degr
                                          float *conics, float *opacities, int32_t *clamp_mask,
                                          float *compensation /*nullable*/, void *stream) {
   using namespace gsr;
+  GSR_TRACE_SCOPE("gsr_fused_preprocess_forward");
   GSR_REQUIRE(num_points >= 0, GSR_ERR_INVALID_ARGUMENT, "fused_preprocess_forward: num_points < 0");
   GSR_REQUIRE(sh_degree >= 0 && sh_degree <= 4, GSR_ERR_UNSUPPORTED, "fused_preprocess_forward: sh_degree %d not in [0,4]", sh_degree);
   GSR_REQUIRE(degrees_to_use >= 0 && degrees_to_use <= sh_degree, GSR_ERR_INVALID_ARGUMENT,
@@ -305,6 +306,7 @@ GSR_API int gsr_fused_preprocess_backward(int num_points, int sh_degree, int deg
                                           float *v_quats_raw, float *v_opacities_raw, float *v_features_dc,
                                           float *v_features_rest, void *stream) {
   using namespace gsr;
+  GSR_TRACE_SCOPE("gsr_fused_preprocess_backward");
   GSR_REQUIRE(num_points >= 0, GSR_ERR_INVALID_ARGUMENT, "fused_preprocess_backward: num_points < 0");
   GSR_REQUIRE(sh_degree >= 0 && sh_degree <= 4, GSR_ERR_UNSUPPORTED, "fused_preprocess_backward: sh_degree %d not in [0,4]", sh_degree);
   GSR_REQUIRE(degrees_to_use >= 0 && degrees_to_use <= sh_degree, GSR_ERR_INVALID_ARGUMENT,

@@ -293,6 +293,7 @@ extern "C" {
 
 GSR_API int gsr_l1_ssim_num_partials(unsigned img_height, unsigned img_width) {
   using namespace gsr;
+  GSR_TRACE_SCOPE("gsr_l1_ssim_num_partials");
   if (img_height < (unsigned)LW || img_width < (unsigned)LW) return 0;
   return (int)(cdiv(img_width - (LW - 1), LT) * cdiv(img_height - (LW - 1), LT));
 }
@@ -300,6 +301,7 @@ GSR_API int gsr_l1_ssim_num_partials(unsigned img_height, unsigned img_width) {
 GSR_API int gsr_l1_ssim_forward(unsigned img_height, unsigned img_width, float ssim_lambda, const float *pred,
                                 const float *gt, float *maps, float *partials, float *loss_l1_ssim, void *stream) {
   using namespace gsr;
+  GSR_TRACE_SCOPE("gsr_l1_ssim_forward");
   GSR_REQUIRE(img_height >= (unsigned)LW && img_width >= (unsigned)LW, GSR_ERR_INVALID_ARGUMENT,
               "l1_ssim_forward: image must be at least 11 x 11 (got %u x %u)", img_height, img_width);
   GSR_REQUIRE(pred && gt && maps && partials && loss_l1_ssim, GSR_ERR_INVALID_ARGUMENT, "l1_ssim_forward: null pointer");
@@ -319,6 +321,7 @@ GSR_API int gsr_l1_ssim_backward(unsigned img_height, unsigned img_width, float 
                                  const float *gt, const float *maps, const float *v_loss /*nullable: 1.0*/,
                                  float *v_pred, void *stream) {
   using namespace gsr;
+  GSR_TRACE_SCOPE("gsr_l1_ssim_backward");
   GSR_REQUIRE(img_height >= (unsigned)LW && img_width >= (unsigned)LW, GSR_ERR_INVALID_ARGUMENT,
               "l1_ssim_backward: image must be at least 11 x 11 (got %u x %u)", img_height, img_width);
   GSR_REQUIRE(pred && gt && maps && v_pred, GSR_ERR_INVALID_ARGUMENT, "l1_ssim_backward: null pointer");

@@ -110,6 +110,7 @@ GSR_API int gsr_adam_step_multi(int num_segments, float *const *params_host, con
                                 const int64_t *numels_host, const double *lrs_host, const int64_t *steps_host,
                                 double beta1, double beta2, double eps, float grad_scale, void *stream) {
   using namespace gsr;
+  GSR_TRACE_SCOPE("gsr_adam_step_multi");
   GSR_REQUIRE(num_segments >= 1 && num_segments <= GSR_ADAM_MAX_SEGMENTS, GSR_ERR_INVALID_ARGUMENT,
               "adam_step_multi: num_segments must be in [1,%d] (got %d)", GSR_ADAM_MAX_SEGMENTS, num_segments);
   GSR_REQUIRE(params_host && grads_host && exp_avg_host && exp_avg_sq_host && numels_host && lrs_host && steps_host,
@@ -160,6 +161,7 @@ GSR_API int gsr_adam_step_multi(int num_segments, float *const *params_host, con
 GSR_API int gsr_opacity_reset(int num_points, float max_logit, float *opacities_raw, float *exp_avg /*nullable*/,
                               float *exp_avg_sq /*nullable*/, void *stream) {
   using namespace gsr;
+  GSR_TRACE_SCOPE("gsr_opacity_reset");
   GSR_REQUIRE(num_points >= 0, GSR_ERR_INVALID_ARGUMENT, "opacity_reset: negative num_points");
   if (num_points == 0) return GSR_OK;
   GSR_REQUIRE(opacities_raw, GSR_ERR_INVALID_ARGUMENT, "opacity_reset: null pointer");

@@ -165,6 +165,7 @@ extern "C" {
 
 GSR_API int gsr_peer_reduce_scatter(int world, int rank, float *const *bufs_host, long long num_floats, void *stream) {
   using namespace gsr;
+  GSR_TRACE_SCOPE("gsr_peer_reduce_scatter");
   PeerBufs b;
   const int rc = fill_bufs(b, world, rank, bufs_host, "peer_reduce_scatter");
   if (rc != GSR_OK) return rc;
@@ -183,6 +184,7 @@ GSR_API int gsr_peer_reduce_scatter(int world, int rank, float *const *bufs_host
 
 GSR_API int gsr_peer_all_gather(int world, int rank, float *const *bufs_host, long long num_floats, void *stream) {
   using namespace gsr;
+  GSR_TRACE_SCOPE("gsr_peer_all_gather");
   PeerBufs b;
   const int rc = fill_bufs(b, world, rank, bufs_host, "peer_all_gather");
   if (rc != GSR_OK) return rc;
@@ -198,6 +200,7 @@ GSR_API int gsr_peer_all_gather(int world, int rank, float *const *bufs_host, lo
 GSR_API int gsr_peer_push(int world, float *const *dsts_host, const float *src, long long src_stride, long long n_per_dst,
                           long long n_total, void *stream) {
   using namespace gsr;
+  GSR_TRACE_SCOPE("gsr_peer_push");
   PeerBufs b;
   const int rc = fill_bufs(b, world, 0, dsts_host, "peer_push");
   if (rc != GSR_OK) return rc;
@@ -213,6 +216,7 @@ GSR_API int gsr_peer_push(int world, float *const *dsts_host, const float *src, 
 GSR_API int gsr_peer_reduce_broadcast(int world, float *const *dsts_host, const float *slots, long long slot_stride,
                                       long long num_floats, void *stream) {
   using namespace gsr;
+  GSR_TRACE_SCOPE("gsr_peer_reduce_broadcast");
   PeerBufs b;
   const int rc = fill_bufs(b, world, 0, dsts_host, "peer_reduce_broadcast");
   if (rc != GSR_OK) return rc;

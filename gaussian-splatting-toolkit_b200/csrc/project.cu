@@ -310,6 +310,7 @@ GSR_API int gsr_project_gaussians_forward(int num_points, const float *means3d, 
                                           int32_t *radii, float *conics, float *compensation,
                                           int32_t *num_tiles_hit, void *stream) {
   using namespace gsr;
+  GSR_TRACE_SCOPE("gsr_project_gaussians_forward");
   GSR_REQUIRE(num_points >= 0, GSR_ERR_INVALID_ARGUMENT, "project_gaussians_forward: num_points < 0");
   GSR_REQUIRE(block_width > 1 && block_width <= 16, GSR_ERR_INVALID_ARGUMENT,
               "block_width must be between 2 and 16 (got %u)", block_width);
@@ -338,6 +339,7 @@ GSR_API int gsr_project_gaussians_backward(int num_points, const float *means3d,
                                            const float *v_compensation, float *v_cov2d, float *v_cov3d,
                                            float *v_mean3d, float *v_scale, float *v_quat, void *stream) {
   using namespace gsr;
+  GSR_TRACE_SCOPE("gsr_project_gaussians_backward");
   (void)cx;
   (void)cy;
   GSR_REQUIRE(num_points >= 0, GSR_ERR_INVALID_ARGUMENT, "project_gaussians_backward: num_points < 0");
@@ -357,6 +359,7 @@ GSR_API int gsr_project_gaussians_backward(int num_points, const float *means3d,
 
 GSR_API int gsr_compute_cov2d_bounds(int num_pts, const float *covs2d, float *conics, float *radii, void *stream) {
   using namespace gsr;
+  GSR_TRACE_SCOPE("gsr_compute_cov2d_bounds");
   GSR_REQUIRE(num_pts >= 0, GSR_ERR_INVALID_ARGUMENT, "compute_cov2d_bounds: num_pts < 0");
   if (num_pts == 0) return GSR_OK;
   GSR_REQUIRE(covs2d && conics && radii, GSR_ERR_INVALID_ARGUMENT, "compute_cov2d_bounds: null pointer");

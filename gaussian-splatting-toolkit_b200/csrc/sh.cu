@@ -464,6 +464,7 @@ GSR_API int gsr_compute_sh_backward_multiview(int num_points, int degree, int de
                                               const float *means3d, const float *cam_positions,
                                               const float *const *v_colors_views_host, float *v_coeffs,
                                               void *stream) {
+  gsr::TraceScope _gsr_trace_scope("gsr_compute_sh_backward_multiview");
   // contiguous camera array -> pointer table
   if (num_views < 1 || num_views > gsr::SH_MAX_VIEWS || cam_positions == nullptr) {
     gsr::set_error("compute_sh_backward_multiview: num_views %d not in [1,%d] or null cam_positions", num_views,
@@ -481,6 +482,7 @@ GSR_API int gsr_compute_sh_backward_multiview_ptrs(int num_points, int degree, i
                                                    const float *const *v_colors_views_host, float *v_coeffs,
                                                    void *stream) {
   using namespace gsr;
+  GSR_TRACE_SCOPE("gsr_compute_sh_backward_multiview_ptrs");
   const float *const *cam_positions = cam_views_host;
   GSR_REQUIRE(num_points >= 0, GSR_ERR_INVALID_ARGUMENT, "compute_sh_backward_multiview: num_points < 0");
   GSR_REQUIRE(degree >= 0 && degree <= 4, GSR_ERR_UNSUPPORTED, "compute_sh_backward_multiview: degree %d not in [0,4]", degree);
@@ -521,6 +523,7 @@ GSR_API int gsr_compute_sh_backward_multiview_ptrs(int num_points, int degree, i
 GSR_API int gsr_compute_sh_forward(int num_points, int degree, int degrees_to_use, const float *viewdirs,
                                    const float *coeffs, float *colors, void *stream) {
   using namespace gsr;
+  GSR_TRACE_SCOPE("gsr_compute_sh_forward");
   GSR_REQUIRE(num_points >= 0, GSR_ERR_INVALID_ARGUMENT, "compute_sh_forward: num_points < 0");
   GSR_REQUIRE(degree >= 0 && degree <= 4, GSR_ERR_UNSUPPORTED, "compute_sh_forward: degree %d not in [0,4]", degree);
   GSR_REQUIRE(degrees_to_use >= 0 && degrees_to_use <= degree, GSR_ERR_INVALID_ARGUMENT,
@@ -554,6 +557,7 @@ GSR_API int gsr_compute_sh_forward(int num_points, int degree, int degrees_to_us
 GSR_API int gsr_compute_sh_backward(int num_points, int degree, int degrees_to_use, const float *viewdirs,
                                     const float *v_colors, float *v_coeffs, void *stream) {
   using namespace gsr;
+  GSR_TRACE_SCOPE("gsr_compute_sh_backward");
   GSR_REQUIRE(num_points >= 0, GSR_ERR_INVALID_ARGUMENT, "compute_sh_backward: num_points < 0");
   GSR_REQUIRE(degree >= 0 && degree <= 4, GSR_ERR_UNSUPPORTED, "compute_sh_backward: degree %d not in [0,4]", degree);
   GSR_REQUIRE(degrees_to_use >= 0 && degrees_to_use <= degree, GSR_ERR_INVALID_ARGUMENT,

@@ -143,3 +143,22 @@ def test_tile_mask_division_magic_is_exact():
         for magic in {int(x * (1 - 2.0 ** -20)) + 1, int(x) + 1, int(x * (1 + 2.0 ** -20)) + 1}:
             for k in range(64):
                 assert (k * magic) >> 16 == k // d, (d, magic, k)
+
+
+def test_nvtx_tracing_switch_is_harmless_without_a_tool():
+    """GSR_NVTX=1 wraps every C-ABI entry point in an NVTX range and marks every kernel launch (csrc/api.cu); without a
+    profiler attached the NVTX 3 calls are no-ops.  Runs in its own interpreter: the switch is read once per process."""
+    import subprocess
+    import sys
+
+    code = (
+        "import sys, os\n"
+        f"sys.path.insert(0, os.path.join({ROOT!r}, 'gaussian-splatting-toolkit_b200'))\n"
+        "from rasterizer import _lib\n"
+        "lib = _lib.load()\n"
+        "rc = lib.gsr_rasterize_forward(8, 8, 1, 0, None, None, None, None, None, None, None, None, None, None, None)\n"
+        "assert rc != 0 and b'block_width' in lib.gsr_last_error(), (rc, lib.gsr_last_error())\n"
+        "print('ok')\n"
+    )
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, GSR_NVTX="1"), capture_output=True, text=True)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr
