@@ -9,8 +9,8 @@
   * `transforms.json`  the reference's own dataset format (data/dataparsers/gs_toolkit_dataparser.py:77-457): frames
     sorted by file name, intrinsics global or per frame, train / eval split by fraction (dataparsers_utils.py:10-32) or
     by explicit `<split>_filenames`, poses oriented ("up") and centred ("poses") as camera_utils.py:552-668 does by
-    default, optional auto-scale; images are NOT decoded here (no image library in this image) — file names are
-    returned;
+    default, optional auto-scale; the file names are returned and `load_image` / `load_depth_image` decode them the
+    way the reference's dataset does (data/datasets/base_dataset.py:48-118; needs Pillow, like the reference);
   * `camera_to_view_proj`  camera-to-world (OpenGL axes) -> the (viewmat, projmat, fovs) the operators take, i.e. the
     per-view prologue of `get_outputs` (vanilla_gs.py:722-741, utils/comms.py:103-123).
 """
@@ -28,6 +28,53 @@ from .synthetic import projection_matrix
 
 GROUPS = ("means", "scales", "quats", "features_dc", "features_rest", "opacities")
 _PREFIX = "_model.gauss_params."
+
+
+# ------------------------------------------------------------------------------------------------- images
+def load_image_uint8(filename: str, scale_factor: float = 1.0) -> np.ndarray:
+    """InputDataset.get_numpy_image (base_dataset.py:48-66): uint8 [H,W,3 or 4]; bilinear resize by `scale_factor`
+    (new size truncated to int, as the reference does), grey images repeated to three channels."""
+    from PIL import Image  # the reference's own dependency; imported here so that the package loads without it
+
+    pil_image = Image.open(filename)
+    if scale_factor != 1.0:
+        width, height = pil_image.size
+        pil_image = pil_image.resize((int(width * scale_factor), int(height * scale_factor)), resample=Image.BILINEAR)
+    image = np.array(pil_image, dtype="uint8")
+    if image.ndim == 2:
+        image = image[:, :, None].repeat(3, axis=2)
+    if image.ndim != 3 or image.shape[2] not in (3, 4):
+        raise ValueError(f"Image shape of {image.shape} is in correct.")
+    return image
+
+
+def load_image(filename: str, scale_factor: float = 1.0, alpha_color: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """InputDataset.get_image (base_dataset.py:68-87): float32 [H,W,3 or 4] in [0,1]; an RGBA image is composited over
+    `alpha_color` (rgb * a + alpha_color * (1 - a)) when one is given, otherwise its four channels are returned."""
+    image = torch.from_numpy(load_image_uint8(filename, scale_factor).astype("float32") / 255.0)
+    if alpha_color is not None and image.shape[-1] == 4:
+        image = image[:, :, :3] * image[:, :, -1:] + torch.as_tensor(alpha_color, dtype=torch.float32) * (1.0 - image[:, :, -1:])
+    return image
+
+
+def load_depth_image(filename: str, scale_factor: float = 1.0, mono_depth: bool = False) -> torch.Tensor:
+    """InputDataset.get_numpy_depth_image / get_depth_image (base_dataset.py:89-131): `.png` / `.jpg` / `.jpeg` through
+    Pillow (bilinear resize by `scale_factor`) or `.npy`; monocular depth maps are stored as 8-bit (/ 255), metric depth
+    in millimetres (/ 1000)."""
+    ext = os.path.splitext(filename)[1]
+    if ext in (".png", ".jpg", ".jpeg"):
+        from PIL import Image
+
+        pil_image = Image.open(filename)
+        if scale_factor != 1.0:
+            width, height = pil_image.size
+            pil_image = pil_image.resize((int(width * scale_factor), int(height * scale_factor)), resample=Image.BILINEAR)
+        depth = np.array(pil_image)
+    elif ext == ".npy":
+        depth = np.load(filename)
+    else:
+        raise ValueError(f"Depth file format {ext} not supported.")
+    return torch.from_numpy(depth.astype("float32") / (255.0 if mono_depth else 1000.0))
 
 
 # ------------------------------------------------------------------------------------------------- checkpoints
@@ -284,3 +331,25 @@ def load_transforms(data: str, split: str = "train", train_split_fraction: float
             "fx": fx[idx] / d, "fy": fy[idx] / d, "cx": cx[idx] / d, "cy": cy[idx] / d,
             "height": (height[idx] // downscale_factor).astype(np.int32), "width": (width[idx] // downscale_factor).astype(np.int32),
             "transform": transform, "scale_factor": s, "indices": idx}
+
+
+def load_views(data: str, split: str = "train", image_scale_factor: float = 1.0, alpha_color=None, load_images: bool = True,
+               **dataparser_kwargs) -> List[Dict[str, object]]:
+    """A whole dataset split ready for the operators: `load_transforms` + per view the (viewmat, projmat, camera position)
+    of `camera_to_view_proj`, the intrinsics rescaled like `Cameras.rescale_output_resolution` does for a dataset scale
+    factor (cameras.py: fx, fy, cx, cy multiplied, height / width truncated to int), and — unless `load_images=False` —
+    the decoded image of `load_image` ([H,W,3] float32 in [0,1] when `alpha_color` is given or the file has no alpha).
+    This is what `InputDataset.get_data` + the model's per-view prologue hand to `get_outputs` / `get_loss_dict`."""
+    t = load_transforms(data, split=split, **dataparser_kwargs)
+    views = []
+    for i, name in enumerate(t["image_filenames"]):
+        s = float(image_scale_factor)
+        fx, fy, cx, cy = (float(t[k][i]) * s for k in ("fx", "fy", "cx", "cy"))
+        height, width = int(int(t["height"][i]) * s), int(int(t["width"][i]) * s)
+        viewmat, projmat, cam_pos = camera_to_view_proj(t["camera_to_worlds"][i], fx, fy, width, height)
+        v = {"image_filename": name, "index": int(t["indices"][i]), "fx": fx, "fy": fy, "cx": cx, "cy": cy,
+             "height": height, "width": width, "viewmat": viewmat, "projmat": projmat, "cam_pos": cam_pos}
+        if load_images:
+            v["image"] = load_image(name, image_scale_factor, alpha_color)
+        views.append(v)
+    return views

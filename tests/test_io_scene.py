@@ -169,3 +169,65 @@ def test_orientation_and_centring_methods_vs_reference_camera_utils():
                 # the sign of the mean up direction afterwards, so the results must agree outright
                 assert np.abs(t - rt).max() < 2e-5, (name, method, center, np.abs(t - rt).max())
                 assert np.abs(o - ro).max() < 5e-5, (name, method, center, np.abs(o - ro).max())
+
+
+def test_image_decoding_vs_reference_dataset(tmp_path):
+    """load_image_uint8 / load_image against what the reference's InputDataset.get_numpy_image / get_image make of the same
+    PNG files (tests/golden/images/*.png, fixtures of gen_golden_images.py): RGB, RGBA and grey, scale factors 1 and 0.5,
+    no alpha colour / white / an arbitrary one.  Bit-exact: same Pillow calls, same float32 arithmetic."""
+    pytest.importorskip("PIL")
+    import torch
+    from rasterizer.io_scene import load_depth_image, load_image, load_image_uint8
+
+    z = np.load(os.path.join(GOLD, "io_images_ref.npz"))
+    names = [str(n) for n in z["names"]]
+    colors = {"none": None, "1.0_1.0_1.0": torch.tensor([1.0, 1.0, 1.0]), "0.2_0.5_0.9": torch.tensor([0.2, 0.5, 0.9])}
+    checked = 0
+    for scale in (1.0, 0.5):
+        for ctag, color in colors.items():
+            for n in names:
+                path = os.path.join(GOLD, "images", n)
+                assert np.array_equal(load_image_uint8(path, scale), z[f"s{scale}_a{ctag}_{n}_u8"]), (scale, ctag, n)
+                got = load_image(path, scale, color).numpy()
+                ref = z[f"s{scale}_a{ctag}_{n}_f32"]
+                assert got.shape == ref.shape and got.dtype == np.float32 and np.array_equal(got, ref), (scale, ctag, n)
+                checked += 1
+    assert checked == 18
+    # depth maps: 16-bit PNG in millimetres, 8-bit monocular, .npy
+    from PIL import Image
+
+    d16 = (np.arange(6 * 8, dtype=np.uint16).reshape(6, 8) * 531).astype(np.uint16)
+    Image.fromarray(d16).save(str(tmp_path / "d.png"))
+    assert np.array_equal(load_depth_image(str(tmp_path / "d.png")).numpy(), d16.astype("float32") / 1000.0)
+    np.save(str(tmp_path / "d.npy"), d16)
+    assert np.array_equal(load_depth_image(str(tmp_path / "d.npy"), mono_depth=True).numpy(), d16.astype("float32") / 255.0)
+    with pytest.raises(ValueError):
+        load_depth_image(str(tmp_path / "d.exr"))
+
+
+def test_load_views_from_a_dataset_directory(tmp_path):
+    """transforms.json + image files on disk -> per-view cameras and decoded images (the inputs of a training view)."""
+    pytest.importorskip("PIL")
+    import json
+    import shutil
+
+    from rasterizer.io_scene import camera_to_view_proj, load_transforms, load_views
+
+    meta = json.load(open(os.path.join(GOLD, "io_transforms.json")))
+    meta["w"], meta["h"], meta["cx"], meta["cy"] = 14, 10, 7.0, 5.0
+    os.makedirs(tmp_path / "images")
+    for k, fr in enumerate(meta["frames"]):
+        shutil.copy(os.path.join(GOLD, "images", ("rgb.png", "rgba.png", "grey.png")[k % 3]), tmp_path / fr["file_path"])
+    json.dump(meta, open(tmp_path / "transforms.json", "w"))
+    t = load_transforms(str(tmp_path), split="train")
+    views = load_views(str(tmp_path), split="train", alpha_color=torch.tensor([1.0, 1.0, 1.0]))
+    assert len(views) == len(t["image_filenames"]) > 0
+    for i, v in enumerate(views):
+        assert v["image"].shape == (10, 14, 3) and v["image"].dtype == torch.float32
+        assert 0.0 <= float(v["image"].min()) and float(v["image"].max()) <= 1.0
+        vm, pm, pos = camera_to_view_proj(t["camera_to_worlds"][i], float(t["fx"][i]), float(t["fy"][i]), 14, 10)
+        assert np.array_equal(v["viewmat"], vm) and np.array_equal(v["projmat"], pm) and np.array_equal(v["cam_pos"], pos)
+    half = load_views(str(tmp_path), split="val", image_scale_factor=0.5, alpha_color=torch.tensor([0.0, 0.0, 0.0]))
+    assert half[0]["image"].shape == (5, 7, 3) and half[0]["height"] == 5 and half[0]["width"] == 7
+    assert half[0]["fx"] == pytest.approx(0.5 * float(load_transforms(str(tmp_path), split="val")["fx"][0]))
+    assert "image" not in load_views(str(tmp_path), load_images=False)[0]
