@@ -23,11 +23,11 @@ struct BlendRecord {
 // |dx| > ext_x = sqrt(2 ln(255 o) Sigma_xx) implies sigma >= dx^2 / (2 Sigma_xx) > ln(255 o)  (marginal bound of
 // the Mahalanobis form), likewise in y.  NaN (never rejects) when the conic is not positive definite; negative
 // (always rejects) when opacity < 1/255.  0.1 % + 0.01 px safety margin against rounding.
-__device__ __forceinline__ void alpha_extents(float a, float b, float c, float opac, float &ex, float &ey) {
+GSR_HD void alpha_extents(float a, float b, float c, float opac, float &ex, float &ey) {
   const float det = a * c - b * b;  // det(conic) = 1 / det(cov2d)
-  const float tau2 = 2.f * __logf(255.f * opac);
+  const float tau2 = 2.f * gsr_logf(255.f * opac);
   if (!(tau2 >= 0.f)) {
-    ex = (opac == opac) ? -1e30f : __int_as_float(0x7fc00000);
+    ex = (opac == opac) ? -1e30f : gsr_int_as_float(0x7fc00000);
     ey = ex;
     return;
   }
@@ -134,12 +134,12 @@ __device__ __forceinline__ int compact_survivors(const float4 *__restrict__ rec0
 // over the block's x segment against -log2(255 o); anything not provably below the threshold is kept (NaNs, A >= 0).
 // Written with margins (>= 0 keeps) combined by min and read off the sign bit: the predicate form of the same logic
 // compiles to ~130 instructions of predicate spilling (P2R / LOP3) on top of the ~300 of arithmetic.
-__device__ __forceinline__ unsigned block_mask_16(const float4 c, const float4 q, float tile_x0, float tile_y0) {
+GSR_HD unsigned block_mask_16(const float4 c, const float4 q, float tile_x0, float tile_y0) {
   // NaN anywhere (non-positive-definite conic, NaN opacity) or inf - inf: keep every block (fmin / fmax drop NaNs)
   const float probe = (c.x + c.y) + (c.z + c.w) + (q.x + q.y) + (q.z + q.w);
   const bool weird = !(probe == probe);
   const bool any_shape = !(q.x < 0.f);  // not concave in dx: only the box test applies
-  const float thr = -1.001f * __log2f(255.f * q.w) - 0.01f;
+  const float thr = -1.001f * gsr_log2f(255.f * q.w) - 0.01f;
   const float k = -0.5f * q.y / q.x;
   const float lo0 = tile_x0 - c.x, hi0 = lo0 + 7.f, lo1 = lo0 + 8.f, hi1 = lo0 + 15.f;
   const float dy0 = tile_y0 - c.y;
@@ -161,8 +161,8 @@ __device__ __forceinline__ unsigned block_mask_16(const float4 c, const float4 q
     }
     const float row0 = any_shape ? 1.f : pm0 - thr, row1 = any_shape ? 1.f : pm1 - thr;  // !(pm < thr)
     const float m1 = fminf(fminf(box_y, box_r), row1), m0 = fminf(fminf(box_y, box_l), row0);
-    reject = (reject << 1) | (__float_as_uint(m1) >> 31);  // bit 2 g + 1
-    reject = (reject << 1) | (__float_as_uint(m0) >> 31);  // bit 2 g
+    reject = (reject << 1) | (gsr_float_as_uint(m1) >> 31);  // bit 2 g + 1
+    reject = (reject << 1) | (gsr_float_as_uint(m0) >> 31);  // bit 2 g
   }
   return weird ? 0xffu : (~reject & 0xffu);
 }

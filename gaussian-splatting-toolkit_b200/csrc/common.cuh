@@ -1,8 +1,10 @@
 // common.cuh — shared host/device helpers of libgsr_b200 (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "../../include/gsr_b200.h"
 
@@ -60,9 +62,46 @@ struct TraceScope {
 
 static inline unsigned cdiv(unsigned a, unsigned b) { return (a + b - 1) / b; }
 
+// The geometric helpers below (tile boxes, the culling ellipse, the warp-block masks) are __host__ __device__ so that
+// tests/test_cull_host.py can run the SAME source on the CPU against a brute-force FP64 evaluation of the reference's
+// per-pixel alpha test; the device code is unchanged (fast-math intrinsics on the device, libm on the host).
+#define GSR_HD __host__ __device__ __forceinline__
+GSR_HD float gsr_logf(float x) {
+#ifdef __CUDA_ARCH__
+  return __logf(x);
+#else
+  return logf(x);
+#endif
+}
+GSR_HD float gsr_log2f(float x) {
+#ifdef __CUDA_ARCH__
+  return __log2f(x);
+#else
+  return log2f(x);
+#endif
+}
+GSR_HD unsigned gsr_float_as_uint(float x) {
+#ifdef __CUDA_ARCH__
+  return __float_as_uint(x);
+#else
+  unsigned u;
+  memcpy(&u, &x, sizeof(u));
+  return u;
+#endif
+}
+GSR_HD float gsr_int_as_float(int i) {
+#ifdef __CUDA_ARCH__
+  return __int_as_float(i);
+#else
+  float f;
+  memcpy(&f, &i, sizeof(f));
+  return f;
+#endif
+}
+
 // tile bbox of a projected Gaussian: reference helpers.cuh:11-34 ((int) truncates toward zero,
 // clamp to [0, tiles]).
-__device__ __forceinline__ void tile_bbox(float cx, float cy, float radius, int tiles_x, int tiles_y,
+GSR_HD void tile_bbox(float cx, float cy, float radius, int tiles_x, int tiles_y,
                                           int block_width, int &x0, int &y0, int &x1, int &y1) {
   const float bw = (float)block_width;
   const float tcx = cx / bw, tcy = cy / bw, tr = radius / bw;

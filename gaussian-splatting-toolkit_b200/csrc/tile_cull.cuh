@@ -25,7 +25,7 @@ struct CullEllipse {
   bool empty;       // opacity < 1/255: no pixel can ever pass the alpha test
 };
 
-__device__ __forceinline__ CullEllipse make_cull_ellipse(float a, float b, float c, float opac, float extent = 0.f) {
+GSR_HD CullEllipse make_cull_ellipse(float a, float b, float c, float opac, float extent = 0.f) {
   CullEllipse e;
   e.a = a;
   e.b = b;
@@ -33,7 +33,7 @@ __device__ __forceinline__ CullEllipse make_cull_ellipse(float a, float b, float
   e.never_cull = !(a > 0.f && c > 0.f && e.det > 0.f) || !(opac == opac);
   e.empty = !e.never_cull && (255.f * opac < 0.999f);
   // 8 ulp (2^-23 each) of the sum of the absolute terms at distance `extent` in both coordinates
-  e.thr = 2.f * __logf(255.f * opac) * 1.001f + 1e-3f + 9.6e-7f * (a + 2.f * fabsf(b) + c) * extent * extent;
+  e.thr = 2.f * gsr_logf(255.f * opac) * 1.001f + 1e-3f + 9.6e-7f * (a + 2.f * fabsf(b) + c) * extent * extent;
   e.inv_a = 1.f / a;
   const float inv_det = 1.f / e.det;
   e.ext_y = sqrtf(a * e.thr * inv_det);
@@ -45,7 +45,7 @@ __device__ __forceinline__ CullEllipse make_cull_ellipse(float a, float b, float
 // Tiles [j0, j1) of tile row `i` (clipped to the bounding box [x0, x1)) that the ellipse can reach; j0 >= j1 if none.
 // inv_bw = 1.f / (float)block_width, hoisted out of the caller's row loop (the compiler does not hoist the MUFU.RCP of
 // the fast-math division out of a divergent loop)
-__device__ __forceinline__ void cull_row_range(const CullEllipse &e, float mx, float my, int i, int x0, int x1,
+GSR_HD void cull_row_range(const CullEllipse &e, float mx, float my, int i, int x0, int x1,
                                                int block_width, float inv_bw, int &j0, int &j1) {
   if (e.never_cull) {
     j0 = x0;
@@ -70,7 +70,7 @@ __device__ __forceinline__ void cull_row_range(const CullEllipse &e, float mx, f
   if (j1 < j0) j1 = j0;
 }
 
-__device__ __forceinline__ void cull_row_range(const CullEllipse &e, float mx, float my, int i, int x0, int x1,
+GSR_HD void cull_row_range(const CullEllipse &e, float mx, float my, int i, int x0, int x1,
                                                int block_width, int &j0, int &j1) {
   cull_row_range(e, mx, my, i, x0, x1, block_width, 1.f / (float)block_width, j0, j1);
 }
