@@ -162,3 +162,21 @@ def test_nvtx_tracing_switch_is_harmless_without_a_tool():
     )
     out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, GSR_NVTX="1"), capture_output=True, text=True)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr
+
+
+def test_mask_bit_gather_multiply_is_exact():
+    """compact_from_masks (csrc/blend_common.cuh) collects bit `warp` of eight mask bytes with two multiplies:
+    ((x >> warp) & 0x01010101) * 0x01020408 puts the four byte flags into bits 24..27 without carries."""
+    import itertools
+
+    for warp in range(8):
+        for flags in itertools.product((0, 1), repeat=4):
+            for noise in (0x00, 0xFF, 0xA5):  # the other bits of the bytes must not matter
+                word = 0
+                for i, f in enumerate(flags):
+                    byte = (noise & ~(1 << warp) & 0xFF) | (f << warp)
+                    word |= byte << (8 * i)
+                lo = (word >> warp) & 0x01010101
+                got = ((lo * 0x01020408) & 0xFFFFFFFF) >> 24
+                assert got & 0xF == sum(f << i for i, f in enumerate(flags)), (warp, flags, noise)
+                assert got >> 4 == 0
