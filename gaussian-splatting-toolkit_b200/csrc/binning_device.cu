@@ -56,54 +56,6 @@ inline int num_sms() {
 }
 
 constexpr int BD_THREADS = 256;
-typedef unsigned long long u64;
-
-// The tiles kept for a Gaussian (exact tile culling, tile_cull.cuh) inside its bounding box [x0, x1) x [y0, y1): calls
-// f(tile_id) for each and returns the count.  For boxes of at most 64 tiles the decision is also returned as a mask
-// (bit k = k-th tile of the box, row-major), which the fill pass walks instead of evaluating the ellipse again.
-template <typename F>
-__device__ __forceinline__ int cull_tiles(float2 ctr, int r, float ca, float cb, float cc, float opac, int x0, int y0, int x1,
-                                          int y1, int tiles_x, int block_width, u64 &mask, F f) {
-  const int bw_tiles = x1 - x0, area = bw_tiles * (y1 - y0);
-  mask = 0ull;
-  const CullEllipse e = make_cull_ellipse(ca, cb, cc, opac, (float)(r + block_width));
-  if (e.empty) return 0;
-  int count = 0;
-  u64 mk = 0ull;
-  const float inv_bw = 1.f / (float)block_width;
-  for (int i = y0; i < y1; ++i) {
-    int j0, j1;
-    cull_row_range(e, ctr.x, ctr.y, i, x0, x1, block_width, inv_bw, j0, j1);
-    for (int j = j0; j < j1; ++j) f(i * tiles_x + j);
-    const int cnt = j1 - j0;
-    if (cnt > 0 && area <= 64) mk |= ((cnt >= 64) ? ~0ull : ((1ull << cnt) - 1ull)) << ((i - y0) * bw_tiles + (j0 - x0));
-    count += cnt;
-  }
-  mask = mk;
-  return count;
-}
-
-// Walk of a cached mask: tile of bit k = (y0 * tiles_x + x0) + k + (k / bw_tiles) * (tiles_x - bw_tiles).
-// k / bw_tiles without an integer division per pair (25 of the 50 instructions of the loop it replaces):
-// (k * magic) >> 16 is exact for k < 64 and every divisor up to 64 for any magic in [ceil(65536 / d), ceil(65536 / d) + 16]
-// — the approximate reciprocal of fast-math cannot leave that interval
-// (tests/test_abi.py::test_tile_mask_division_magic_is_exact).
-template <typename F>
-__device__ __forceinline__ void walk_tile_mask(u64 mask, int x0, int y0, int bw_tiles, int tiles_x, F f) {
-  const unsigned magic = (unsigned)(65536.f / (float)bw_tiles) + 1u;
-  const int base = y0 * tiles_x + x0, skip = tiles_x - bw_tiles;
-#pragma unroll 1
-  for (int h = 0; h < 2; ++h) {
-    unsigned w = h ? (unsigned)(mask >> 32) : (unsigned)mask;
-    const int k0 = 32 * h;
-    while (w) {
-      const unsigned low = w & (0u - w);
-      const int k = k0 + 31 - __clz((int)low);
-      w ^= low;
-      f(base + k + (int)(((unsigned)k * magic) >> 16) * skip);
-    }
-  }
-}
 
 // count pass of one Gaussian
 template <typename F>

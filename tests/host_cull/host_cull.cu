@@ -17,25 +17,32 @@ unsigned host_block_mask_16(float x, float y, float a, float b, float c, float o
   return block_mask_16(r0, r1, tile_x0, tile_y0);
 }
 
-// the tiles the binning keeps for one Gaussian (cull_tiles of binning_device.cu: bounding box, ellipse, one range per
-// tile row); returns the count, writes at most `cap` tile ids
+// the tiles the binning keeps for one Gaussian — the count pass's own function (cull_tiles, csrc/tile_cull.cuh): returns the
+// count, writes at most `cap` tile ids in visiting order and the cached 64-bit mask (0 for boxes of more than 64 tiles)
 int host_kept_tiles(float x, float y, int radius, float a, float b, float c, float opac, int tiles_x, int tiles_y,
-                    int block_width, int *out, int cap) {
+                    int block_width, int *out, int cap, unsigned long long *mask_out) {
   int x0, y0, x1, y1;
   tile_bbox(x, y, (float)radius, tiles_x, tiles_y, block_width, x0, y0, x1, y1);
+  if (mask_out) *mask_out = 0ull;
   if ((x1 - x0) * (y1 - y0) <= 0) return 0;
-  const CullEllipse e = make_cull_ellipse(a, b, c, opac, (float)(radius + block_width));
-  if (e.empty) return 0;
   int n = 0;
-  const float inv_bw = 1.f / (float)block_width;
-  for (int i = y0; i < y1; ++i) {
-    int j0, j1;
-    cull_row_range(e, x, y, i, x0, x1, block_width, inv_bw, j0, j1);
-    for (int j = j0; j < j1; ++j) {
-      if (n < cap) out[n] = i * tiles_x + j;
-      ++n;
-    }
-  }
+  u64 mask = 0ull;
+  const int count = cull_tiles(make_float2(x, y), radius, a, b, c, opac, x0, y0, x1, y1, tiles_x, block_width, mask,
+                               [&](int tile) {
+                                 if (n < cap) out[n] = tile;
+                                 ++n;
+                               });
+  if (mask_out) *mask_out = mask;
+  return count == n ? n : -1;
+}
+
+// the fill pass's walk of a cached mask (walk_tile_mask, csrc/tile_cull.cuh)
+int host_walk_mask(unsigned long long mask, int x0, int y0, int bw_tiles, int tiles_x, int *out, int cap) {
+  int n = 0;
+  walk_tile_mask((u64)mask, x0, y0, bw_tiles, tiles_x, [&](int tile) {
+    if (n < cap) out[n] = tile;
+    ++n;
+  });
   return n;
 }
 

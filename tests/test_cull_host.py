@@ -7,7 +7,9 @@ for the host (built here with nvcc, no GPU needed).  For seeded Gaussians, inclu
 
     sigma = 0.5 (a dx^2 + c dy^2) + b dx dy >= 0   and   alpha = min(0.999, o exp(-sigma)) >= 1/255     (forward.cu:355-363)
 
-evaluated in FP32 in the reference's expression order, must be kept.  (On the GPU the same property is checked end to end
+evaluated in FP32 in the reference's expression order, must be kept.  The same run checks that the binning's two passes
+agree: walking the cached 64-bit tile mask (fill pass, division-free `walk_tile_mask`) visits exactly the tiles `cull_tiles`
+counted (count pass), in the same order.  (On the GPU the same property is checked end to end
 by test_tight_binning_is_exact / test_block_masks_match_per_warp_tests: bitwise image, superset of pairs.)"""
 import ctypes
 import os
@@ -35,8 +37,11 @@ def lib(tmp_path_factory):
     fl, it = ctypes.c_float, ctypes.c_int
     L.host_block_mask_16.argtypes = [fl] * 8
     L.host_block_mask_16.restype = ctypes.c_uint
-    L.host_kept_tiles.argtypes = [fl, fl, it, fl, fl, fl, fl, it, it, it, ctypes.POINTER(it), it]
+    L.host_kept_tiles.argtypes = [fl, fl, it, fl, fl, fl, fl, it, it, it, ctypes.POINTER(it), it,
+                                  ctypes.POINTER(ctypes.c_ulonglong)]
     L.host_kept_tiles.restype = it
+    L.host_walk_mask.argtypes = [ctypes.c_ulonglong, it, it, it, it, ctypes.POINTER(it), it]
+    L.host_walk_mask.restype = it
     L.host_tile_bbox.argtypes = [fl, fl, it, it, it, it, ctypes.POINTER(it)]
     return L
 
@@ -107,15 +112,28 @@ def test_tile_culling_is_conservative(lib):
     ctr = ctr * f32(W / min(W, H))
     py, px = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
     buf = (ctypes.c_int * (tiles_x * tiles_y))()
+    buf2 = (ctypes.c_int * (tiles_x * tiles_y))()
     box = (ctypes.c_int * 4)()
-    kept = needed = in_box = 0
+    kept = needed = in_box = walked = big_boxes = 0
     for i in range(len(opac)):
         x, y, r = ctr[i, 0], ctr[i, 1], int(radius[i])
-        n = lib.host_kept_tiles(x, y, r, a[i], b[i], c[i], opac[i], tiles_x, tiles_y, bw, buf, len(buf))
-        tiles = set(buf[:n])
+        mask = ctypes.c_ulonglong(0)
+        n = lib.host_kept_tiles(x, y, r, a[i], b[i], c[i], opac[i], tiles_x, tiles_y, bw, buf, len(buf), ctypes.byref(mask))
+        assert n >= 0  # the returned count equals the number of visits
+        order = list(buf[:n])
+        tiles = set(order)
         assert len(tiles) == n
         lib.host_tile_bbox(x, y, r, tiles_x, tiles_y, bw, box)
         x0, y0, x1, y1 = box
+        # count pass and fill pass must agree: walking the cached mask visits exactly the tiles the count pass counted, in
+        # the same order (a disagreement would write keys outside the tile's segment); boxes of > 64 tiles cache nothing
+        if (x1 - x0) * (y1 - y0) <= 64:
+            m = lib.host_walk_mask(mask.value, x0, y0, x1 - x0, tiles_x, buf2, len(buf2))
+            assert m == n == bin(mask.value).count("1") and list(buf2[:m]) == order, (i, hex(mask.value))
+            walked += 1
+        else:
+            assert mask.value == 0
+            big_boxes += 1
         in_box += max(0, x1 - x0) * max(0, y1 - y0)
         hit = _contributes((x, y), a[i], b[i], c[i], opac[i], px, py)
         per_tile = hit.reshape(tiles_y, bw, tiles_x, bw).any(axis=(1, 3))
@@ -129,3 +147,4 @@ def test_tile_culling_is_conservative(lib):
     assert needed > 3000
     print(f"[tile culling] bounding boxes {in_box} pairs, kept {kept}, contributing {needed}")
     assert kept <= 1.25 * needed and kept < in_box
+    assert walked > 1500 and big_boxes > 20  # both the cached-mask and the re-evaluation path were exercised
