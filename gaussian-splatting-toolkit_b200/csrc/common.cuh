@@ -112,7 +112,7 @@ GSR_HD void tile_bbox(float cx, float cy, float radius, int tiles_x, int tiles_y
 }
 
 // cov2d -> conic + 3-sigma radius: reference helpers.cuh:36-59
-__device__ __forceinline__ bool cov2d_to_conic_radius(float cxx, float cxy, float cyy, float &ca,
+GSR_HD bool cov2d_to_conic_radius(float cxx, float cxy, float cyy, float &ca,
                                                       float &cb, float &cc, float &radius) {
   float det = cxx * cyy - cxy * cxy;
   if (det == 0.f) return false;
@@ -128,7 +128,7 @@ __device__ __forceinline__ bool cov2d_to_conic_radius(float cxx, float cxy, floa
 }
 
 // (w,x,y,z) quaternion -> row-major rotation matrix (normalises inside): reference helpers.cuh:144-159
-__device__ __forceinline__ void quat_to_rotmat(float qw, float qx, float qy, float qz, float R[9]) {
+GSR_HD void quat_to_rotmat(float qw, float qx, float qy, float qz, float R[9]) {
   // summation order of the reference: its float4 holds (w,x,y,z) in the fields (x,y,z,w) and it adds w*w + x*x + y*y + z*z
   // over the FIELDS, i.e. z^2 first (helpers.cuh:146-147)
   float s = rsqrtf(qz * qz + qw * qw + qx * qx + qy * qy);
@@ -145,7 +145,7 @@ __device__ __forceinline__ void quat_to_rotmat(float qw, float qx, float qy, flo
 }
 
 // C = A * B, 3x3 row-major, fully unrolled
-__device__ __forceinline__ void mat3_mul(const float A[9], const float B[9], float C[9]) {
+GSR_HD void mat3_mul(const float A[9], const float B[9], float C[9]) {
 #pragma unroll
   for (int i = 0; i < 3; ++i)
 #pragma unroll

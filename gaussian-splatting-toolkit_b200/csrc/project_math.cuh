@@ -15,7 +15,7 @@ struct ProjFwd {
 };
 
 // s0,s1,s2 = glob_scale * (activated) scales; V = viewmat (12 floats), PM = projmat (16 floats)
-__device__ __forceinline__ ProjFwd project_one(float px, float py, float pz, float s0, float s1, float s2, float qw,
+GSR_HD ProjFwd project_one(float px, float py, float pz, float s0, float s1, float s2, float qw,
                                                float qx, float qy, float qz, const float *V, const float *PM, float fx,
                                                float fy, float cx, float cy, float tan_fovx, float tan_fovy, int img_w,
                                                int img_h, int tiles_x, int tiles_y, int block_width,
@@ -109,7 +109,7 @@ struct ProjBwd {
 };
 
 // sc0..2 = (activated) scales before glob_scale; c3 = cov3d[6]; (ca,cb,cc) = conic; outputs are zero when !visible
-__device__ __forceinline__ ProjBwd project_one_vjp(bool visible, float px, float py, float pz, float sc0, float sc1,
+GSR_HD ProjBwd project_one_vjp(bool visible, float px, float py, float pz, float sc0, float sc1,
                                                    float sc2, float glob_scale, float qw, float qx, float qy, float qz,
                                                    const float *V, const float *PM, float fx, float fy, int img_w,
                                                    int img_h, const float *c3, float ca, float cb, float cc, float comp,

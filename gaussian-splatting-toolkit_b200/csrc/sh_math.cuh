@@ -7,7 +7,7 @@
 namespace gsr {
 
 // Y[0..(deg+1)^2) for direction (dx,dy,dz) (normalised here, as sh.cuh:44-48 does)
-__device__ __forceinline__ void sh_basis_all(int deg, float dx, float dy, float dz, float *Y) {
+GSR_HD void sh_basis_all(int deg, float dx, float dy, float dz, float *Y) {
   Y[0] = 0.28209479177387814f;
   if (deg < 1) return;
   const float C1 = 0.4886025119029199f;
